@@ -1,0 +1,71 @@
+"""Masked hyper-network (MADE) restated from zuko's published description."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class MaskedLinear(nn.Linear):
+    """Linear layer whose weight is multiplied elementwise by a fixed boolean adjacency."""
+
+    def __init__(self, adjacency: torch.Tensor, bias: bool = True):
+        super().__init__(adjacency.shape[1], adjacency.shape[0], bias)
+        self.register_buffer("mask", adjacency.to(torch.bool))
+
+    def forward(self, x):
+        return F.linear(x, self.mask * self.weight, self.bias)
+
+
+class Residual(nn.Module):
+    """y = x + f(x)."""
+
+    def __init__(self, f):
+        super().__init__()
+        self.f = f
+
+    def forward(self, x):
+        return x + self.f(x)
+
+
+class MaskedMLP(nn.Sequential):
+    """MLP whose Jacobian sparsity follows ``adjacency`` (out_features x in_features).
+
+    Hidden unit h of every hidden layer takes the dependency pattern
+    ``reachable[h % len(reachable)]`` where ``reachable`` are the unique adjacency rows
+    (lexicographically sorted) that have at least one dependency.  Layer i>0 is masked by
+    the precedence relation "deps(in) is a subset of deps(out)".
+
+    STRUCTURAL GUESS (isolated here): with ``residual=True`` every interior hidden->hidden
+    layer with a square mask is wrapped as ``h + MaskedLinear(h)``; the activation follows
+    the sum.  Layer stack for 3 hidden layers: L0, act, Res(L1), act, Res(L2), act, L3.
+    """
+
+    def __init__(self, adjacency, hidden_features=(64, 64), activation=None, residual=False):
+        out_features, in_features = adjacency.shape
+        if activation is None:
+            activation = nn.ReLU
+        adjacency, inverse = torch.unique(adjacency, dim=0, return_inverse=True)
+        a = adjacency.int()
+        precedence = a @ a.t() == a.sum(dim=-1)
+
+        layers = []
+        indices = None
+        n_hidden = len(hidden_features)
+        for i, features in enumerate((*hidden_features, out_features)):
+            mask = precedence[:, indices] if i > 0 else adjacency
+            if (~mask).all():
+                raise ValueError("The adjacency matrix leads to a null Jacobian.")
+            if i < n_hidden:
+                reachable = mask.sum(dim=-1).nonzero().squeeze(dim=-1)
+                indices = reachable[torch.arange(features) % len(reachable)]
+                mask = mask[indices]
+            else:
+                mask = mask[inverse]
+            layer = MaskedLinear(mask)
+            if residual and 0 < i < n_hidden and mask.shape[0] == mask.shape[1]:
+                layer = Residual(layer)
+            layers.append(layer)
+            if i < n_hidden:
+                layers.append(activation())
+        super().__init__(*layers)
+        self.in_features = in_features
+        self.out_features = out_features
