@@ -1,0 +1,101 @@
+"""ctypes binding of libpmc_b200.so (include/pmc_b200.h).  No CPU fallback: every compute entry
+point raises if the library or a CUDA device is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _build
+
+_P, _I32, _I64, _F64, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_uint64
+
+
+class PmcScaler(C.Structure):
+    _fields_ = [("kind", _P), ("bc", _P), ("low", _P), ("high", _P), ("mu", _P), ("sigma", _P),
+                ("log_sigma_sum", _F64), ("logit", _I32), ("scale", _I32)]
+
+
+# name -> (restype, argtypes); mirrors include/pmc_b200.h one to one
+SIGNATURES = {
+    "pmc_last_error": (C.c_char_p, []),
+    "pmc_version": (C.c_int, []),
+    "pmc_device_info": (C.c_int, [_P, _P, _P]),
+    "pmc_flow_pack": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "pmc_flow_sweep": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_flow_base_logprob": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "pmc_tpcn_propose": (C.c_int, [_I32, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_rwm_propose": (C.c_int, [_I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_scaler_inverse": (C.c_int, [_I32, _P, C.POINTER(PmcScaler), _P, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_scaler_forward": (C.c_int, [_P, C.POINTER(PmcScaler), _P, _I64, _I32, _P]),
+    "pmc_apply_bc": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_mh_partials_size": (_I64, [_I64, _I32]),
+    "pmc_mh_accept_update": (C.c_int, [_I32, _F64, _F64] + [_P] * 20 + [_I64, _I32, _P]),
+    "pmc_mcmc_finalize": (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _I32, _I64, _I32, _P]),
+    "pmc_rng_fill": (C.c_int, [_U64, _U64, _I64, _F64, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_ps_append": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _P]),
+    "pmc_ps_scratch_size": (_I64, [_I64]),
+    "pmc_ps_reduce": (C.c_int, [_P, _P, _F64, _I32, _I64, _I64, _P, _P, _P]),
+    "pmc_ps_weights": (C.c_int, [_P, _P, _F64, _I32, _I64, _P, _P, _P, _P]),
+    "pmc_weight_stats": (C.c_int, [_P, _I64, _I64, _P, _P, _P]),
+    "pmc_cumsum_f64": (C.c_int, [_P, _P, _I64, _P]),
+    "pmc_resample_multinomial": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
+    "pmc_resample_systematic": (C.c_int, [_P, _F64, _P, _I64, _I64, _P]),
+    "pmc_gather_rows_f64": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "pmc_trim_threshold": (C.c_int, [_P, _I64, _F64, _I32, _P, _P, _P]),
+    "pmc_trim_scratch_size": (_I64, [_I64]),
+    "pmc_lse": (C.c_int, [_P, _I64, _P, _P, _P]),
+    "pmc_lse_bootstrap": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
+    "pmc_loglike": (C.c_int, [_I32, _P, _P, _P, _F64, _F64, _P, _I64, _I32, _P]),
+    "pmc_logprior": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIBPATH
+
+
+def load():
+    """dlopen the in-tree library (building it first if nvcc is around and it is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIBPATH
+    if not os.path.exists(path):
+        _build.build()
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing: loud by design
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pocomc_b200: no CUDA device -- the hot path is CUDA-only (sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(code: int, what: str = ""):
+    if code != 0:
+        msg = load().pmc_last_error()
+        raise RuntimeError(f"libpmc_b200 {what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point on the current torch stream; raise on a non-zero code."""
+    require_cuda()
+    lib = load()
+    check(getattr(lib, name)(*args, stream_ptr()), name)

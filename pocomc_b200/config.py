@@ -1,0 +1,34 @@
+"""Run-time switches that have no counterpart in the reference.
+
+rng_mode
+    ``"host"`` (default): every random number of the MCMC step is drawn on the host from the
+    legacy global ``np.random`` stream in the reference's order and uploaded --
+    bit-faithful to the reference for a given ``random_state``.
+    ``"device"``: Philox4x32-10 counters on the GPU keyed by (seed, step, global particle id);
+    statistically equivalent, no per-step noise upload, independent of the number of GPUs.
+mean_mode
+    1 (default with rng_mode "host") reproduces ``np.mean(theta_f32, axis=0)``'s sequential f32
+    accumulation exactly (mcmc.py:156); 0 uses deterministic f64 block partial sums.
+device_callbacks
+    False (default): prior and likelihood are host black boxes like the reference's (x' crosses
+    PCIe every MCMC step).  True: a likelihood object exposing ``device(x, finite, out)`` and a
+    ``Prior`` of frozen scipy ``norm`` / ``uniform`` factors are evaluated on the GPU instead.
+"""
+import os
+
+rng_mode = os.environ.get("PMC_B200_RNG", "host")
+mean_mode = None  # None -> 1 for "host", 0 for "device"
+device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
+
+
+def set_rng_mode(mode: str):
+    global rng_mode
+    if mode not in ("host", "device"):
+        raise ValueError("rng mode must be 'host' or 'device'")
+    rng_mode = mode
+
+
+def resolved_mean_mode() -> int:
+    if mean_mode is not None:
+        return int(mean_mode)
+    return 1 if rng_mode == "host" else 0

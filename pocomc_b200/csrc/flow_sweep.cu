@@ -1,0 +1,337 @@
+// Degree-ordered MADE sweep: Flow.forward / Flow.inverse for zuko MAF (affine) and NSF (RQS).
+//
+// Reference path: pocomc/flow.py:99-132 -> zuko transform.call_and_ladj / .inv.call_and_ladj
+// (1 hyper-network pass forward, D+1 passes inverse).  Here one sweep in order of autoregressive
+// degree computes every hidden unit and every output exactly once; the packed slab
+// layout is built by pocomc_b200/made_layout.py.
+//
+// Mapping: a warp owns PW = 32/LPP particles; lane = q*PW + p (q = slice of the reduction, p =
+// particle).  Activations live in shared memory as [unit][PW] so lane l touches word 32*j + l
+// (conflict free); the weights of one 4-unit chunk are one 16-byte read-only load shared by the
+// PW lanes of a slice.  fp32 FMA throughout -- the reference flow is fp32 (tools.py:292).
+#include "common.cuh"
+#include <algorithm>
+
+namespace pmc {
+
+// meta header slots -- keep in sync with made_layout.py
+enum { M_D = 0, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE, M_HP, M_MAXCH,
+       M_OFF_GSTART, M_OFF_NCHUNK, M_OFF_SLOT, M_OFF_W0, M_OFF_WH, M_OFF_WO, M_OFF_B0, M_OFF_BH,
+       M_OFF_BO, M_RAW_TSTRIDE, M_BINS };
+
+constexpr float LOG_SLOPE = -6.90775527898213705205f;  // log(1e-3)
+
+__device__ __forceinline__ float softclip(float a, float ls) { return a / (1.0f + fabsf(a / ls)); }
+
+// ---- univariate transforms -----------------------------------------------------------------
+// zuko MonotonicAffineTransform: y = x*exp(ls) + shift, ls soft-clipped.
+struct Affine {
+  static constexpr int TOTAL = 2, TP = 4;
+  __device__ static __forceinline__ float apply(const float* phi, float v, bool inverse, float& ladj) {
+    const float ls = softclip(phi[1], LOG_SLOPE);
+    ladj = ls;
+    const float sc = expf(ls);
+    return inverse ? (v - phi[0]) / sc : fmaf(v, sc, phi[0]);
+  }
+};
+
+// zuko MonotonicRQSTransform, bins = 8, bound = 5.
+struct Rqs {
+  static constexpr int BINS = 8, TOTAL = 23, TP = 24;
+  __device__ static __forceinline__ void knots(const float* a, float* out /*BINS+1*/) {
+    float c[BINS], mx = -INFINITY, sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < BINS; ++i) { c[i] = softclip(a[i], 0.5f * LOG_SLOPE); mx = fmaxf(mx, c[i]); }
+#pragma unroll
+    for (int i = 0; i < BINS; ++i) { c[i] = expf(c[i] - mx); sum += c[i]; }
+    double acc = 0.0;  // torch's CPU cumsum accumulates float inputs in double
+    out[0] = -5.0f;
+#pragma unroll
+    for (int i = 0; i < BINS; ++i) {
+      acc += (double)(c[i] / sum);
+      out[i + 1] = 5.0f * (2.0f * (float)acc - 1.0f);
+    }
+  }
+  __device__ static __forceinline__ float apply(const float* phi, float v, bool inverse, float& ladj) {
+    float hx[BINS + 1], hy[BINS + 1], dv[BINS + 1];
+    knots(phi, hx);
+    knots(phi + BINS, hy);
+    dv[0] = 1.0f; dv[BINS] = 1.0f;
+#pragma unroll
+    for (int i = 0; i < BINS - 1; ++i) dv[i + 1] = expf(softclip(phi[2 * BINS + i], LOG_SLOPE));
+    int cnt = 0;  // searchsorted(left) = #knots < v
+#pragma unroll
+    for (int i = 0; i <= BINS; ++i) cnt += ((inverse ? hy[i] : hx[i]) < v) ? 1 : 0;
+    const int k = cnt - 1;
+    const bool in = (k >= 0) && (k < BINS);
+    const int kk = ((k % BINS) + BINS) % BINS;
+    float x0 = 0, x1 = 0, y0 = 0, y1 = 0, d0 = 0, d1 = 0;
+#pragma unroll
+    for (int i = 0; i < BINS; ++i)
+      if (i == kk) { x0 = hx[i]; x1 = hx[i + 1]; y0 = hy[i]; y1 = hy[i + 1]; d0 = dv[i]; d1 = dv[i + 1]; }
+    const float s = (y1 - y0) / (x1 - x0);
+    const float t2 = d0 + d1 - 2.0f * s;
+    float x = v, res = v;
+    if (inverse) {
+      const float y_ = in ? (v - y0) : 0.0f;
+      const float a = (y1 - y0) * (s - d0) + y_ * t2;
+      const float b = (y1 - y0) * d0 - y_ * t2;
+      const float c = -s * y_;
+      const float z = 2.0f * c / (-b - sqrtf(b * b - 4.0f * a * c));
+      x = in ? (x0 + z * (x1 - x0)) : v;
+      res = x;
+    }
+    const float z = in ? (x - x0) / (x1 - x0) : 0.0f;
+    const float den = s + t2 * z * (1.0f - z);
+    const float jac = s * s * (2.0f * s * z * (1.0f - z) + d0 * (1.0f - z) * (1.0f - z) + d1 * z * z) / (den * den);
+    ladj = in ? logf(jac) : 0.0f;
+    if (!inverse) res = in ? (y0 + (y1 - y0) * (s * z * z + d0 * z * (1.0f - z)) / den) : v;
+    return res;
+  }
+};
+
+// ---- partial dot products --------------------------------------------------------------------
+// acc[0..3] = sum_{s in slice q} slab[s][col..col+3] * act[s][p], then butterfly over the LPP slices.
+template <int LPP>
+__device__ __forceinline__ void dot4(const float* __restrict__ slab, int wd, int col, int nrows,
+                                     const float* act, int p, int q, float (&acc)[4]) {
+  constexpr int PW = 32 / LPP;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  const float* wp = slab + (size_t)q * wd + col;
+  const float* ap = act + q * PW + p;
+  const size_t wstep = (size_t)LPP * wd;
+  int s = q;
+  for (; s + LPP < nrows; s += 2 * LPP) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + wstep));
+    const float x0 = ap[0], x1 = ap[32];
+    a0 = fmaf(w0.x, x0, a0); a1 = fmaf(w0.y, x0, a1); a2 = fmaf(w0.z, x0, a2); a3 = fmaf(w0.w, x0, a3);
+    b0 = fmaf(w1.x, x1, b0); b1 = fmaf(w1.y, x1, b1); b2 = fmaf(w1.z, x1, b2); b3 = fmaf(w1.w, x1, b3);
+    wp += 2 * wstep; ap += 64;
+  }
+  if (s < nrows) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+    const float x0 = ap[0];
+    a0 = fmaf(w0.x, x0, a0); a1 = fmaf(w0.y, x0, a1); a2 = fmaf(w0.z, x0, a2); a3 = fmaf(w0.w, x0, a3);
+  }
+  acc[0] = a0 + b0; acc[1] = a1 + b1; acc[2] = a2 + b2; acc[3] = a3 + b3;
+#pragma unroll
+  for (int o = PW; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+  }
+}
+
+template <class UNI, int LPP>
+__global__ void __launch_bounds__(128)
+made_sweep_kernel(const float* __restrict__ packed, const int* __restrict__ meta, int meta_len,
+                  const float* __restrict__ in, float* __restrict__ out, float* __restrict__ ladj_out,
+                  long long n, int inverse) {
+  constexpr int PW = 32 / LPP;
+  constexpr int TP = UNI::TP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* sm = reinterpret_cast<int*>(smem_raw);
+  for (int i = threadIdx.x; i < meta_len; i += blockDim.x) sm[i] = meta[i];
+  __syncthreads();
+  const int D = sm[M_D], H = sm[M_H], L = sm[M_L], T = sm[M_T], ng = sm[M_NG];
+  const int tstride = sm[M_TSTRIDE];
+  const int* gstart = sm + sm[M_OFF_GSTART];
+  const int* nchunk = sm + sm[M_OFF_NCHUNK];
+  const int* slot = sm + sm[M_OFF_SLOT];
+  const int* off_w0 = sm + sm[M_OFF_W0];
+  const int* off_wh = sm + sm[M_OFF_WH];
+  const int* off_wo = sm + sm[M_OFF_WO];
+  const int* off_bh = sm + sm[M_OFF_BH];
+  const int off_b0 = sm[M_OFF_B0], off_bo = sm[M_OFF_BO];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = lane % PW, q = lane / PW;
+  const int per_warp = (2 * D + L * H) * PW;
+  float* base = reinterpret_cast<float*>(smem_raw + (((size_t)meta_len * 4 + 15) & ~(size_t)15)) + (size_t)warp * per_warp;
+  float* cur = base;            // [D][PW] running vector (feature order)
+  float* xs = base + D * PW;    // [D][PW] data-side values by ORDER position (MLP inputs)
+  float* act = xs + D * PW;     // [L][H][PW]
+
+  const long long n_tiles = (n + PW - 1) / PW;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += warps_total) {
+    const long long row0 = tile * PW;
+    const int rows = (int)min((long long)PW, n - row0);
+    // stage the PW input rows (contiguous in global) transposed into cur[feat][p]
+    for (int i = lane; i < PW * D; i += 32) {
+      const int r = i / D, c = i - r * D;
+      cur[c * PW + r] = (r < rows) ? in[row0 * D + i] : 0.0f;
+    }
+    __syncwarp();
+    float ladj = 0.0f;
+    for (int tt = 0; tt < T; ++tt) {
+      const int t = inverse ? (T - 1 - tt) : tt;
+      const float* P = packed + (size_t)t * tstride;
+      const bool rev = (t & 1);
+      for (int k = 0; k < D; ++k) {
+        const int feat = rev ? (D - 1 - k) : k;
+        const int Ek = gstart[k];  // sorted units with degree <= k
+        float phi[TP];
+        const float* slab = P + off_wo[k];
+        const float* bo = P + off_bo + k * TP;
+#pragma unroll
+        for (int c = 0; c < TP / 4; ++c) {
+          float acc[4];
+          dot4<LPP>(slab, TP, 4 * c, Ek, act + (size_t)(L - 1) * H * PW, p, q, acc);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bo + 4 * c));
+          phi[4 * c + 0] = acc[0] + b.x; phi[4 * c + 1] = acc[1] + b.y;
+          phi[4 * c + 2] = acc[2] + b.z; phi[4 * c + 3] = acc[3] + b.w;
+        }
+        const float v = cur[feat * PW + p];
+        float l;
+        const float res = UNI::apply(phi, v, inverse != 0, l);
+        ladj = inverse ? (ladj - l) : (ladj + l);
+        __syncwarp();  // every slice has read cur[feat] before it is overwritten
+        if (q == 0) {
+          xs[k * PW + p] = inverse ? res : v;
+          cur[feat * PW + p] = res;
+        }
+        __syncwarp();
+        const int g = k + 1;
+        if (g > ng) continue;
+        const int gs = gstart[g - 1], ge = gstart[g];
+        if (ge == gs) continue;
+        const int nch = nchunk[g - 1], wd = 4 * nch, sl = slot[g - 1];
+        {  // input layer: units of degree g see the orders 0..g-1
+          const float* w = P + off_w0[g - 1];
+          for (int c = 0; c < nch; ++c) {
+            float acc[4];
+            dot4<LPP>(w, wd, 4 * c, g, xs, p, q, acc);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(P + off_b0 + sl + 4 * c));
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int u = gs + 4 * c + i;
+              if (u < ge && q == (i % LPP)) act[u * PW + p] = fmaxf(acc[i] + bb[i], 0.0f);
+            }
+          }
+        }
+        __syncwarp();
+        for (int l_ = 1; l_ < L; ++l_) {  // residual hidden layers: h + W h, then ReLU
+          const float* w = P + off_wh[(l_ - 1) * ng + (g - 1)];
+          const float* src = act + (size_t)(l_ - 1) * H * PW;
+          float* dst = act + (size_t)l_ * H * PW;
+          const int ob = off_bh[l_ - 1] + sl;
+          for (int c = 0; c < nch; ++c) {
+            float acc[4];
+            dot4<LPP>(w, wd, 4 * c, ge, src, p, q, acc);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(P + ob + 4 * c));
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int u = gs + 4 * c + i;
+              if (u < ge && q == (i % LPP)) dst[u * PW + p] = fmaxf(src[u * PW + p] + (acc[i] + bb[i]), 0.0f);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    // write back
+    for (int i = lane; i < PW * D; i += 32) {
+      const int r = i / D, c = i - r * D;
+      if (r < rows) out[row0 * D + i] = cur[c * PW + r];
+    }
+    if (q == 0 && p < rows) ladj_out[row0 + p] = ladj;
+    __syncwarp();
+  }
+}
+
+__global__ void pack_kernel(const float* __restrict__ raw, const int* __restrict__ gather,
+                            float* __restrict__ packed, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int g = gather[i];
+    packed[i] = g >= 0 ? raw[g] : 0.0f;
+  }
+}
+
+__global__ void base_logprob_kernel(const float* __restrict__ z, const float* __restrict__ ladj,
+                                    float* __restrict__ lp, long long n, int d) {
+  // warp per row: sum_d (-0.5 z^2 - 0.5 log 2pi) + ladj   (zuko DiagNormal.log_prob + ladj)
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      const float v = z[r * d + j];
+      s += -0.5f * v * v - 0.91893853320467274178f;
+    }
+    s = warp_sum(s);
+    if (lane == 0) lp[r] = s + ladj[r];
+  }
+}
+
+template <class UNI>
+static int launch_sweep(const float* packed, const int* meta, int meta_len, const int* hmeta,
+                        const float* in, float* out, float* ladj, long long n, int inverse, cudaStream_t st) {
+  const int D = hmeta[M_D], H = hmeta[M_H], L = hmeta[M_L];
+  const size_t meta_bytes = ((size_t)meta_len * 4 + 15) & ~(size_t)15;
+  const int sms = sm_count();
+  const int warps_per_block = 4;
+  // pick lanes-per-particle: smallest LPP whose tile fits shared memory, then raise it while the
+  // launch would leave SMs without enough resident warps (latency-bound regime at small N).
+  int lpp = 1;
+  auto smem_for = [&](int l) { return meta_bytes + (size_t)warps_per_block * (2 * D + L * H) * (32 / l) * 4; };
+  while (lpp < 32 && smem_for(lpp) > 100 * 1024) lpp <<= 1;
+  while (lpp < 8 && (n + (32 / lpp) - 1) / (32 / lpp) < (long long)sms * 16) lpp <<= 1;
+  const size_t smem = smem_for(lpp);
+  if (smem > 227 * 1024) { set_error("flow too large for the sweep kernel: %zu B shared memory", smem); return 3; }
+  const long long tiles = (n + (32 / lpp) - 1) / (32 / lpp);
+  long long blocks = (tiles + warps_per_block - 1) / warps_per_block;
+  const long long cap = (long long)sms * std::max(1, (int)((200 * 1024) / smem));
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define PMC_SWEEP_CASE(LPPV)                                                                          \
+  case LPPV: {                                                                                        \
+    auto kern = made_sweep_kernel<UNI, LPPV>;                                                         \
+    PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    kern<<<(unsigned)blocks, warps_per_block * 32, smem, st>>>(packed, meta, meta_len, in, out, ladj, n, inverse); \
+  } break;
+  switch (lpp) {
+    PMC_SWEEP_CASE(1) PMC_SWEEP_CASE(2) PMC_SWEEP_CASE(4) PMC_SWEEP_CASE(8) PMC_SWEEP_CASE(16) PMC_SWEEP_CASE(32)
+  }
+#undef PMC_SWEEP_CASE
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace pmc
+
+using namespace pmc;
+
+extern "C" int pmc_flow_pack(const float* raw, const int32_t* gather, float* packed, int64_t n, pmc_stream_t stream) {
+  PMC_REQUIRE(raw && gather && packed && n > 0, "pmc_flow_pack: bad arguments");
+  const int blocks = grid_for(n, 256, 8);
+  pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(raw, gather, packed, n);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_flow_sweep(const float* packed, const int32_t* meta, const int32_t* meta_host, int32_t meta_len,
+                              const float* in, float* out, float* ladj, int64_t n, int32_t inverse,
+                              pmc_stream_t stream) {
+  PMC_REQUIRE(packed && meta && meta_host && in && out && ladj, "pmc_flow_sweep: null pointer");
+  PMC_REQUIRE(meta_len >= 32, "pmc_flow_sweep: meta too short");
+  if (n == 0) return 0;
+  const int* hm = meta_host;
+  PMC_REQUIRE(hm[M_D] >= 2 && hm[M_H] >= 1 && hm[M_L] >= 1 && hm[M_T] >= 1, "pmc_flow_sweep: bad meta header");
+  if (hm[M_KIND] == 0) return launch_sweep<Affine>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
+  PMC_REQUIRE(hm[M_BINS] == 8 && hm[M_TOTAL] == 23, "pmc_flow_sweep: only bins=8 splines are built");
+  return launch_sweep<Rqs>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
+}
+
+extern "C" int pmc_flow_base_logprob(const float* z, const float* ladj, float* logprob, int64_t n, int32_t d,
+                                     pmc_stream_t stream) {
+  PMC_REQUIRE(z && ladj && logprob, "pmc_flow_base_logprob: null pointer");
+  if (n == 0) return 0;
+  const int blocks = grid_for(n, 8, 8);
+  base_logprob_kernel<<<blocks, 256, 0, as_stream(stream)>>>(z, ladj, logprob, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,612 @@
+// Vectorised MCMC step kernels: proposal, reparameterisation, Metropolis accept/update,
+// scalar adaptation, device RNG.  Reference: pocomc/mcmc.py (all four kernels) and
+// pocomc/scaler.py.  SMC state is f64 like the reference's numpy arrays; these kernels are
+// HBM-bound: one warp per particle row, lanes stride the D columns so every
+// global access is a contiguous row segment.
+#include "common.cuh"
+
+namespace pmc {
+
+constexpr int ROWS_PER_BLOCK = 256;  // accept kernel: fixed row->block map => deterministic partials
+
+// ------------------------------------------------------------------------------------------
+// proposals
+// ------------------------------------------------------------------------------------------
+template <typename PosT>
+__global__ void __launch_bounds__(128)
+tpcn_propose_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl,
+                    const double* __restrict__ inv_t, const double* __restrict__ chol_t, double nu,
+                    const double* __restrict__ g, const double* __restrict__ z,
+                    double* __restrict__ prop64, float* __restrict__ prop32,
+                    double* __restrict__ m_cur, double* __restrict__ m_prop, long long n, int d) {
+  extern __shared__ double sh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* diff = sh + (size_t)warp * 3 * d;
+  double* zz = diff + d;
+  double* dp = zz + d;
+  const double sigma = ctl[PMC_CTL_SIGMA];
+  const double* mu = ctl + PMC_CTL_MU;
+  const double keep = sqrt(1.0 - sigma * sigma);  // (1 - sigma**2)**0.5   mcmc.py:85
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    for (int j = lane; j < d; j += 32) {
+      diff[j] = (double)pos[row * d + j] - mu[j];
+      zz[j] = z[row * d + j];
+    }
+    __syncwarp();
+    double part = 0.0;
+    for (int i = lane; i < d; i += 32) {
+      double v = 0.0;
+      for (int j = 0; j < d; ++j) v = fma(inv_t[(size_t)j * d + i], diff[j], v);
+      part = fma(diff[i], v, part);
+    }
+    const double m = warp_sum(part);
+    const double s = 1.0 / (g[row] * (2.0 / (nu + m)));   // 1 / gamma(a, scale = 2/(nu+m))   mcmc.py:80
+    const double amp = sigma * sqrt(s);
+    for (int i = lane; i < d; i += 32) {
+      double lz = 0.0;
+      for (int j = 0; j < d; ++j) lz = fma(chol_t[(size_t)j * d + i], zz[j], lz);
+      const double pr = (mu[i] + keep * diff[i]) + amp * lz;
+      prop64[row * d + i] = pr;
+      if (prop32) prop32[row * d + i] = (float)pr;
+      dp[i] = pr - mu[i];
+    }
+    __syncwarp();
+    part = 0.0;
+    for (int i = lane; i < d; i += 32) {
+      double v = 0.0;
+      for (int j = 0; j < d; ++j) v = fma(inv_t[(size_t)j * d + i], dp[j], v);
+      part = fma(dp[i], v, part);
+    }
+    const double mp = warp_sum(part);
+    if (lane == 0) { m_cur[row] = m; m_prop[row] = mp; }
+    __syncwarp();
+  }
+}
+
+template <typename PosT>
+__global__ void __launch_bounds__(128)
+rwm_propose_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl,
+                   const double* __restrict__ chol_t, const double* __restrict__ z,
+                   double* __restrict__ prop64, float* __restrict__ prop32, long long n, int d) {
+  extern __shared__ double sh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* zz = sh + (size_t)warp * d;
+  const double sigma = ctl[PMC_CTL_SIGMA];
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    for (int j = lane; j < d; j += 32) zz[j] = z[row * d + j];
+    __syncwarp();
+    for (int i = lane; i < d; i += 32) {
+      double lz = 0.0;
+      for (int j = 0; j < d; ++j) lz = fma(chol_t[(size_t)j * d + i], zz[j], lz);
+      const double pr = (double)pos[row * d + i] + sigma * lz;   // mcmc.py:253
+      prop64[row * d + i] = pr;
+      if (prop32) prop32[row * d + i] = (float)pr;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// reparameterisation (scaler.py)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scaler_inv_dim(int kind, int logit, double v, double lo, double hi,
+                                               double& x, double& J) {
+  if (kind == 0) { x = v; J = 0.0; }
+  else if (kind == 1) { x = exp(v) + lo; J = v; }                    // scaler.py:329-346
+  else if (kind == 2) { x = hi - exp(v); J = v; }                    // scaler.py:362-378
+  else {
+    const double span = hi - lo;
+    double p;
+    if (logit) {                                                     // scaler.py:418-421
+      p = exp(-logaddexp(0.0, -v));
+      J = log(span) + log(p) + log(1.0 - p);
+    } else {                                                         // scaler.py:422-425
+      p = (erf(v / 1.4142135623730951) + 1.0) / 2.0;
+      J = log(span) + (-(v * v) / 2.0) - 0.91893853320467267;
+    }
+    x = p * span + lo;
+  }
+}
+
+__device__ __forceinline__ double scaler_fwd_dim(int kind, int logit, double x, double lo, double hi) {
+  if (kind == 0) return x;
+  if (kind == 1) return log(x - lo);
+  if (kind == 2) return log(hi - x);
+  const double p = (x - lo) / (hi - lo);
+  return logit ? log(p / (1.0 - p)) : 1.4142135623730951 * erfinv(2.0 * p - 1.0);
+}
+
+__device__ __forceinline__ double wrap_bc(double x, int bc, double lo, double hi) {
+  if (!isfinite(x)) return x;  // the reference's while-loops would never terminate here
+  int guard = 0;
+  if (bc & 1) {                // periodic, scaler.py:109-131
+    while (x > hi && guard++ < 100000) x = lo + x - hi;
+    while (x < lo && guard++ < 100000) x = hi + x - lo;
+  }
+  if (bc & 2) {                // reflective, scaler.py:133-157
+    while (x > hi && guard++ < 100000) x = hi - x + hi;
+    while (x < lo && guard++ < 100000) x = lo + lo - x;
+  }
+  return x;
+}
+
+template <typename UT>
+__global__ void __launch_bounds__(256)
+scaler_inverse_kernel(const UT* __restrict__ u_in, pmc_scaler sc, double* __restrict__ u_out,
+                      double* __restrict__ x_out, double* __restrict__ logdetj,
+                      uint8_t* __restrict__ finite, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    double jsum = 0.0;
+    int ok = 1;
+    for (int j = lane; j < d; j += 32) {
+      double uu = (double)u_in[row * d + j];
+      const int kind = sc.kind[j];
+      const double lo = sc.low[j], hi = sc.high[j];
+      double v = sc.scale ? (sc.mu[j] + sc.sigma[j] * uu) : uu;
+      double xx, J;
+      scaler_inv_dim(kind, sc.logit, v, lo, hi, xx, J);
+      if (sc.bc) {  // mcmc.py:94-97: wrap x, re-forward to u, re-inverse
+        xx = wrap_bc(xx, sc.bc[j], lo, hi);
+        v = scaler_fwd_dim(kind, sc.logit, xx, lo, hi);
+        uu = sc.scale ? (v - sc.mu[j]) / sc.sigma[j] : v;
+        v = sc.scale ? (sc.mu[j] + sc.sigma[j] * uu) : uu;
+        scaler_inv_dim(kind, sc.logit, v, lo, hi, xx, J);
+      }
+      u_out[row * d + j] = uu;
+      x_out[row * d + j] = xx;
+      jsum += J;
+      ok &= isfinite(xx) ? 1 : 0;
+    }
+    jsum = warp_sum(jsum);
+    ok = warp_and(ok);
+    if (lane == 0) {
+      const double ld = (sc.scale ? sc.log_sigma_sum : 0.0) + jsum;
+      logdetj[row] = ld;
+      finite[row] = (uint8_t)(ok && isfinite(ld));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scaler_forward_kernel(const double* __restrict__ x, pmc_scaler sc, double* __restrict__ u, long long total, int d) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int j = (int)(i % d);
+    const double v = scaler_fwd_dim(sc.kind[j], sc.logit, x[i], sc.low[j], sc.high[j]);
+    u[i] = sc.scale ? (v - sc.mu[j]) / sc.sigma[j] : v;
+  }
+}
+
+
+__global__ void __launch_bounds__(256)
+apply_bc_kernel(double* __restrict__ x, const int* __restrict__ bc, const double* __restrict__ low,
+                const double* __restrict__ high, long long total, int d) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int j = (int)(i % d);
+    if (bc[j]) x[i] = wrap_bc(x[i], bc[j], low[j], high[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Metropolis accept + masked update + block partial sums
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, double* __restrict__ u,
+                 double* __restrict__ x, double* __restrict__ logdetj, double* __restrict__ logl,
+                 double* __restrict__ logp, float* __restrict__ ldjf, const double* __restrict__ prop64,
+                 const double* __restrict__ u_p, const double* __restrict__ x_p,
+                 const double* __restrict__ logdetj_p, const double* __restrict__ logl_p,
+                 const double* __restrict__ logp_p, const float* __restrict__ ldjf_p,
+                 const double* __restrict__ m_cur, const double* __restrict__ m_prop,
+                 const double* __restrict__ r, const uint8_t* __restrict__ finite,
+                 double* __restrict__ alpha_out, double* __restrict__ partials, long long n, int d) {
+  extern __shared__ double sh[];  // [8 warps][d] theta sums + [8][4] scalars
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* th = sh + (size_t)warp * d;
+  double* sc = sh + (size_t)8 * d + warp * 4;
+  const bool flow = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_RWM_FLOW);
+  const bool tp = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_TPCN);
+  const bool want_theta = (kind == PMC_KIND_TPCN_FLOW);
+  for (int j = lane; j < d; j += 32) th[j] = 0.0;
+  const long long base = (long long)blockIdx.x * ROWS_PER_BLOCK + warp * 32;
+  const long long row = base + lane;
+  const bool valid = row < n;
+  double alpha = 0.0, track = 0.0;
+  int acc = 0, fin = 0;
+  if (valid) {
+    // mcmc.py:130-134 (left-to-right f64 sum; f32 flow log-dets promoted)
+    double t = logl_p[row] * beta - logl[row] * beta + logp_p[row] - logp[row] + logdetj_p[row] - logdetj[row];
+    if (flow) t = t + (double)ldjf_p[row] - (double)ldjf[row];
+    if (tp) {
+      const double A = -(d + nu) / 2 * log(1 + m_prop[row] / nu);
+      const double B = -(d + nu) / 2 * log(1 + m_cur[row] / nu);
+      t = t - A + B;
+    }
+    alpha = fmin(1.0, exp(t));
+    if (isnan(alpha) || isnan(t)) alpha = 0.0;
+    acc = r[row] < alpha;
+    fin = finite ? finite[row] : 0;
+    if (alpha_out) alpha_out[row] = alpha;
+    double nl = logl[row], np_ = logp[row], nj = logdetj[row];
+    if (acc) {
+      nl = logl_p[row]; np_ = logp_p[row]; nj = logdetj_p[row];
+      logl[row] = nl; logp[row] = np_; logdetj[row] = nj;
+      if (flow) ldjf[row] = ldjf_p[row];
+    }
+    track = tp ? (nl + np_) : (nl + np_ + nj);   // mcmc.py:170 vs :327
+  }
+  const unsigned ballot = __ballot_sync(FULL, acc);
+  const double s_alpha = warp_sum(alpha), s_track = warp_sum(track);
+  const int s_fin = __popc(__ballot_sync(FULL, fin));
+  for (int rr = 0; rr < 32; ++rr) {
+    const long long rw = base + rr;
+    if (rw >= n) break;
+    const bool a = (ballot >> rr) & 1u;
+    for (int j = lane; j < d; j += 32) {
+      const long long o = rw * d + j;
+      if (a) {
+        u[o] = u_p[o];
+        x[o] = x_p[o];
+        if (pos32) pos32[o] = (float)prop64[o];   // theta[mask] = theta_prime[mask] rounds to f32, mcmc.py:141
+      }
+      if (want_theta) th[j] += (double)pos32[o];
+    }
+  }
+  if (lane == 0) { sc[0] = s_alpha; sc[1] = s_track; sc[2] = (double)__popc(ballot); sc[3] = (double)s_fin; }
+  __syncthreads();
+  double* out = partials + (size_t)blockIdx.x * (d + 4);
+  for (int j = threadIdx.x; j < d + 4; j += blockDim.x) {
+    double s = 0.0;
+    if (j < 4) { for (int w = 0; w < 8; ++w) s += sh[(size_t)8 * d + w * 4 + j]; }
+    else if (want_theta) { for (int w = 0; w < 8; ++w) s += sh[(size_t)w * d + (j - 4)]; }
+    out[j] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mcmc_finalize_kernel(int kind, double* __restrict__ ctl, const double* __restrict__ partials, int n_blocks,
+                     const float* __restrict__ pos32, int mean_mode, int n_steps, int n_max, long long n, int d) {
+  extern __shared__ double tot[];  // [d + 4]
+  const bool tpf = (kind == PMC_KIND_TPCN_FLOW);
+  for (int j = threadIdx.x; j < d + 4; j += blockDim.x) {
+    double s = 0.0;
+    if (j < 4 || (tpf && mean_mode == 0)) {
+      for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * (d + 4) + j];
+      if (j >= 4) s /= (double)n;
+    } else if (tpf) {
+      // np.mean(theta, axis=0) on the f32 theta array: sequential f32 accumulation over rows, f32 divide
+      float a = 0.0f;
+      const float* p = pos32 + (j - 4);
+      for (long long rw = 0; rw < n; ++rw) a += p[rw * d];
+      s = (double)(a / (float)n);
+    }
+    tot[j] = s;
+  }
+  __syncthreads();
+  const double step = ctl[PMC_CTL_STEP] + 1.0;   // i (1-based) of the step just finished
+  if (tpf) {
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+      const double mu = ctl[PMC_CTL_MU + j];
+      ctl[PMC_CTL_MU + j] = mu + 1.0 / (step + 1.0) * (tot[4 + j] - mu);   // mcmc.py:156
+    }
+  }
+  if (threadIdx.x == 0) {
+    const double mean_alpha = tot[0] / (double)n;
+    const double track = tot[1] / (double)n;
+    double sigma = ctl[PMC_CTL_SIGMA];
+    const double cap = 2.38 / pow((double)d, 0.5);
+    if (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_TPCN)
+      sigma = fabs(fmin(sigma + 1.0 / pow(step + 1.0, 0.75) * (mean_alpha - 0.234), fmin(cap, 0.99)));  // mcmc.py:152
+    else if (kind == PMC_KIND_RWM_FLOW)
+      sigma = sigma + 1.0 / (step + 1.0) * (mean_alpha - 0.234);                                         // mcmc.py:314
+    else
+      sigma = fabs(sigma + 1.0 / (step + 1.0) * (mean_alpha - 0.234));                                   // mcmc.py:627
+    double best = ctl[PMC_CTL_BEST], cnt = ctl[PMC_CTL_CNT], stop = 0.0;
+    if (track > best) { cnt = 0.0; best = track; }
+    else {
+      cnt += 1.0;
+      double ratio = cap / sigma;
+      if (kind == PMC_KIND_RWM_FLOW) ratio = fmin(1.0, ratio);                                           // mcmc.py:333
+      if (cnt >= n_steps * pow(ratio, 2.0)) stop = 1.0;
+    }
+    if (step >= (double)n_max) stop = 1.0;
+    ctl[PMC_CTL_SIGMA] = sigma;
+    ctl[PMC_CTL_STEP] = step;
+    ctl[PMC_CTL_BEST] = best;
+    ctl[PMC_CTL_CNT] = cnt;
+    ctl[PMC_CTL_STOP] = stop;
+    ctl[PMC_CTL_ACCEPT] = mean_alpha;
+    ctl[PMC_CTL_CALLS] += tot[3];
+    ctl[PMC_CTL_TRACK] = track;
+    ctl[PMC_CTL_NACC] = tot[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (throughput mode; parity mode uploads numpy's legacy stream instead)
+// ------------------------------------------------------------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ uint4 operator()(uint4 c) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+      c = make_uint4(hi1 ^ c.y ^ a, lo1, hi0 ^ c.w ^ b, lo0);
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return c;
+  }
+};
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {  // (0,1)
+  const unsigned long long v = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ void box_muller(uint4 c, double& n0, double& n1) {
+  const double u1 = u53(c.x, c.y), u2 = u53(c.z, c.w);
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  n0 = rad * cs; n1 = rad * sn;
+}
+
+__global__ void __launch_bounds__(256)
+rng_fill_kernel(uint64_t seed, uint64_t step, long long offset, double shape, double* __restrict__ g,
+                double* __restrict__ z, double* __restrict__ r, long long n, int d) {
+  const Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  const int half = (d + 1) / 2;
+  const long long total = n * (half + 1);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / (half + 1);
+    const int slot = (int)(i - row * (half + 1));
+    const unsigned long long pid = (unsigned long long)(row + offset);
+    if (slot < half) {  // two normals
+      double a, b;
+      box_muller(ph(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)slot << 8))), a, b);
+      z[row * d + 2 * slot] = a;
+      if (2 * slot + 1 < d) z[row * d + 2 * slot + 1] = b;
+    } else {            // uniform + gamma (Marsaglia-Tsang, shape >= 1)
+      const uint32_t tag = 0x80000000u;
+      uint4 c = ph(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)step, ((uint32_t)(step >> 32)) ^ tag));
+      if (r) r[row] = u53(c.x, c.y);
+      if (g && shape > 0.0) {
+        const double a = shape < 1.0 ? shape + 1.0 : shape;
+        const double dd = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+        double out = dd;
+        for (uint32_t att = 1; att < 4096; ++att) {
+          uint4 c1 = ph(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)step, ((uint32_t)(step >> 32)) ^ tag ^ (att << 8)));
+          uint4 c2 = ph(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)step, ((uint32_t)(step >> 32)) ^ tag ^ (att << 8) ^ 1u));
+          double xn, unused;
+          box_muller(c1, xn, unused);
+          const double uu = u53(c2.x, c2.y);
+          double v = 1.0 + cc * xn;
+          if (v <= 0.0) continue;
+          v = v * v * v;
+          if (log(uu) < 0.5 * xn * xn + dd - dd * v + dd * log(v)) { out = dd * v; break; }
+        }
+        if (shape < 1.0) out *= pow(u53(c.z, c.w), 1.0 / shape);
+        g[row] = out;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic likelihoods / product priors on device (bench + opt-in fast path)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+loglike_kernel(int which, const double* __restrict__ x, const uint8_t* __restrict__ finite,
+               const double* __restrict__ mat_t, double p0, double p1, double* __restrict__ logl,
+               long long n, int d) {
+  extern __shared__ double sh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* xr = sh + (size_t)warp * d;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    if (finite && !finite[row]) { if (lane == 0) logl[row] = -INFINITY; continue; }
+    for (int j = lane; j < d; j += 32) xr[j] = x[row * d + j];
+    __syncwarp();
+    double part = 0.0, res;
+    if (which == PMC_LIKE_GAUSS) {          // -0.5 x^T P x + p0
+      for (int i = lane; i < d; i += 32) {
+        double v = 0.0;
+        for (int j = 0; j < d; ++j) v = fma(mat_t[(size_t)j * d + i], xr[j], v);
+        part = fma(xr[i], v, part);
+      }
+      res = -0.5 * warp_sum(part) + p0;
+    } else if (which == PMC_LIKE_ROSENBROCK) {   // README.md:53-55
+      for (int i = 2 * lane; i + 1 < d; i += 64) {
+        const double a = xr[i] * xr[i] - xr[i + 1], b = xr[i] - 1.0;
+        part += 10.0 * a * a + b * b;
+      }
+      res = -warp_sum(part);
+    } else if (which == PMC_LIKE_MIXTURE) {      // logaddexp(N(x;+c,s^2 I), N(x;-c,s^2 I)) - log 2
+      double qa = 0.0, qb = 0.0;
+      for (int i = lane; i < d; i += 32) { qa += (xr[i] - p0) * (xr[i] - p0); qb += (xr[i] + p0) * (xr[i] + p0); }
+      qa = warp_sum(qa); qb = warp_sum(qb);
+      const double norm = -0.5 * d * log(2.0 * 3.14159265358979323846 * p1 * p1);
+      res = logaddexp(norm - 0.5 * qa / (p1 * p1), norm - 0.5 * qb / (p1 * p1)) - 0.69314718055994530942;
+    } else {                                     // Neal funnel: x0 ~ N(0,p0^2), x_i ~ N(0, e^{x0})
+      const double x0 = xr[0];
+      for (int i = lane + 1; i < d; i += 32) part += xr[i] * xr[i];
+      part = warp_sum(part);
+      res = -0.5 * x0 * x0 / (p0 * p0) - 0.5 * log(2.0 * 3.14159265358979323846 * p0 * p0)
+            - 0.5 * part * exp(-x0) - 0.5 * (d - 1) * (log(2.0 * 3.14159265358979323846) + x0);
+    }
+    if (lane == 0) logl[row] = res;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+logprior_kernel(const double* __restrict__ x, uint8_t* __restrict__ finite, const int* __restrict__ kind,
+                const double* __restrict__ loc, const double* __restrict__ scale, double* __restrict__ logp,
+                long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    if (finite && !finite[row]) { if (lane == 0) logp[row] = -INFINITY; continue; }
+    double s = 0.0;
+    for (int j = lane; j < d; j += 32) {
+      const double v = x[row * d + j];
+      if (kind[j] == 0) {
+        const double t = (v - loc[j]) / scale[j];
+        s += -0.5 * t * t - 0.91893853320467267 - log(scale[j]);
+      } else {
+        s += (v >= loc[j] && v <= loc[j] + scale[j]) ? -log(scale[j]) : -INFINITY;
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      logp[row] = s;
+      if (finite && !isfinite(s)) finite[row] = 0;
+    }
+  }
+}
+
+}  // namespace pmc
+
+using namespace pmc;
+
+extern "C" int pmc_tpcn_propose(int32_t pos_is_f32, const void* pos, const double* ctl, const double* inv_cov_t,
+                                const double* chol_t, double nu, const double* g, const double* z, double* prop64,
+                                float* prop32, double* m_cur, double* m_prop, int64_t n, int32_t d,
+                                pmc_stream_t stream) {
+  PMC_REQUIRE(pos && ctl && inv_cov_t && chol_t && g && z && prop64 && m_cur && m_prop, "pmc_tpcn_propose: null pointer");
+  PMC_REQUIRE(d >= 1 && d <= 1024, "pmc_tpcn_propose: unsupported dimension");
+  if (n == 0) return 0;
+  const size_t smem = (size_t)4 * 3 * d * sizeof(double);
+  const int blocks = grid_for(n, 4, 16);
+  if (pos_is_f32)
+    tpcn_propose_kernel<float><<<blocks, 128, smem, as_stream(stream)>>>((const float*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+  else
+    tpcn_propose_kernel<double><<<blocks, 128, smem, as_stream(stream)>>>((const double*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_rwm_propose(int32_t pos_is_f32, const void* pos, const double* ctl, const double* chol_t,
+                               const double* z, double* prop64, float* prop32, int64_t n, int32_t d,
+                               pmc_stream_t stream) {
+  PMC_REQUIRE(pos && ctl && chol_t && z && prop64, "pmc_rwm_propose: null pointer");
+  PMC_REQUIRE(d >= 1 && d <= 1024, "pmc_rwm_propose: unsupported dimension");
+  if (n == 0) return 0;
+  const size_t smem = (size_t)4 * d * sizeof(double);
+  const int blocks = grid_for(n, 4, 16);
+  if (pos_is_f32)
+    rwm_propose_kernel<float><<<blocks, 128, smem, as_stream(stream)>>>((const float*)pos, ctl, chol_t, z, prop64, prop32, n, d);
+  else
+    rwm_propose_kernel<double><<<blocks, 128, smem, as_stream(stream)>>>((const double*)pos, ctl, chol_t, z, prop64, prop32, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_scaler_inverse(int32_t u_is_f32, const void* u_in, const pmc_scaler* sc, double* u_out, double* x,
+                                  double* logdetj, uint8_t* finite, int64_t n, int32_t d, pmc_stream_t stream) {
+  PMC_REQUIRE(u_in && sc && u_out && x && logdetj && finite, "pmc_scaler_inverse: null pointer");
+  PMC_REQUIRE(sc->kind && sc->low && sc->high && (!sc->scale || (sc->mu && sc->sigma)), "pmc_scaler_inverse: incomplete scaler");
+  if (n == 0) return 0;
+  const int blocks = grid_for(n, 8, 8);
+  if (u_is_f32)
+    scaler_inverse_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((const float*)u_in, *sc, u_out, x, logdetj, finite, n, d);
+  else
+    scaler_inverse_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>((const double*)u_in, *sc, u_out, x, logdetj, finite, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_scaler_forward(const double* x, const pmc_scaler* sc, double* u, int64_t n, int32_t d,
+                                  pmc_stream_t stream) {
+  PMC_REQUIRE(x && sc && u, "pmc_scaler_forward: null pointer");
+  if (n == 0) return 0;
+  const int blocks = grid_for(n * d, 256, 8);
+  scaler_forward_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, *sc, u, n * (long long)d, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+
+extern "C" int pmc_apply_bc(double* x, const int32_t* bc, const double* low, const double* high, int64_t n, int32_t d,
+                            pmc_stream_t stream) {
+  PMC_REQUIRE(x && bc && low && high, "pmc_apply_bc: null pointer");
+  if (n == 0) return 0;
+  apply_bc_kernel<<<grid_for(n * d, 256, 8), 256, 0, as_stream(stream)>>>(x, bc, low, high, n * (long long)d, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+static inline int64_t mh_blocks(int64_t n) { return (n + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK; }
+
+extern "C" int64_t pmc_mh_partials_size(int64_t n, int32_t d) { return mh_blocks(n) * (int64_t)(d + 4); }
+
+extern "C" int pmc_mh_accept_update(int32_t kind, double beta, double nu, float* pos32, double* u, double* x,
+                                    double* logdetj, double* logl, double* logp, float* logdetj_flow,
+                                    const double* prop64, const double* u_p, const double* x_p,
+                                    const double* logdetj_p, const double* logl_p, const double* logp_p,
+                                    const float* logdetj_flow_p, const double* m_cur, const double* m_prop,
+                                    const double* r, const uint8_t* finite, double* alpha_out, double* partials,
+                                    int64_t n, int32_t d, pmc_stream_t stream) {
+  PMC_REQUIRE(kind >= 0 && kind <= 3, "pmc_mh_accept_update: bad kind");
+  PMC_REQUIRE(u && x && logdetj && logl && logp && u_p && x_p && logdetj_p && logl_p && logp_p && r && partials,
+              "pmc_mh_accept_update: null pointer");
+  const bool flow = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_RWM_FLOW);
+  const bool tp = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_TPCN);
+  PMC_REQUIRE(!flow || (pos32 && prop64 && logdetj_flow && logdetj_flow_p), "pmc_mh_accept_update: flow kinds need theta + flow log-dets");
+  PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_update: tpCN kinds need the Mahalanobis distances");
+  if (n == 0) return 0;
+  const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
+  mh_accept_kernel<<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
+      kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
+      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_mcmc_finalize(int32_t kind, double* ctl, const double* partials, const float* pos32,
+                                 int32_t mean_mode, int32_t n_steps, int32_t n_max, int64_t n, int32_t d,
+                                 pmc_stream_t stream) {
+  PMC_REQUIRE(ctl && partials && n > 0, "pmc_mcmc_finalize: bad arguments");
+  PMC_REQUIRE(!(kind == PMC_KIND_TPCN_FLOW && mean_mode == 1) || pos32, "pmc_mcmc_finalize: mean_mode 1 needs theta");
+  mcmc_finalize_kernel<<<1, 256, (size_t)(d + 4) * sizeof(double), as_stream(stream)>>>(
+      kind, ctl, partials, (int)mh_blocks(n), pos32, mean_mode, n_steps, n_max, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_rng_fill(uint64_t seed, uint64_t step, int64_t particle_offset, double gamma_shape, double* g,
+                            double* z, double* r, int64_t n, int32_t d, pmc_stream_t stream) {
+  PMC_REQUIRE(z && n >= 0 && d >= 1, "pmc_rng_fill: bad arguments");
+  if (n == 0) return 0;
+  const int blocks = grid_for(n * ((d + 1) / 2 + 1), 256, 8);
+  rng_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, step, particle_offset, gamma_shape, g, z, r, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_loglike(int32_t which, const double* x, const uint8_t* finite, const double* mat_t, double p0,
+                           double p1, double* logl, int64_t n, int32_t d, pmc_stream_t stream) {
+  PMC_REQUIRE(x && logl && which >= 0 && which <= 3, "pmc_loglike: bad arguments");
+  PMC_REQUIRE(which != PMC_LIKE_GAUSS || mat_t, "pmc_loglike: gauss needs the precision matrix");
+  if (n == 0) return 0;
+  const int blocks = grid_for(n, 4, 16);
+  loglike_kernel<<<blocks, 128, (size_t)4 * d * sizeof(double), as_stream(stream)>>>(which, x, finite, mat_t, p0, p1, logl, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_logprior(const double* x, uint8_t* finite, const int32_t* kind, const double* loc,
+                            const double* scale, double* logp, int64_t n, int32_t d, pmc_stream_t stream) {
+  PMC_REQUIRE(x && kind && loc && scale && logp, "pmc_logprior: null pointer");
+  if (n == 0) return 0;
+  const int blocks = grid_for(n, 8, 8);
+  logprior_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, finite, kind, loc, scale, logp, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}

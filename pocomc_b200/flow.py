@@ -1,0 +1,440 @@
+"""Normalizing-flow preconditioner: the reference's ``pocomc.flow.Flow`` API on sm_100a kernels.
+
+Mirrors pocomc/flow.py (class Flow: __init__ 46-90, forward 99-114, inverse 116-132, log_prob
+134-147, sample 149-163, fit 165-384).  The flow arithmetic that the reference delegates to zuko
+(MAF / NSF over a masked MLP hyper-network) is implemented here:
+  * inference (no grad): libpmc_b200's degree-ordered sweep kernels (csrc/flow_sweep.cu) --
+    one sweep replaces zuko's D+1 hyper-network passes for the inverse;
+  * training (grad enabled): an autograd graph over the same parameters (north_star: "PyTorch
+    only for tensor containers and autograd on the flow").
+Tensors may live on the host (like the reference's) or on the GPU; results come back on the
+input's device.  There is no CPU compute path: without a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import copy
+import math
+import time
+import warnings
+from typing import Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from . import made_layout as ML
+from .tools import torch_double_to_float
+
+__all__ = ["Flow", "regularization_loss", "MaskedAutoregressiveFlow"]
+
+PRESETS = {"maf3": (ML.KIND_AFFINE, 3), "maf6": (ML.KIND_AFFINE, 6), "maf12": (ML.KIND_AFFINE, 12),
+           "nsf3": (ML.KIND_RQS, 3), "nsf6": (ML.KIND_RQS, 6), "nsf12": (ML.KIND_RQS, 12)}
+_LOG_SLOPE = math.log(1e-3)
+
+
+def _device():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------------------
+# differentiable univariate transforms (training path)
+# ------------------------------------------------------------------------------------------
+def _softclip(a, ls):
+    return a / (1 + abs(a / ls))
+
+
+def _affine_forward(x, phi):
+    """zuko MonotonicAffineTransform: y = x exp(ls) + shift, ladj = ls."""
+    ls = _softclip(phi[..., 1], _LOG_SLOPE)
+    return x * ls.exp() + phi[..., 0], ls
+
+
+def _rqs_forward(x, phi, bins=8, bound=5.0):
+    """zuko MonotonicRQSTransform forward + log|dy/dx|."""
+    w = _softclip(phi[..., :bins], _LOG_SLOPE / 2)
+    h = _softclip(phi[..., bins:2 * bins], _LOG_SLOPE / 2)
+    d = _softclip(phi[..., 2 * bins:], _LOG_SLOPE)
+    hx = bound * (2 * torch.cumsum(F.pad(F.softmax(w, dim=-1), (1, 0)), dim=-1) - 1)
+    hy = bound * (2 * torch.cumsum(F.pad(F.softmax(h, dim=-1), (1, 0)), dim=-1) - 1)
+    dv = torch.exp(F.pad(d, (1, 1)))
+    k = torch.searchsorted(hx.detach(), x.detach()[..., None].contiguous()).squeeze(-1) - 1
+    mask = (k >= 0) & (k < bins)
+    k = k % bins
+    k01 = torch.stack((k, k + 1), dim=-1)
+    x0, x1 = torch.gather(hx, -1, k01).unbind(-1)
+    y0, y1 = torch.gather(hy, -1, k01).unbind(-1)
+    d0, d1 = torch.gather(dv, -1, k01).unbind(-1)
+    s = (y1 - y0) / (x1 - x0)
+    z = mask * (x - x0) / (x1 - x0)
+    den = s + (d0 + d1 - 2 * s) * z * (1 - z)
+    y = y0 + (y1 - y0) * (s * z ** 2 + d0 * z * (1 - z)) / den
+    jac = s ** 2 * (2 * s * z * (1 - z) + d0 * (1 - z) ** 2 + d1 * z ** 2) / den ** 2
+    return torch.where(mask, y, x), torch.log(jac) * mask
+
+
+class MaskedAutoregressiveFlow(nn.Module):
+    """T masked-autoregressive transforms (affine = zuko MAF, rqs = zuko NSF bins=8) over a
+    diagonal-normal base; the object the reference stores as ``Flow.flow``.
+
+    All parameters live in ONE flat fp32 blob ``raw`` laid out in module order per transform
+    (W0,b0,W1,b1,...,W_out,b_out; torch [out,in]); initialised layer by layer exactly like
+    ``nn.Linear.reset_parameters`` so a given ``torch.manual_seed`` yields the same weights as
+    constructing the zuko flow.
+    """
+
+    def __init__(self, features: int, hidden: int, n_layers: int, transforms: int, kind: int, bins: int = 8):
+        super().__init__()
+        self.layout = ML.build_layout(int(features), int(hidden), int(n_layers), int(transforms), int(kind), bins)
+        lay = self.layout
+        raw = torch.empty(lay.raw_numel, dtype=torch.float32)
+        off = 0
+        for _ in range(lay.n_transforms):
+            shapes = lay.raw_sizes
+            for i in range(0, len(shapes), 2):
+                wshape, bshape = shapes[i], shapes[i + 1]
+                w = raw[off:off + wshape[0] * wshape[1]].view(wshape)
+                off += w.numel()
+                b = raw[off:off + bshape[0]]
+                off += b.numel()
+                nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+                bound = 1 / math.sqrt(wshape[1]) if wshape[1] > 0 else 0
+                nn.init.uniform_(b, -bound, bound)
+        self.raw = nn.Parameter(raw)
+        self.register_buffer("gather", torch.from_numpy(lay.gather.copy()), persistent=False)
+        self.register_buffer("meta", torch.from_numpy(lay.meta.copy()), persistent=False)
+        self._meta_host = np.ascontiguousarray(lay.meta)
+        self._packed = None
+        self._packed_key = None
+        self._masks = None
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_packed"], st["_packed_key"], st["_masks"] = None, None, None
+        return st
+
+    def _apply(self, fn, *a, **k):
+        self._packed, self._packed_key, self._masks = None, None, None
+        return super()._apply(fn, *a, **k)
+
+    def ensure_cuda(self):
+        if not self.raw.is_cuda:
+            self.to(_device())
+        return self
+
+    def transform_params(self, t: int):
+        """[(W, b), ...] views of transform ``t`` (torch [out, in])."""
+        lay, out, off = self.layout, [], t * self.layout.raw_tstride
+        for i in range(0, len(lay.raw_sizes), 2):
+            ws, bs = lay.raw_sizes[i], lay.raw_sizes[i + 1]
+            w = self.raw[off:off + ws[0] * ws[1]].view(ws)
+            off += ws[0] * ws[1]
+            b = self.raw[off:off + bs[0]]
+            off += bs[0]
+            out.append((w, b))
+        return out
+
+    def packed(self) -> torch.Tensor:
+        """degree-sorted slab copy of ``raw`` for the sweep kernels; rebuilt when raw changes."""
+        self.ensure_cuda()
+        key = (self.raw.data_ptr(), self.raw._version)
+        if self._packed is None or self._packed_key != key:
+            if self._packed is None or self._packed.device != self.raw.device:
+                self._packed = torch.empty(self.layout.packed_numel, dtype=torch.float32, device=self.raw.device)
+            _lib.call("pmc_flow_pack", _lib.ptr(self.raw.detach()), _lib.ptr(self.gather), _lib.ptr(self._packed),
+                      self.layout.packed_numel)
+            self._packed_key = key
+        return self._packed
+
+    # -- inference: sweep kernels -----------------------------------------------------------
+    @torch.no_grad()
+    def sweep(self, v: torch.Tensor, inverse: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """v [N, D] f32 (any device) -> (out [N, D], ladj [N]) on v's device."""
+        if v.dim() != 2 or v.shape[1] != self.layout.n_dim:
+            raise ValueError(f"expected input of shape (n, {self.layout.n_dim}), got {tuple(v.shape)}")
+        packed = self.packed()
+        src = v.detach().to(self.raw.device, torch.float32).contiguous()
+        out = torch.empty_like(src)
+        ladj = torch.empty(src.shape[0], dtype=torch.float32, device=src.device)
+        _lib.call("pmc_flow_sweep", _lib.ptr(packed), _lib.ptr(self.meta),
+                  self._meta_host.ctypes.data_as(_lib.C.c_void_p), int(self._meta_host.size), _lib.ptr(src),
+                  _lib.ptr(out), _lib.ptr(ladj), src.shape[0], 1 if inverse else 0)
+        return out.to(v.device), ladj.to(v.device)
+
+    @torch.no_grad()
+    def sweep_into(self, src: torch.Tensor, out: torch.Tensor, ladj: torch.Tensor, inverse: bool):
+        """Allocation-free variant for the MCMC loop: CUDA f32 src/out [N, D], ladj [N]."""
+        packed = self.packed()
+        if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
+            raise ValueError("sweep_into needs a contiguous CUDA float32 input")
+        _lib.call("pmc_flow_sweep", _lib.ptr(packed), _lib.ptr(self.meta),
+                  self._meta_host.ctypes.data_as(_lib.C.c_void_p), int(self._meta_host.size), _lib.ptr(src),
+                  _lib.ptr(out), _lib.ptr(ladj), src.shape[0], 1 if inverse else 0)
+
+    # -- training: autograd graph over the same parameters -----------------------------------
+    def _dense_masks(self):
+        if self._masks is None or self._masks[0][0].device != self.raw.device:
+            self._masks = [[torch.from_numpy(m).to(self.raw.device, torch.float32) for m in ML.masks(self.layout, t)]
+                           for t in range(self.layout.n_transforms)]
+        return self._masks
+
+    def forward_autograd(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """data -> latent with a graph (1 masked-MLP pass per transform, like zuko's forward)."""
+        self.ensure_cuda()
+        lay = self.layout
+        x = x.to(self.raw.device, torch.float32)
+        ladj = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
+        masks = self._dense_masks()
+        for t in range(lay.n_transforms):
+            params = self.transform_params(t)
+            h = x
+            last = len(params) - 1
+            for i, ((w, b), m) in enumerate(zip(params, masks[t])):
+                y = F.linear(h, w * m, b)
+                if i == 0:
+                    h = torch.relu(y)
+                elif i < last:
+                    h = torch.relu(h + y)       # residual hidden block (oracle/zuko/nn.py)
+                else:
+                    h = y
+            phi = h.unflatten(-1, (lay.n_dim, lay.total))
+            x, l = _affine_forward(x, phi) if lay.kind == ML.KIND_AFFINE else _rqs_forward(x, phi, lay.bins)
+            ladj = ladj + l.sum(dim=-1)
+        return x, ladj
+
+    # -- the lazy-flow protocol the reference expects from ``zuko.flows.Flow`` ---------------
+    def forward(self, c=None):
+        return _BoundFlow(self)
+
+
+class _Transform:
+    """``flow().transform`` : call_and_ladj / inv.call_and_ladj (flow.py:114,131)."""
+
+    def __init__(self, module: MaskedAutoregressiveFlow, inverse=False):
+        self.module, self._inverse = module, inverse
+
+    @property
+    def inv(self):
+        return _Transform(self.module, not self._inverse)
+
+    def call_and_ladj(self, x):
+        m = self.module
+        if not self._inverse and torch.is_grad_enabled() and (m.raw.requires_grad or x.requires_grad):
+            z, ladj = m.forward_autograd(x)
+            return z.to(x.device), ladj.to(x.device)
+        return m.sweep(x, self._inverse)
+
+    def __call__(self, x):
+        return self.call_and_ladj(x)[0]
+
+
+class _BoundFlow:
+    """``flow()`` : NormalizingFlow(transform, DiagNormal(0, I))."""
+
+    def __init__(self, module):
+        self.module = module
+        self.transform = _Transform(module)
+
+    def log_prob(self, x):
+        z, ladj = self.transform.call_and_ladj(x)
+        return (-0.5 * z ** 2 - 0.5 * math.log(2 * math.pi)).sum(dim=-1) + ladj
+
+    def rsample_and_log_prob(self, shape=()):
+        n = int(np.prod(shape)) if len(shape) else 1
+        d = self.module.layout.n_dim
+        z = torch.randn((n, d), dtype=torch.float32)        # host global torch RNG, like zuko's base.rsample
+        x, ladj = self.transform.inv.call_and_ladj(z)
+        lp = (-0.5 * z ** 2 - 0.5 * math.log(2 * math.pi)).sum(dim=-1) - ladj
+        return x.reshape(*shape, d), lp.reshape(*shape)
+
+    def rsample(self, shape=()):
+        return self.rsample_and_log_prob(shape)[0]
+
+
+def epoch_batches(n: int, batch_size: int, shuffle: bool):
+    """Index batches of one pass of ``DataLoader(TensorDataset(..n rows..), batch_size, shuffle)``
+    with the same draws from the global torch generator (flow.py:251-257,301,331):
+    the iterator's base seed, then (shuffle only) RandomSampler's private seed + randperm."""
+    torch.empty((), dtype=torch.int64).random_()
+    if shuffle:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        g = torch.Generator()
+        g.manual_seed(seed)
+        perm = torch.randperm(n, generator=g)
+    else:
+        perm = torch.arange(n)
+    return [perm[i:i + batch_size] for i in range(0, n, batch_size)]
+
+
+class Flow:
+    """
+    Normalizing flow model (API of ``pocomc.Flow``).
+
+    Parameters
+    ----------
+    n_dim : ``int``
+        Number of dimensions of the distribution to be modeled.
+    flow : ``str`` or ``MaskedAutoregressiveFlow``, optional
+        One of ``maf3, maf6, maf12, nsf3, nsf6, nsf12`` (default ``nsf3``) or a ready module.
+    """
+
+    def __init__(self, n_dim, flow="nsf3"):
+        self.n_dim = n_dim
+        n_hidden = ML.hidden_width(int(n_dim))
+        if isinstance(flow, str) and flow in PRESETS:
+            kind, transforms = PRESETS[flow]
+            self.flow = MaskedAutoregressiveFlow(n_dim, n_hidden, 3, transforms, kind)
+        elif isinstance(flow, MaskedAutoregressiveFlow):
+            self.flow = flow
+        else:
+            raise ValueError('Invalid flow type. Choose from: maf3, maf6, maf12, nsf3, nsf6, nsf12, '
+                             'or provide a MaskedAutoregressiveFlow object.')
+        if torch.cuda.is_available():
+            self.flow.ensure_cuda()
+
+    @property
+    def transform(self):
+        return self.flow().transform
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """data -> latent: (u, log|du/dx|)   (flow.py:99-114)."""
+        x = torch_double_to_float(x)
+        return self.transform.call_and_ladj(x)
+
+    __call__ = forward
+
+    def inverse(self, u: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """latent -> data: (x, log|dx/du|)   (flow.py:116-132)."""
+        u = torch_double_to_float(u)
+        return self.transform.inv.call_and_ladj(u)
+
+    def log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        """flow.py:134-147."""
+        x = torch_double_to_float(x)
+        return self.flow().log_prob(x)
+
+    def sample(self, size: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+        """flow.py:149-163."""
+        return self.flow().rsample_and_log_prob((size,))
+
+    def fit(self, x, weights=None, validation_split=0.0, epochs=1000, batch_size=1000, patience=20,
+            learning_rate=1e-3, weight_decay=0, laplace_scale=None, gaussian_scale=None, annealing=True,
+            noise=None, shuffle=True, clip_grad_norm=1.0, verbose=0):
+        """Weighted maximum-likelihood training, same control flow and RNG consumption as
+        flow.py:165-384 (including its quirks): ``validation_split`` is the TRAIN
+        fraction, losses are divided by the split size, best weights are restored only on early
+        stop.  Data, parameters, optimiser state and the running losses stay on the GPU; the host
+        synchronises once per epoch for the early-stopping test."""
+        from torch.optim.lr_scheduler import ReduceLROnPlateau
+        x = torch_double_to_float(x)
+        module = self.flow.ensure_cuda()
+        dev = module.raw.device
+        n_samples, n_dim = x.shape
+        if shuffle:
+            rand_indx = torch.randperm(n_samples)
+            x = x[rand_indx.to(x.device)]
+            if weights is not None:
+                weights = weights[rand_indx.to(weights.device)]
+        x = x.to(dev)
+        if weights is not None:
+            weights = weights.to(dev, torch.float32)
+        mean_min_dist = None
+        if noise is not None:
+            # reference quirk (flow.py:241-245): the mean is taken over the LAST row's distances
+            mean_min_dist = torch.mean(torch.linalg.norm(x[-1] - x, dim=1))
+        n_train = int(validation_split * n_samples) if validation_split > 0.0 else n_samples
+        validation = validation_split > 0.0
+        n_valid = n_samples - n_train
+
+        optimizer = torch.optim.AdamW(module.parameters(), learning_rate, weight_decay=weight_decay)
+        scheduler = None
+        if annealing:
+            scheduler = ReduceLROnPlateau(optimizer, mode='min', factor=0.2, patience=patience, threshold=0.0001,
+                                          threshold_mode='abs', min_lr=1e-6)
+        history = dict(loss=[], val_loss=[])
+        monitor = 'val_loss' if validation else 'loss'
+        best_epoch, best_loss = 0, np.inf
+        best_model = module.raw.detach().clone()
+        start = time.time()
+
+        def batch_loss(idx, offset):
+            idx = idx.to(dev) + offset
+            xb = x[idx]
+            if noise is not None:
+                xb = xb + noise * mean_min_dist * torch.randn(xb.shape).to(dev)
+            lp = module().log_prob(xb)
+            if weights is None:
+                loss = -lp.sum()
+            else:
+                wb = weights[idx]
+                loss = (-lp * wb * 1000.0).sum() / wb.sum()
+            if laplace_scale is not None or gaussian_scale is not None:
+                loss = loss - regularization_loss(module, laplace_scale, gaussian_scale)
+            return loss
+
+        for epoch in range(epochs):
+            module.train()
+            train_loss = torch.zeros((), dtype=torch.float64, device=dev)
+            for idx in epoch_batches(n_train, batch_size, shuffle):
+                optimizer.zero_grad(set_to_none=True)
+                loss = batch_loss(idx, 0)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(module.parameters(), clip_grad_norm)
+                optimizer.step()
+                train_loss += loss.detach().double()
+            val_loss = None
+            if validation:
+                module.eval()
+                val_loss = torch.zeros((), dtype=torch.float64, device=dev)
+                with torch.no_grad():       # no graph needed: validation runs on the sweep kernel
+                    for idx in epoch_batches(n_valid, batch_size, shuffle):
+                        val_loss += batch_loss(idx, n_train).double()
+            train_loss = float(train_loss.item()) / n_train          # one sync per epoch
+            history['loss'].append(train_loss)
+            if validation:
+                val_loss = float(val_loss.item()) / n_valid
+                history['val_loss'].append(val_loss)
+            if scheduler is not None:
+                scheduler.step(val_loss if validation else train_loss)
+            if verbose > 1:
+                if validation:
+                    print('Epoch %3d/%3d, train loss: %5.2f, val loss: %5.2f' % (epoch + 1, epochs, train_loss, val_loss))
+                else:
+                    print('Epoch %3d/%3d, train loss: %5.2f' % (epoch + 1, epochs, train_loss))
+            if history[monitor][-1] < best_loss:
+                best_loss, best_epoch = history[monitor][-1], epoch
+                best_model.copy_(module.raw.detach())
+            if epoch - best_epoch >= int(1.5 * patience):
+                with torch.no_grad():
+                    module.raw.copy_(best_model)
+                if verbose > 0:
+                    print('Finished early after %3d epochs' % best_epoch)
+                    print('Best loss achieved %5.2f' % best_loss)
+                break
+        if verbose > 0:
+            total = time.time() - start
+            print()
+            print('Time total:     %5.2f sec' % total)
+            print('Time per epoch: %5.2f sec' % (total / epochs))
+        return history
+
+
+def regularization_loss(model, laplace_scale=None, gaussian_scale=None):
+    """L1 / L2 penalty on the hyper-network weights (flow.py:387-422).  ``model`` is the
+    ``MaskedAutoregressiveFlow``; biases are excluded like the reference's name filter."""
+    total_laplace, total_gaussian = 0.0, 0.0
+    for t in range(model.layout.n_transforms):
+        for w, _ in model.transform_params(t):
+            if laplace_scale is not None:
+                total_laplace = total_laplace + w.abs().sum()
+            if gaussian_scale is not None:
+                total_gaussian = total_gaussian + w.square().sum()
+    total = 0.0
+    if laplace_scale is not None:
+        total = total - total_laplace / laplace_scale
+    if gaussian_scale is not None:
+        total = total - total_gaussian / (2.0 * gaussian_scale ** 2.0)
+    return total

@@ -1,0 +1,278 @@
+"""Vectorised MCMC kernels with the reference's dict-in / dict-out protocol (pocomc/mcmc.py):
+``preconditioned_pcn`` (8-183), ``preconditioned_rwm`` (186-341), ``pcn`` (344-506), ``rwm``
+(508-654).  One implementation drives all four: the particle state stays on the GPU for the whole
+call, every step is a short chain of libpmc_b200 kernels
+(noise -> proposal -> flow pull-back -> reparameterisation -> [host prior / likelihood] ->
+Metropolis update -> scalar adaptation), and only x' / logp' / logl' cross the PCIe bus because the
+user's log_likelihood is a host-side black box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, config
+from .flow import Flow
+
+KIND_TPCN_FLOW, KIND_RWM_FLOW, KIND_TPCN, KIND_RWM = 0, 1, 2, 3
+CTL_SIGMA, CTL_STEP, CTL_BEST, CTL_CNT, CTL_STOP, CTL_ACCEPT, CTL_CALLS, CTL_TRACK, CTL_NACC, CTL_MU = \
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 16
+
+__all__ = ["preconditioned_pcn", "preconditioned_rwm", "pcn", "rwm", "McmcEngine"]
+
+
+def _f64(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+
+class McmcEngine:
+    """Device-resident state + buffers of one ``_mutate`` call."""
+
+    def __init__(self, kind, state_dict, function_dict, option_dict):
+        _lib.require_cuda()
+        self.kind = kind
+        self.use_flow = kind in (KIND_TPCN_FLOW, KIND_RWM_FLOW)
+        self.tp = kind in (KIND_TPCN_FLOW, KIND_TPCN)
+        dev = self.dev = torch.device("cuda", torch.cuda.current_device())
+        # -- state copies (mcmc.py:31-41)
+        x = np.copy(state_dict.get('x'))
+        self.n, self.d = n, d = x.shape
+        self.u = _f64(state_dict.get('u'), dev)
+        self.x = _f64(x, dev)
+        self.logdetj = _f64(state_dict.get('logdetj'), dev)
+        self.logl = _f64(state_dict.get('logl'), dev)
+        self.logp = _f64(state_dict.get('logp'), dev)
+        self.beta = float(state_dict.get('beta'))
+        self.blobs = state_dict.get('blobs')
+        self.have_blobs = self.blobs is not None
+        # -- functions (mcmc.py:44-48)
+        self.log_like = function_dict.get('loglike')
+        self.log_prior = function_dict.get('logprior')
+        self.loglike_device = function_dict.get('loglike_device')
+        self.logprior_device = function_dict.get('logprior_device')
+        self.scaler = function_dict.get('scaler')
+        geometry = function_dict.get('theta_geometry' if self.use_flow else 'u_geometry')
+        self.with_bc = (self.scaler.periodic is not None) or (self.scaler.reflective is not None)
+        # -- options (mcmc.py:51-54)
+        self.n_max = int(option_dict.get('n_max'))
+        self.n_steps = int(option_dict.get('n_steps'))
+        self.progress_bar = option_dict.get('progress_bar')
+        sigma = option_dict.get('proposal_scale')
+        if self.tp:
+            sigma = np.minimum(sigma, 0.99)
+        # -- flow push: theta, logdetj_flow = flow.forward(u) through the f32 shim (mcmc.py:60, tools.py:336-341)
+        self.module = None
+        self.theta = self.ldjf = None
+        if self.use_flow:
+            flow = function_dict.get('flow')
+            if not isinstance(flow, Flow):
+                raise TypeError("pocomc_b200 MCMC kernels need a pocomc_b200.Flow (sm_100a kernels); "
+                                f"got {type(flow).__name__}")
+            self.module = flow.flow.ensure_cuda()
+            self.theta = torch.empty((n, d), dtype=torch.float32, device=dev)
+            self.ldjf = torch.empty(n, dtype=torch.float32, device=dev)
+            self.module.sweep_into(self.u.float(), self.theta, self.ldjf, inverse=False)
+            self.ldjf.neg_()
+        # -- geometry (mcmc.py:63-68 / 237-238)
+        self.nu = 0.0
+        self.inv_t = None
+        mu = np.zeros(d)
+        if self.tp:
+            mu = np.asarray(geometry.t_mean, dtype=np.float64)
+            cov = np.asarray(geometry.t_cov, dtype=np.float64)
+            self.nu = float(geometry.t_nu)
+            self.inv_t = _f64(np.linalg.inv(cov).T, dev)
+            self.chol_t = _f64(np.linalg.cholesky(cov).T, dev)
+        else:
+            self.chol_t = _f64(np.linalg.cholesky(np.asarray(geometry.normal_cov, dtype=np.float64)).T, dev)
+        # -- controller block
+        logl0, logp0, ldj0 = (np.asarray(state_dict.get(k), dtype=np.float64) for k in ('logl', 'logp', 'logdetj'))
+        best = np.mean(logl0 + logp0) if self.tp else np.mean(logl0 + logp0 + ldj0)   # mcmc.py:70 / 243
+        ctl = np.zeros(CTL_MU + d)
+        ctl[CTL_SIGMA], ctl[CTL_BEST] = sigma, best
+        ctl[CTL_MU:] = mu
+        self.ctl = _f64(ctl, dev)
+        self.ctl_host = torch.empty(CTL_MU + d, dtype=torch.float64).pin_memory()
+        # -- per-step buffers
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.g = torch.empty(n, **f64) if self.tp else None
+        self.z = torch.empty((n, d), **f64)
+        self.r = torch.empty(n, **f64)
+        self.prop64 = torch.empty((n, d), **f64)
+        self.prop32 = torch.empty((n, d), dtype=torch.float32, device=dev) if self.use_flow else None
+        self.m_cur = torch.empty(n, **f64) if self.tp else None
+        self.m_prop = torch.empty(n, **f64) if self.tp else None
+        self.u_p32 = torch.empty((n, d), dtype=torch.float32, device=dev) if self.use_flow else None
+        self.ldjf_p = torch.empty(n, dtype=torch.float32, device=dev) if self.use_flow else None
+        self.u_p = torch.empty((n, d), **f64)
+        self.x_p = torch.empty((n, d), **f64)
+        self.ldj_p = torch.empty(n, **f64)
+        self.finite = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.logl_p = torch.empty(n, **f64)
+        self.logp_p = torch.empty(n, **f64)
+        self.alpha = torch.empty(n, **f64)
+        self.partials = torch.empty(int(_lib.load().pmc_mh_partials_size(n, d)), **f64)
+        # pinned staging
+        self.h_x = torch.empty((n, d), dtype=torch.float64).pin_memory()
+        self.h_fin = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self.h_ll = torch.empty((2, n), dtype=torch.float64).pin_memory()
+        self.h_noise = torch.empty(n * (d + 2), dtype=torch.float64).pin_memory() if config.rng_mode == "host" else None
+        self.rng_mode = config.rng_mode
+        self.mean_mode = config.resolved_mean_mode()
+        self.seed = int(np.random.randint(0, 2 ** 62)) if self.rng_mode == "device" else 0
+        self.n_calls = 0
+        self.step = 0
+        self.sigma = float(sigma)
+        self.accept = 0.0
+        self.stop = False
+        self.sc, self._sc_keep, _ = self.scaler._params(True)
+        if self.with_bc and self._sc_keep["bc"] is not None:
+            self.sc.bc = _lib.ptr(self._sc_keep["bc"])
+
+    # -- one step ---------------------------------------------------------------------------------
+    def draw_noise(self):
+        """N gammas then N*D normals (mcmc.py:80,85 / 253), host stream or Philox."""
+        n, d = self.n, self.d
+        if self.rng_mode == "host":
+            hn = self.h_noise.numpy()
+            if self.tp:
+                hn[:n] = np.random.standard_gamma((d + self.nu) / 2, size=n)   # == gamma(a, s_k)/s_k draw for draw
+                self.g.copy_(self.h_noise[:n], non_blocking=True)
+            hn[n:n + n * d] = np.random.randn(n, d).reshape(-1)
+            self.z.copy_(self.h_noise[n:n + n * d].view(n, d), non_blocking=True)
+        else:
+            _lib.call("pmc_rng_fill", C.c_uint64(self.seed), C.c_uint64(self.step + 1), 0,
+                      (d + self.nu) / 2 if self.tp else 0.0, _lib.ptr(self.g), _lib.ptr(self.z), _lib.ptr(self.r), n, d)
+
+    def propose(self):
+        n, d = self.n, self.d
+        pos = self.theta if self.use_flow else self.u
+        if self.tp:
+            _lib.call("pmc_tpcn_propose", 1 if self.use_flow else 0, _lib.ptr(pos), _lib.ptr(self.ctl),
+                      _lib.ptr(self.inv_t), _lib.ptr(self.chol_t), self.nu, _lib.ptr(self.g), _lib.ptr(self.z),
+                      _lib.ptr(self.prop64), _lib.ptr(self.prop32), _lib.ptr(self.m_cur), _lib.ptr(self.m_prop), n, d)
+        else:
+            _lib.call("pmc_rwm_propose", 1 if self.use_flow else 0, _lib.ptr(pos), _lib.ptr(self.ctl),
+                      _lib.ptr(self.chol_t), _lib.ptr(self.z), _lib.ptr(self.prop64), _lib.ptr(self.prop32), n, d)
+
+    def pull_back(self):
+        """theta' -> u' (flow.inverse, mcmc.py:88) -> x', logdetj' (+ boundary conditions, :91-97)."""
+        n, d = self.n, self.d
+        if self.use_flow:
+            self.module.sweep_into(self.prop32, self.u_p32, self.ldjf_p, inverse=True)
+            src, is32 = self.u_p32, 1
+        else:
+            src, is32 = self.prop64, 0
+        _lib.call("pmc_scaler_inverse", is32, _lib.ptr(src), C.byref(self.sc), _lib.ptr(self.u_p), _lib.ptr(self.x_p),
+                  _lib.ptr(self.ldj_p), _lib.ptr(self.finite), n, d)
+
+    def evaluate_host(self):
+        """Host black boxes on the finite rows only (mcmc.py:100-121)."""
+        n = self.n
+        self.h_x.copy_(self.x_p, non_blocking=True)
+        self.h_fin.copy_(self.finite, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        x_p = self.h_x.numpy()
+        mask = self.h_fin.numpy().astype(bool)
+        logp_p = np.full(n, -np.inf)
+        logp_p[mask] = self.log_prior(x_p[mask])
+        mask = mask & np.isfinite(logp_p)
+        logl_p = np.full(n, -np.inf)
+        blobs_p = None
+        if self.have_blobs:
+            blobs_p = np.empty(n, dtype=np.dtype((self.blobs[0].dtype, self.blobs[0].shape)))
+            logl_p[mask], blobs_p[mask] = self.log_like(x_p[mask])
+        else:
+            logl_p[mask], _ = self.log_like(x_p[mask])
+        calls = int(np.sum(mask))
+        hl = self.h_ll.numpy()
+        hl[0], hl[1] = logl_p, logp_p
+        self.logl_p.copy_(self.h_ll[0], non_blocking=True)
+        self.logp_p.copy_(self.h_ll[1], non_blocking=True)
+        return calls, blobs_p
+
+    def evaluate_device(self):
+        """Opt-in device prior / likelihood (synthetic benchmarks): no PCIe traffic."""
+        self.logprior_device(self.x_p, self.finite, self.logp_p)
+        self.loglike_device(self.x_p, self.finite, self.logl_p)
+        return None, None
+
+    def accept_and_adapt(self, calls):
+        n, d = self.n, self.d
+        if self.rng_mode == "host":
+            hn = self.h_noise.numpy()
+            hn[n + n * d:] = np.random.rand(n)                                   # mcmc.py:137
+            self.r.copy_(self.h_noise[n + n * d:], non_blocking=True)
+        _lib.call("pmc_mh_accept_update", self.kind, self.beta, self.nu, _lib.ptr(self.theta), _lib.ptr(self.u),
+                  _lib.ptr(self.x), _lib.ptr(self.logdetj), _lib.ptr(self.logl), _lib.ptr(self.logp), _lib.ptr(self.ldjf),
+                  _lib.ptr(self.prop64), _lib.ptr(self.u_p), _lib.ptr(self.x_p), _lib.ptr(self.ldj_p),
+                  _lib.ptr(self.logl_p), _lib.ptr(self.logp_p), _lib.ptr(self.ldjf_p), _lib.ptr(self.m_cur),
+                  _lib.ptr(self.m_prop), _lib.ptr(self.r), _lib.ptr(self.finite) if calls is None else None,
+                  _lib.ptr(self.alpha), _lib.ptr(self.partials), n, d)
+        _lib.call("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(self.partials), _lib.ptr(self.theta),
+                  self.mean_mode, self.n_steps, self.n_max, n, d)
+
+    def read_controller(self):
+        self.ctl_host.copy_(self.ctl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        c = self.ctl_host.numpy()
+        self.sigma, self.accept = float(c[CTL_SIGMA]), float(c[CTL_ACCEPT])
+        self.step, self.stop = int(c[CTL_STEP]), bool(c[CTL_STOP] != 0.0)
+        return c
+
+    def run(self):
+        device_eval = self.loglike_device is not None and self.logprior_device is not None and not self.have_blobs
+        while True:
+            self.draw_noise()
+            self.propose()
+            self.pull_back()
+            if device_eval:
+                calls, blobs_p = self.evaluate_device()
+            else:
+                calls, blobs_p = self.evaluate_host()
+                self.n_calls += calls
+            self.accept_and_adapt(calls)
+            c = self.read_controller()
+            if device_eval:
+                step_calls = int(c[CTL_CALLS]) - self.n_calls
+                self.n_calls = int(c[CTL_CALLS])
+            else:
+                step_calls = calls
+            if self.have_blobs:
+                acc = (self.r < self.alpha).cpu().numpy()
+                self.blobs[acc] = blobs_p[acc]                                   # mcmc.py:148-149
+            if self.progress_bar is not None:                                    # mcmc.py:159-167
+                self.progress_bar.update_stats(dict(
+                    calls=self.progress_bar.info['calls'] + step_calls, acc=self.accept, steps=self.step,
+                    logP=float(c[CTL_TRACK]) if self.tp else float((self.logl + self.logp).mean().item()),
+                    eff=self.sigma / (2.38 / np.sqrt(self.d))))
+            if self.stop:
+                break
+        return dict(u=self.u.cpu().numpy(), x=self.x.cpu().numpy(), logdetj=self.logdetj.cpu().numpy(),
+                    logl=self.logl.cpu().numpy(), logp=self.logp.cpu().numpy(), blobs=self.blobs,
+                    efficiency=self.sigma, accept=self.accept, steps=self.step, calls=self.n_calls,
+                    proposal_scale=self.sigma)
+
+
+@torch.no_grad()
+def preconditioned_pcn(state_dict: dict, function_dict: dict, option_dict: dict):
+    """Doubly preconditioned Crank-Nicolson in flow-latent space (mcmc.py:8-183)."""
+    return McmcEngine(KIND_TPCN_FLOW, state_dict, function_dict, option_dict).run()
+
+
+@torch.no_grad()
+def preconditioned_rwm(state_dict: dict, function_dict: dict, option_dict: dict):
+    """Preconditioned random-walk Metropolis in flow-latent space (mcmc.py:186-341)."""
+    return McmcEngine(KIND_RWM_FLOW, state_dict, function_dict, option_dict).run()
+
+
+def pcn(state_dict: dict, function_dict: dict, option_dict: dict):
+    """t-preconditioned Crank-Nicolson in u space (mcmc.py:344-506)."""
+    return McmcEngine(KIND_TPCN, state_dict, function_dict, option_dict).run()
+
+
+def rwm(state_dict: dict, function_dict: dict, option_dict: dict):
+    """Random-walk Metropolis in u space (mcmc.py:508-654)."""
+    return McmcEngine(KIND_RWM, state_dict, function_dict, option_dict).run()

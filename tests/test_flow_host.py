@@ -1,0 +1,46 @@
+"""CPU: host-side logic of pocomc_b200.flow that needs no device."""
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+import flow_ref as F
+from pocomc_b200.flow import Flow, epoch_batches
+
+
+@pytest.mark.parametrize("preset,d", [("maf3", 4), ("nsf6", 7), ("maf12", 2)])
+def test_init_matches_zuko_rng_order(preset, d):
+    """Same torch seed -> same initial weights as constructing the zuko flow."""
+    torch.manual_seed(123)
+    ref = F.make_flow(d, preset)
+    torch.manual_seed(123)
+    mine = Flow(d, preset)
+    flat = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+    assert torch.equal(flat, mine.flow.raw.detach().cpu())
+    # and the generator is left in the same state
+    assert torch.equal(torch.rand(3), (torch.manual_seed(123), F.make_flow(d, preset), torch.rand(3))[2])
+
+
+def test_invalid_flow_name():
+    with pytest.raises(ValueError):
+        Flow(4, "realnvp")
+    with pytest.raises(ValueError):
+        Flow(1, "maf3")           # 1-D autoregressive net has a null Jacobian (zuko raises too)
+
+
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_epoch_batches_replicates_dataloader(shuffle):
+    n, bs = 103, 16
+    data = torch.arange(n)
+    torch.manual_seed(5)
+    dl = DataLoader(TensorDataset(data), bs, shuffle)
+    ref = [[b[0] for b in dl] for _ in range(3)]
+    after_ref = torch.rand(2)
+    torch.manual_seed(5)
+    mine = [epoch_batches(n, bs, shuffle) for _ in range(3)]
+    after = torch.rand(2)
+    for e_ref, e in zip(ref, mine):
+        assert len(e_ref) == len(e)
+        for a, b in zip(e_ref, e):
+            assert torch.equal(a, b)
+    assert torch.equal(after_ref, after)

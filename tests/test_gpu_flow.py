@@ -1,0 +1,134 @@
+"""GPU parity: the sm_100a flow sweep kernels (through the C-ABI) against the zuko oracle and the
+golden vectors recorded from the reference's Flow wrapper.  fp32 tolerance: 2e-5 abs/rel for
+maf, 2e-4 for nsf (spline knots amplify rounding), stated per assert."""
+import numpy as np
+import pytest
+import torch
+
+import flow_ref as F
+from conftest import flow_param_list
+
+pytestmark = pytest.mark.gpu
+
+
+def _mine(preset, d, params):
+    from pocomc_b200.flow import Flow
+    f = Flow(d, preset)
+    flat = np.concatenate([np.asarray(p).reshape(-1) for p in params])
+    with torch.no_grad():
+        f.flow.raw.copy_(torch.from_numpy(flat).to(f.flow.raw.device))
+    return f
+
+
+@pytest.mark.parametrize("preset,d", [("maf3", 4), ("nsf3", 5), ("maf6", 10)])
+def test_flow_matches_reference_wrapper_goldens(golden, preset, d):
+    g = golden("flow")
+    pre = preset + "_"
+    f = _mine(preset, d, flow_param_list(g, pre))
+    tol = dict(rtol=2e-5, atol=2e-5) if preset.startswith("maf") else dict(rtol=2e-4, atol=2e-4)
+    x = torch.tensor(g[pre + "x"])
+    with torch.no_grad():
+        z, ladj = f.forward(x)
+        xi, li = f.inverse(x)
+        lp = f.log_prob(x)
+    assert z.device == x.device and z.dtype == torch.float32
+    np.testing.assert_allclose(z.numpy(), g[pre + "z"], **tol)
+    np.testing.assert_allclose(ladj.numpy(), g[pre + "ladj"], **tol)
+    np.testing.assert_allclose(xi.numpy(), g[pre + "inv_x"], **tol)
+    np.testing.assert_allclose(li.numpy(), g[pre + "inv_ladj"], **tol)
+    np.testing.assert_allclose(lp.numpy(), g[pre + "logprob"], **tol)
+    # Flow.sample consumes the same host normals as zuko's base.rsample
+    torch.manual_seed(8)
+    with torch.no_grad():
+        xs, lq = f.sample(32)
+    np.testing.assert_allclose(xs.numpy(), g[pre + "sample_x"], **tol)
+    np.testing.assert_allclose(lq.numpy(), g[pre + "sample_logq"], **tol)
+
+
+@pytest.mark.parametrize("preset,d,n", [("maf6", 32, 1000), ("nsf6", 10, 257), ("maf3", 2, 33), ("nsf3", 3, 1),
+                                        ("maf12", 50, 300), ("maf6", 100, 64), ("nsf6", 32, 500)])
+def test_sweep_vs_oracle_sizes(preset, d, n):
+    """every lanes-per-particle variant / ragged tile / big-H case against the oracle's D+1-pass inverse"""
+    torch.manual_seed(d * 7 + n)
+    ref = F.make_flow(d, preset)
+    f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
+    x = torch.randn(n, d)
+    with torch.no_grad():
+        z_ref, l_ref = ref().transform.call_and_ladj(x)
+        xi_ref, li_ref = ref().transform.inv.call_and_ladj(z_ref)
+        z, l = f.forward(x)
+        xi, li = f.inverse(z_ref)
+    tol = dict(rtol=5e-5, atol=5e-5) if preset.startswith("maf") else dict(rtol=5e-4, atol=5e-4)
+    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **tol)
+    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), **tol)
+    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), **tol)
+    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **tol)
+
+
+def test_flow_properties_like_reference_tests():
+    """reference tests/test_flow.py: round trip 1e-5, ladj antisymmetry, f64 warning, 1-row batch, fit stays finite"""
+    from pocomc_b200.flow import Flow
+    torch.manual_seed(0)
+    x = torch.randn(100, 4) * 1.5
+    f = Flow(4, "maf3")
+    with torch.no_grad():
+        z, ladj = f.forward(x)
+        xr, li = f.inverse(z)
+    assert torch.allclose(x, xr, atol=1e-5)
+    torch.testing.assert_close(ladj, -li, atol=1e-5, rtol=1e-5)
+    with pytest.warns(UserWarning):
+        lp = f.log_prob(x.double())
+    assert lp.dtype == torch.float32 and lp.shape == (100,) and torch.isfinite(lp).all()
+    with pytest.raises(ValueError):
+        f.forward(x.to(torch.int64))
+    with torch.no_grad():
+        z1, l1 = f.forward(x[:1])
+    assert z1.shape == (1, 4) and l1.shape == (1,)
+    # every parameter receives a gradient through log_prob (test_flow.py:136-150)
+    f.flow.zero_grad()
+    f.log_prob(x).sum().backward()
+    g = f.flow.raw.grad
+    assert g is not None and torch.isfinite(g).all()
+    hist = f.fit(x, epochs=5)
+    assert len(hist["loss"]) == 5
+    with torch.no_grad():
+        z, _ = f.forward(x)
+        s, lq = f.sample(10)
+    assert torch.isfinite(z).all() and torch.isfinite(s).all() and torch.isfinite(lq).all()
+
+
+@pytest.mark.parametrize("preset,d", [("maf3", 4), ("nsf3", 6)])
+def test_autograd_path_matches_oracle_gradients(preset, d):
+    torch.manual_seed(3)
+    ref = F.make_flow(d, preset)
+    f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
+    x = torch.randn(64, d)
+    lp_ref = ref().log_prob(x)
+    lp_ref.sum().backward()
+    gref = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    lp = f.log_prob(x)
+    lp.sum().backward()
+    np.testing.assert_allclose(lp.detach().cpu().numpy(), lp_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(f.flow.raw.grad.cpu().numpy(), gref.numpy(), rtol=1e-3, atol=1e-3)
+    # masked weight entries never receive gradient
+    with torch.no_grad():
+        z_sweep, l_sweep = f.forward(x)
+    z_auto, l_auto = f.flow.forward_autograd(x)
+    np.testing.assert_allclose(z_sweep.numpy(), z_auto.detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("tag", ["w", "nw"])
+def test_fit_matches_reference_history(golden, tag):
+    """Flow.fit against the loss history / final weights the reference produced from the same
+    initial weights, data and torch seed (flow.py:165-384)."""
+    from pocomc_b200.flow import Flow
+    g = golden("flow_fit")
+    f = _mine("maf3", 4, flow_param_list(g, f"{tag}_init_"))
+    w = torch.tensor(g["w"]) if tag == "w" else None
+    torch.manual_seed(14)
+    hist = f.fit(torch.tensor(g["data"]), weights=w, validation_split=0.5, epochs=4, batch_size=64, patience=4,
+                 annealing=False, shuffle=True, clip_grad_norm=1.0)
+    np.testing.assert_allclose(hist["loss"], g[f"{tag}_loss"], rtol=2e-4)
+    np.testing.assert_allclose(hist["val_loss"], g[f"{tag}_val_loss"], rtol=2e-4)
+    final = np.concatenate([p.reshape(-1) for p in flow_param_list(g, f"{tag}_final_")])
+    np.testing.assert_allclose(f.flow.raw.detach().cpu().numpy(), final, rtol=2e-2, atol=2e-4)

@@ -1,0 +1,70 @@
+"""GPU parity: Reparameterize kernels vs vectors recorded from the reference's scaler.py (f64, 1e-12)."""
+import numpy as np
+import pytest
+
+import smc_ref as O
+
+pytestmark = pytest.mark.gpu
+F64 = dict(rtol=1e-12, atol=1e-12)
+
+
+def _mk(g, tr, **kw):
+    from pocomc_b200.scaler import Reparameterize
+    s = Reparameterize(len(g["low"]), bounds=np.stack([g["low"], g["high"]], 1), transform=tr, **kw)
+    return s
+
+
+@pytest.mark.parametrize("tr", ["probit", "logit"])
+def test_scaler_matches_reference(golden, tr):
+    g = golden("scaler")
+    s = _mk(g, tr)
+    s.fit(g["x"])
+    np.testing.assert_allclose(s.mu, g[f"{tr}_mu"], **F64)
+    np.testing.assert_allclose(s.sigma, g[f"{tr}_sigma"], **F64)
+    s.mu, s.sigma = g[f"{tr}_mu"], g[f"{tr}_sigma"]
+    np.testing.assert_allclose(s.forward(g["x"]), g[f"{tr}_fwd"], **F64)
+    x, ld = s.inverse(g["u_probe"])
+    np.testing.assert_allclose(x, g[f"{tr}_inv_x"], **F64)
+    np.testing.assert_allclose(ld, g[f"{tr}_inv_logdet"], **F64)
+    x32, ld32 = s.inverse(g["u_probe"].astype(np.float32))
+    np.testing.assert_allclose(x32, g[f"{tr}_inv32_x"], **F64)
+    np.testing.assert_allclose(ld32, g[f"{tr}_inv32_logdet"], **F64)
+    xr, _ = s.inverse(s.forward(g["x"]))
+    np.testing.assert_allclose(xr, g["x"], rtol=1e-9, atol=1e-9)
+
+
+def test_boundary_conditions_and_errors(golden):
+    g = golden("scaler")
+    s = _mk(g, "probit", periodic=[3], reflective=[4])
+    np.testing.assert_allclose(s.apply_boundary_conditions_x(g["bc_in"]), g["bc_out"], rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        bad = g["x"].copy()
+        bad[0, 3] = 99.0
+        s.fit(bad)
+    # fused wrap + re-forward + re-inverse used inside the MCMC step (mcmc.py:94-97) vs the oracle
+    import torch
+    s.fit(g["x"])
+    p = O.ScalerParams(g["low"], g["high"], s.mu, s.sigma)
+    u = g["u_probe"][4:] * 1.5
+    x0, _ = O.scaler_inverse(u, p)
+    xb = O.apply_boundary_conditions(x0, p, [3], [4])
+    ub = O.scaler_forward(xb, p)
+    xo, ldo = O.scaler_inverse(ub, p)
+    u_out, x, ld, fin = s.inverse_device(torch.from_numpy(u).cuda(), with_bc=True)
+    np.testing.assert_allclose(u_out.cpu().numpy(), ub, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(x.cpu().numpy(), xo, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(ld.cpu().numpy(), ldo, rtol=1e-11, atol=1e-11)
+    np.testing.assert_array_equal(fin.cpu().numpy().astype(bool), np.isfinite(ldo) & np.isfinite(xo).all(1))
+
+
+def test_scaler_kats():
+    from pocomc_b200.scaler import Reparameterize
+    s = Reparameterize(3, bounds=np.array([[0, 1], [0, np.inf], [-np.inf, np.inf]], dtype=float))
+    s.mu, s.sigma = np.zeros(3), np.array([1, 2, .5])
+    x, ld = s.inverse(np.array([[0., 0, 0], [1, -1, 2]]))
+    np.testing.assert_allclose(x, [[0.5, 1, 0], [0.8413447460685429, 0.1353352832366127, 1]], rtol=1e-14)
+    np.testing.assert_allclose(ld, [-0.9189385332046727, -3.4189385332046727], rtol=1e-14)
+    np.testing.assert_allclose(s.forward(x), [[0., 0, 0], [1, -1, 2]], atol=1e-12)
+    # empty batch
+    x, ld = s.inverse(np.zeros((0, 3)))
+    assert x.shape == (0, 3) and ld.shape == (0,)
