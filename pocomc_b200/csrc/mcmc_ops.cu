@@ -510,9 +510,9 @@ extern "C" int pmc_rwm_propose(int32_t pos_is_f32, const void* pos, const double
 
 extern "C" int pmc_scaler_inverse(int32_t u_is_f32, const void* u_in, const pmc_scaler* sc, double* u_out, double* x,
                                   double* logdetj, uint8_t* finite, int64_t n, int32_t d, pmc_stream_t stream) {
+  if (n == 0) return 0;   // empty batch: torch hands out null data pointers for 0-element tensors
   PMC_REQUIRE(u_in && sc && u_out && x && logdetj && finite, "pmc_scaler_inverse: null pointer");
   PMC_REQUIRE(sc->kind && sc->low && sc->high && (!sc->scale || (sc->mu && sc->sigma)), "pmc_scaler_inverse: incomplete scaler");
-  if (n == 0) return 0;
   const int blocks = grid_for(n, 8, 8);
   if (u_is_f32)
     scaler_inverse_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((const float*)u_in, *sc, u_out, x, logdetj, finite, n, d);
@@ -524,8 +524,8 @@ extern "C" int pmc_scaler_inverse(int32_t u_is_f32, const void* u_in, const pmc_
 
 extern "C" int pmc_scaler_forward(const double* x, const pmc_scaler* sc, double* u, int64_t n, int32_t d,
                                   pmc_stream_t stream) {
-  PMC_REQUIRE(x && sc && u, "pmc_scaler_forward: null pointer");
   if (n == 0) return 0;
+  PMC_REQUIRE(x && sc && u, "pmc_scaler_forward: null pointer");
   const int blocks = grid_for(n * d, 256, 8);
   scaler_forward_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, *sc, u, n * (long long)d, d);
   PMC_LAUNCH_CHECK();
@@ -535,8 +535,8 @@ extern "C" int pmc_scaler_forward(const double* x, const pmc_scaler* sc, double*
 
 extern "C" int pmc_apply_bc(double* x, const int32_t* bc, const double* low, const double* high, int64_t n, int32_t d,
                             pmc_stream_t stream) {
-  PMC_REQUIRE(x && bc && low && high, "pmc_apply_bc: null pointer");
   if (n == 0) return 0;
+  PMC_REQUIRE(x && bc && low && high, "pmc_apply_bc: null pointer");
   apply_bc_kernel<<<grid_for(n * d, 256, 8), 256, 0, as_stream(stream)>>>(x, bc, low, high, n * (long long)d, d);
   PMC_LAUNCH_CHECK();
   return 0;

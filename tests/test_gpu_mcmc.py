@@ -96,14 +96,15 @@ def test_single_step_operators_vs_oracle(golden):
     prop = torch.empty((n, d), dtype=torch.float64, device=dev)
     m_cur = torch.empty(n, dtype=torch.float64, device=dev); m_prop = torch.empty_like(m_cur)
     u_d, g_d, z_d = t(g["u"]), t(gg), t(zz)
-    _lib.call("pmc_tpcn_propose", 0, _lib.ptr(u_d), _lib.ptr(ctl_d), _lib.ptr(t(inv.T)), _lib.ptr(t(chol.T)), nu,
+    inv_d, chol_d = t(inv.T), t(chol.T)          # keep the device copies alive across the async launch
+    _lib.call("pmc_tpcn_propose", 0, _lib.ptr(u_d), _lib.ptr(ctl_d), _lib.ptr(inv_d), _lib.ptr(chol_d), nu,
               _lib.ptr(g_d), _lib.ptr(z_d), _lib.ptr(prop), None, _lib.ptr(m_cur), _lib.ptr(m_prop), n, d)
     np.testing.assert_allclose(prop.cpu().numpy(), prop_ref, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(m_cur.cpu().numpy(), m_ref, rtol=1e-12)
     np.testing.assert_allclose(m_prop.cpu().numpy(), mp_ref, rtol=1e-12)
     # rwm proposal
     pr = torch.empty_like(prop)
-    _lib.call("pmc_rwm_propose", 0, _lib.ptr(u_d), _lib.ptr(ctl_d), _lib.ptr(t(chol.T)), _lib.ptr(z_d), _lib.ptr(pr), None, n, d)
+    _lib.call("pmc_rwm_propose", 0, _lib.ptr(u_d), _lib.ptr(ctl_d), _lib.ptr(chol_d), _lib.ptr(z_d), _lib.ptr(pr), None, n, d)
     np.testing.assert_allclose(pr.cpu().numpy(), O.rwm_propose(g["u"], chol, sigma, zz), rtol=1e-12, atol=1e-12)
     # Metropolis update with made-up primed scalars incl. -inf / nan cases
     rng = np.random.default_rng(0)
@@ -118,10 +119,11 @@ def test_single_step_operators_vs_oracle(golden):
     st = {k: t(g[k]) for k in ("u", "x", "logdetj", "logl", "logp")}
     parts = torch.zeros(int(_lib.load().pmc_mh_partials_size(n, d)), dtype=torch.float64, device=dev)
     alpha = torch.empty(n, dtype=torch.float64, device=dev)
+    xp_d, ldjp_d, llp_d, lpp_d, rr_d = t(x_p), t(ldj_p), t(logl_p), t(logp_p), t(rr)
     _lib.call("pmc_mh_accept_update", 2, beta, nu, None, _lib.ptr(st["u"]), _lib.ptr(st["x"]), _lib.ptr(st["logdetj"]),
-              _lib.ptr(st["logl"]), _lib.ptr(st["logp"]), None, _lib.ptr(prop), _lib.ptr(prop), _lib.ptr(t(x_p)),
-              _lib.ptr(t(ldj_p)), _lib.ptr(t(logl_p)), _lib.ptr(t(logp_p)), None, _lib.ptr(m_cur), _lib.ptr(m_prop),
-              _lib.ptr(t(rr)), None, _lib.ptr(alpha), _lib.ptr(parts), n, d)
+              _lib.ptr(st["logl"]), _lib.ptr(st["logp"]), None, _lib.ptr(prop), _lib.ptr(prop), _lib.ptr(xp_d),
+              _lib.ptr(ldjp_d), _lib.ptr(llp_d), _lib.ptr(lpp_d), None, _lib.ptr(m_cur), _lib.ptr(m_prop),
+              _lib.ptr(rr_d), None, _lib.ptr(alpha), _lib.ptr(parts), n, d)
     np.testing.assert_allclose(alpha.cpu().numpy(), alpha_ref, rtol=1e-11, atol=1e-300)
     exp_x = np.where(acc[:, None], x_p, g["x"])
     np.testing.assert_array_equal(st["x"].cpu().numpy(), exp_x)

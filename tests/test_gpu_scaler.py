@@ -51,9 +51,17 @@ def test_boundary_conditions_and_errors(golden):
     ub = O.scaler_forward(xb, p)
     xo, ldo = O.scaler_inverse(ub, p)
     u_out, x, ld, fin = s.inverse_device(torch.from_numpy(u).cuda(), with_bc=True)
-    np.testing.assert_allclose(u_out.cpu().numpy(), ub, rtol=1e-11, atol=1e-11)
+    # the reference's re-forward goes through erfinv(2p-1) with p = (erf(v/sqrt2)+1)/2, which is
+    # ill-conditioned in the tails (1 ulp of erf at |v| ~ 7 moves v by ~1e-6): tail elements are
+    # compared at 1e-5, everything else at 1e-11
+    tail = np.abs(ub * s.sigma + s.mu) > 5.0
+    got_u = u_out.cpu().numpy()
+    np.testing.assert_allclose(got_u[~tail], ub[~tail], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(got_u[tail], ub[tail], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(x.cpu().numpy(), xo, rtol=1e-11, atol=1e-11)
-    np.testing.assert_allclose(ld.cpu().numpy(), ldo, rtol=1e-11, atol=1e-11)
+    tail_row = tail.any(axis=1)
+    np.testing.assert_allclose(ld.cpu().numpy()[~tail_row], ldo[~tail_row], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(ld.cpu().numpy()[tail_row], ldo[tail_row], rtol=1e-4, atol=1e-4)
     np.testing.assert_array_equal(fin.cpu().numpy().astype(bool), np.isfinite(ldo) & np.isfinite(xo).all(1))
 
 
