@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of pocoMC's flow-preconditioned MCMC hot path (BASELINE.json).
+
+Workload (configs[1]): 32-D correlated Gaussian likelihood
+(C = 0.95 11^T + 0.05 I), prior N(0, 3^2)^32, n_active = 10 000 particles per GPU, flow 'maf6'
+(H = 128) trained for 200 optimiser steps, Student-t geometry fitted on the latent cloud, beta = 1.
+One bench "step" = one `_mutate`-sized call of the t-preconditioned Crank-Nicolson kernel
+(pocomc/mcmc.py:8-183): MCMC_STEPS Metropolis steps over every particle with the plateau rule
+disabled.  particle-steps/s = particles x MCMC steps / time.
+
+  value : device-resident arm -- state in HBM, Philox noise and the synthetic prior/likelihood
+          evaluated on the GPU, no host traffic inside the timed region.
+  e2e   : the reference-facing call `pocomc_b200.mcmc.preconditioned_pcn(state_dict, function_dict,
+          option_dict)` with HOST numpy buffers, the likelihood and the scipy prior as host black
+          boxes (x' D2H and logl'/logp' H2D every MCMC step), state H2D and result D2H per call.
+  --impl reference : the reference's own CPU path for the same call.  pocoMC is pure Python and
+          needs the third-party zuko (absent here and on the GPU box), so the arm runs the in-repo
+          CPU oracle port (oracle/smc_ref.py + oracle/zuko) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 10_000
+N_DIM = 32
+FLOW = "maf6"
+MCMC_STEPS = 50          # Metropolis steps per bench step (n_max of SURVEY 8d-2)
+REF_MCMC_STEPS = 1       # bounded sample for the CPU arms (one step is ~seconds on a CPU)
+TRAIN_EPOCHS = 20        # x 10 batches of 512 (train split = 5000 rows) = 200 optimiser steps
+L2_FLUSH_BYTES = 256 << 20
+
+
+# ---------------------------------------------------------------------------------------------
+# workload (numpy / scipy only: shared by every arm)
+# ---------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, n, d, seed=0, row_offset=0):
+        from scipy.stats import norm
+        self.n, self.d = n, d
+        self.cov = 0.95 * np.ones((d, d)) + 0.05 * np.eye(d)
+        self.prec = np.linalg.inv(self.cov)
+        self.c0 = -0.5 * (d * math.log(2 * math.pi) + np.linalg.slogdet(self.cov)[1])
+        self.prior_sd = 3.0
+        self.dists = [norm(0.0, self.prior_sd)] * d
+        rng = np.random.default_rng(seed)
+        self.prior_samples = rng.normal(0.0, self.prior_sd, size=(2 * N_PER_GPU, d))     # scaler.fit input (same on all ranks)
+        chol = np.linalg.cholesky(self.cov)
+        rng_x = np.random.default_rng([seed, 1, row_offset])
+        self.x0 = rng_x.normal(size=(n, d)) @ chol.T
+        self.bounds = np.array([dd.support() for dd in self.dists])
+
+    def loglike(self, x):
+        return -0.5 * np.einsum("ki,ij,kj->k", x, self.prec, x) + self.c0
+
+    def logprior(self, x):
+        out = np.zeros(len(x))
+        for i, dd in enumerate(self.dists):
+            out += dd.logpdf(x[:, i])
+        return out
+
+
+def clocks_sampler(stop_evt, out):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                              "-i", os.environ.get("LOCAL_RANK", "0")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop_evt.wait()
+    p.terminate()
+    t.join(timeout=2)
+
+
+def summarise_clocks(lines):
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [s.strip() for s in ln.split(",")]
+        if len(f) < 9:
+            continue
+        try:
+            sm.append(float(f[1])); mx.append(float(f[2]))
+        except ValueError:
+            continue
+        for name, v in zip(names, f[5:9]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_problem(wl, flow_params=None, threads=None):
+    """Build the CPU-side problem with the oracle (test infrastructure used as the timed CPU baseline)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import flow_ref as F
+    import smc_ref as O
+    if threads:
+        torch.set_num_threads(threads)
+    scaler = O.scaler_fit(wl.prior_samples, wl.bounds[:, 0], wl.bounds[:, 1])
+    u0 = O.scaler_forward(wl.x0, scaler)
+    _, ldj0 = O.scaler_inverse(u0, scaler)
+    torch.manual_seed(0)
+    flow = F.make_flow(wl.d, FLOW)
+    if flow_params is not None:
+        F.load_params(flow, flow_params)
+    else:
+        F.fit(flow, torch.tensor(u0, dtype=torch.float32), validation_split=0.5, epochs=TRAIN_EPOCHS, batch_size=512,
+              patience=10 ** 6)
+    nf = F.NumpyFlow(flow)
+    theta0, _ = nf.forward(u0)
+    t_mean, t_cov, t_nu = O.fit_mvstud(theta0.astype(np.float64))
+    if not np.isfinite(t_nu):
+        t_nu = 1e6
+    geo = dict(t_mean=t_mean, t_cov=t_cov, t_nu=t_nu)
+    state = dict(u=u0, x=wl.x0, logdetj=ldj0, logl=wl.loglike(wl.x0), logp=wl.logprior(wl.x0), beta=1.0)
+    return O, nf, scaler, geo, state
+
+
+def cpu_steps(O, nf, scaler, geo, state, wl, mcmc_steps):
+    t0 = time.perf_counter()
+    res = O.mcmc_kernel("tpcn_flow", state, wl.loglike, wl.logprior, scaler, geo,
+                        dict(n_max=mcmc_steps, n_steps=10 ** 9, proposal_scale=2.38 / wl.d ** 0.5), flow=nf)
+    dt = time.perf_counter() - t0
+    assert res["steps"] == mcmc_steps
+    return dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    wl = Workload(N_PER_GPU, N_DIM)
+    np.random.seed(0)
+    prob = cpu_problem(wl, threads=threads)
+    for _ in range(args.warmup):
+        cpu_steps(*prob, wl, REF_MCMC_STEPS)
+    times = [cpu_steps(*prob, wl, REF_MCMC_STEPS) for _ in range(args.steps)]
+    total = float(np.sum(times))
+    value = wl.n * REF_MCMC_STEPS * args.steps / total
+    sample = f"{REF_MCMC_STEPS} tpCN step(s) x {wl.n} particles per bench step (oracle port of mcmc.py:8-183 + zuko MAF inverse)"
+    line = dict(impl="reference", metric="particle-steps/sec", value=value, unit="particle-steps/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32 flow / f64 SMC state", data="synthetic",
+                config=workload_config(1, REF_MCMC_STEPS),
+                cpu_baseline=dict(value=value, unit="particle-steps/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit="particle-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, mcmc_steps):
+    return {"workload": f"{N_DIM}-D correlated Gaussian, n_particles={N_PER_GPU} per GPU, flow-precond MCMC only "
+                        f"(tpCN, {FLOW}, beta=1)", "n_particles_per_gpu": N_PER_GPU, "n_particles_total": N_PER_GPU * n_gpus,
+            "n_dim": N_DIM, "flow": FLOW, "mcmc_steps_per_bench_step": mcmc_steps, "kernel": "preconditioned_pcn",
+            "parallelism": f"particle-shard x{n_gpus}" if n_gpus > 1 else "single GPU",
+            "l2": "state (~10 MB) is L2-resident within a bench step by design; L2 flushed (256 MiB write) between bench steps"}
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import pocomc_b200 as pc
+    from pocomc_b200 import config, dist, mcmc as M
+    from pocomc_b200 import made_layout as ML
+    from pocomc_b200.synthetic import CorrelatedGaussian, DevicePrior
+
+    rank, world = dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_local = N_PER_GPU
+    n_global = n_local * world
+    wl = Workload(n_local, N_DIM, row_offset=rank * n_local)
+
+    # ---- untimed setup: scaler, flow training, geometry (identical on every rank) ----
+    np.random.seed(0)
+    torch.manual_seed(0)
+    scaler = pc.scaler.Reparameterize(N_DIM, bounds=wl.bounds)
+    scaler.fit(wl.prior_samples)
+    wl0 = Workload(N_PER_GPU, N_DIM, row_offset=0)            # rank-0 cloud trains the (replicated) flow
+    u_train = scaler.forward(wl0.x0)
+    flow = pc.Flow(N_DIM, FLOW)
+    flow.fit(torch.tensor(u_train, dtype=torch.float32), validation_split=0.5, epochs=TRAIN_EPOCHS, batch_size=512,
+             patience=10 ** 6, annealing=False)
+    theta_train = pc.tools.flow_numpy_wrapper(flow).forward(u_train)[0]
+    geo = pc.geometry.Geometry()
+    geo.fit(theta_train.astype(np.float64))
+    u0 = scaler.forward(wl.x0)
+    ldj0 = scaler.inverse(u0)[1]
+    state = dict(u=u0, x=wl.x0, logdetj=ldj0, logl=wl.loglike(wl.x0), logp=wl.logprior(wl.x0), beta=1.0, blobs=None)
+    like_dev = CorrelatedGaussian(N_DIM)
+    prior_dev = DevicePrior(np.zeros(N_DIM, np.int32), np.zeros(N_DIM), np.full(N_DIM, wl.prior_sd))
+    blocks = int(pc._lib.load().pmc_mh_partials_size(n_local, N_DIM)) // (N_DIM + 4)
+    shard = (rank * n_local, n_global, [blocks] * world) if world > 1 else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- arm 1: device resident -----------------------------------------------------------------
+    config.set_rng_mode("device")
+    sweep_events = []
+    fd = dict(loglike=lambda x: (wl.loglike(x), None), logprior=wl.logprior, scaler=scaler, flow=flow,
+              theta_geometry=geo, u_geometry=geo, loglike_device=like_dev.device, logprior_device=prior_dev)
+    od = dict(n_max=MCMC_STEPS, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / N_DIM ** 0.5, shard=shard,
+              seed=1234, sweep_events=None)
+    eng = M.McmcEngine(M.KIND_TPCN_FLOW, state, fd, od)
+
+    def device_step():
+        flush.fill_(1)
+        eng.reset_controller()
+        eng.loop()
+        assert eng.step == MCMC_STEPS
+
+    for _ in range(args.warmup):
+        device_step()
+    eng.sweep_events = sweep_events
+    clock_lines, stop_evt = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop_evt, clock_lines), daemon=True)
+    th.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = eng.launches
+    eng.launches = 0
+    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sweep_events]))
+    eng.sweep_events = None
+    accept_dev = eng.accept
+
+    # ---- arm 2: end to end through the reference-facing kernel seam, host buffers ---------------
+    fd_host = dict(loglike=lambda x: (wl.loglike(x), None), logprior=wl.logprior, scaler=scaler, flow=flow,
+                   theta_geometry=geo, u_geometry=geo)
+    od_host = dict(n_max=MCMC_STEPS, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / N_DIM ** 0.5, shard=shard, seed=1234)
+
+    def e2e_step():
+        flush.fill_(1)
+        res = M.preconditioned_pcn({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in state.items()}, fd_host, od_host)
+        assert res["steps"] == MCMC_STEPS
+        return res
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    stop_evt.set()
+    th.join(timeout=3)
+
+    per_call_h2d = n_local * (2 * N_DIM + 3) * 8
+    per_call_d2h = n_local * (2 * N_DIM + 3) * 8
+    per_mcmc_d2h = n_local * (N_DIM * 8 + 1) + (M.CTL_MU + N_DIM) * 8
+    per_mcmc_h2d = n_local * 2 * 8
+    h2d = per_call_h2d + MCMC_STEPS * per_mcmc_h2d
+    d2h = per_call_d2h + MCMC_STEPS * per_mcmc_d2h
+
+    # ---- roofline of the dominant kernel (flow inverse sweep) ------------------------------------
+    lay = flow.flow.layout
+    macs = ML.useful_macs(lay)                      # per particle, all transforms
+    flop = 2.0 * macs * n_local
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    achieved_tf = flop / (sweep_ms * 1e-3) / 1e12
+    roofline = dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
+                    traffic=None, kernel="made_sweep_kernel<Affine> (flow inverse, degree-ordered sweep)",
+                    peak_source="MEASURED_PEAKS.json bf16 burst" if peaks else "fallback 1.59 PFLOP/s",
+                    flop_per_launch=flop, avg_launch_ms=sweep_ms,
+                    note="fp32 FMA sweep on CUDA cores; 2*nnz(masks) useful FLOP per particle; share of step = "
+                         f"{sweep_ms * MCMC_STEPS * args.steps / (t_dev * 1e3):.2f}")
+
+    value = n_global * MCMC_STEPS * args.steps / t_dev
+    e2e_value = n_global * MCMC_STEPS * args.steps / t_e2e
+    line = dict(metric="particle-steps/sec", value=value, unit="particle-steps/s", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32 flow / f64 SMC state", data="synthetic",
+                config=workload_config(world, MCMC_STEPS), clocks=summarise_clocks(clock_lines),
+                e2e=dict(value=e2e_value, unit="particle-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         ms_per_step=1e3 * t_e2e / args.steps, rng="device Philox", callbacks="host numpy likelihood + scipy prior"),
+                gpu_launches=launches, roofline=roofline, accept_rate=accept_dev)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        params = [p.detach().cpu().numpy() for _, p in sorted(flow_param_arrays(flow))]
+        prob = cpu_problem(wl, flow_params=params, threads=threads)
+        dt = cpu_steps(*prob, wl, REF_MCMC_STEPS)
+        dt = min(dt, cpu_steps(*prob, wl, REF_MCMC_STEPS))
+        line["cpu_baseline"] = dict(value=wl.n * REF_MCMC_STEPS / dt, unit="particle-steps/s", cores=threads, kind="port",
+                                    sample=f"{REF_MCMC_STEPS} tpCN step x {wl.n} particles, same trained flow weights, best of 2 "
+                                           "(oracle port: vectorised numpy + zuko-restated MAF inverse with D+1 passes)")
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def flow_param_arrays(flow):
+    """(index, tensor) per module-order parameter tensor of the flat blob (for the oracle flow)."""
+    out, k = [], 0
+    for t in range(flow.flow.layout.n_transforms):
+        for w, b in flow.flow.transform_params(t):
+            out.append((k, w)); out.append((k + 1, b)); k += 2
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,10 +144,12 @@ int pmc_mh_accept_update(int32_t kind, double beta, double nu, float* pos32, dou
 /* Scalar adaptation + stop rule (mcmc.py:152-180 and the three siblings), on device:
  * reduces `partials` in fixed order, updates ctl (sigma, mu, step, best, cnt, stop, accept...).
  * mean_mode 1 reproduces np.mean(theta f32, axis=0)'s sequential f32 accumulation exactly
- * (needs pos32), 0 uses the f64 block partials.                                               */
-int pmc_mcmc_finalize(int32_t kind, double* ctl, const double* partials, const float* pos32,
-                      int32_t mean_mode, int32_t n_steps, int32_t n_max, int64_t n, int32_t d,
-                      pmc_stream_t stream);
+ * (needs pos32), 0 uses the f64 block partials.  `partials` holds n_blocks rows of D+4 and `n`
+ * is the number of particles they cover: for a sharded run pass the rank-ordered all-gather of
+ * every rank's partials and the GLOBAL particle count (n_blocks <= 0: pmc_mh_partials_size(n,d)/(d+4)). */
+int pmc_mcmc_finalize(int32_t kind, double* ctl, const double* partials, int64_t n_blocks,
+                      const float* pos32, int32_t mean_mode, int32_t n_steps, int32_t n_max, int64_t n,
+                      int32_t d, pmc_stream_t stream);
 
 /* Counter-based device RNG (Philox4x32-10) for throughput mode: fills the explicit noise tensors
  * the kernels above consume.  Keyed by (seed, step, particle, stream id) -> independent of the

@@ -32,7 +32,7 @@ SIGNATURES = {
     "pmc_apply_bc": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_mh_partials_size": (_I64, [_I64, _I32]),
     "pmc_mh_accept_update": (C.c_int, [_I32, _F64, _F64] + [_P] * 20 + [_I64, _I32, _P]),
-    "pmc_mcmc_finalize": (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _I32, _I64, _I32, _P]),
+    "pmc_mcmc_finalize": (C.c_int, [_I32, _P, _P, _I64, _P, _I32, _I32, _I32, _I64, _I32, _P]),
     "pmc_rng_fill": (C.c_int, [_U64, _U64, _I64, _F64, _P, _P, _P, _I64, _I32, _P]),
     "pmc_ps_append": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _P]),
     "pmc_ps_scratch_size": (_I64, [_I64]),

@@ -17,7 +17,7 @@ namespace pmc {
 // meta header slots -- keep in sync with made_layout.py
 enum { M_D = 0, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE, M_HP, M_MAXCH,
        M_OFF_GSTART, M_OFF_NCHUNK, M_OFF_SLOT, M_OFF_W0, M_OFF_WH, M_OFF_WO, M_OFF_B0, M_OFF_BH,
-       M_OFF_BO, M_RAW_TSTRIDE, M_BINS };
+       M_OFF_BO, M_RAW_TSTRIDE, M_BINS, M_VERSION, M_NCHUNKS, M_SLOT_FLOATS, M_OFF_CHUNKS };
 
 constexpr float LOG_SLOPE = -6.90775527898213705205f;  // log(1e-3)
 
@@ -242,6 +242,215 @@ made_sweep_kernel(const float* __restrict__ packed, const int* __restrict__ meta
   }
 }
 
+// ---- v2: TMA-streamed weights ------------------------------------------------------------------
+// The v1 kernel above reads every weight with a dependent global load, so each of the T*D*(L+1)
+// sequential hops of a particle pays L1/L2 latency (ncu: 6% issue-active, 1.9 ms at ANY n).  Here the
+// weights arrive in consumption order (made_layout.build_stream) through a shared-memory ring filled
+// by one producer lane with cp.async.bulk (TMA 1-D bulk copy) + mbarrier complete_tx; the consumer
+// warps (PW particles x LPP reduction slices each) only ever touch shared memory inside a hop.
+constexpr int STREAM_STAGES = 3;   // ring depth; keep in sync with made_layout.STREAM_STAGES
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// acc[0..3] = sum over rows s = q, q+LPP, ... < nrows of slab[s][0..3] * act[s][p]; slab and act in
+// shared memory (slab rows are 16 B -> the LPP slices of a warp read 16*LPP contiguous bytes).
+template <int LPP>
+__device__ __forceinline__ void dot4s(const float* slab, int nrows, const float* act, int p, int q, float (&acc)[4]) {
+  constexpr int PW = 32 / LPP;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  const float4* wp = reinterpret_cast<const float4*>(slab) + q;
+  const float* ap = act + q * PW + p;
+  int s = q;
+#pragma unroll 2
+  for (; s + LPP < nrows; s += 2 * LPP) {
+    const float4 w0 = wp[0], w1 = wp[LPP];
+    const float x0 = ap[0], x1 = ap[32];
+    a0 = fmaf(w0.x, x0, a0); a1 = fmaf(w0.y, x0, a1); a2 = fmaf(w0.z, x0, a2); a3 = fmaf(w0.w, x0, a3);
+    b0 = fmaf(w1.x, x1, b0); b1 = fmaf(w1.y, x1, b1); b2 = fmaf(w1.z, x1, b2); b3 = fmaf(w1.w, x1, b3);
+    wp += 2 * LPP; ap += 64;
+  }
+  if (s < nrows) {
+    const float4 w0 = wp[0];
+    const float x0 = ap[0];
+    a0 = fmaf(w0.x, x0, a0); a1 = fmaf(w0.y, x0, a1); a2 = fmaf(w0.z, x0, a2); a3 = fmaf(w0.w, x0, a3);
+  }
+  acc[0] = a0 + b0; acc[1] = a1 + b1; acc[2] = a2 + b2; acc[3] = a3 + b3;
+#pragma unroll
+  for (int o = PW; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+  }
+}
+
+template <class UNI, int LPP>
+__global__ void __launch_bounds__(1024, 1)
+made_sweep_stream_kernel(const float* __restrict__ stream, const int* __restrict__ meta, int meta_len,
+                         const float* __restrict__ in, float* __restrict__ out, float* __restrict__ ladj_out,
+                         long long n, int inverse, int ppc) {
+  constexpr int PW = 32 / LPP;
+  constexpr int TP = UNI::TP;
+  constexpr int NS = STREAM_STAGES;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  int* sm = reinterpret_cast<int*>(smem_raw);
+  for (int i = threadIdx.x; i < meta_len; i += blockDim.x) sm[i] = meta[i];
+  __syncthreads();
+  const int D = sm[M_D], H = sm[M_H], L = sm[M_L], T = sm[M_T], ng = sm[M_NG];
+  const int tstride = sm[M_TSTRIDE], nchunks = sm[M_NCHUNKS], slot_floats = sm[M_SLOT_FLOATS];
+  const int* gstart = sm + sm[M_OFF_GSTART];
+  const int* nchunk = sm + sm[M_OFF_NCHUNK];
+  const int* chunks = sm + sm[M_OFF_CHUNKS];
+  size_t off = ((size_t)meta_len * 4 + 15) & ~(size_t)15;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + off);
+  unsigned long long* empty = full + NS;
+  off = (off + 2 * NS * 8 + 127) & ~(size_t)127;
+  float* ring = reinterpret_cast<float*>(smem_raw + off);
+  off += (size_t)NS * slot_floats * 4;
+  float* acts = reinterpret_cast<float*>(smem_raw + off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long cta_row0 = (long long)blockIdx.x * ppc;
+  const int cta_rows = (int)min((long long)ppc, n - cta_row0);
+  const int active = (cta_rows + PW - 1) / PW;          // consumer warps with particles
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, active); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {  // ---- producer: one lane streams T * nchunks bulk copies through the ring
+    if (lane == 0) {
+      int it = 0;
+      for (int tt = 0; tt < T; ++tt) {
+        const int t = inverse ? (T - 1 - tt) : tt;
+        const float* src = stream + (size_t)t * tstride;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int slot = it % NS;
+          if (it >= NS) mbar_wait(empty + slot, ((it / NS) - 1) & 1);
+          const unsigned bytes = (unsigned)chunks[4 * c + 3] * 4u;
+          mbar_expect_tx(full + slot, bytes);
+          bulk_g2s(ring + (size_t)slot * slot_floats, src + chunks[4 * c + 2], bytes, full + slot);
+        }
+      }
+    }
+    return;
+  }
+  const int cw = warp - 1;
+  if (cw >= active) return;
+
+  // ---- consumers
+  const int p = lane % PW, q = lane / PW;
+  const int per_warp = (2 * D + L * H) * PW;
+  float* cur = acts + (size_t)cw * per_warp;  // [D][PW] running vector (feature order)
+  float* xs = cur + D * PW;                   // [D][PW] data-side values by ORDER position (MLP inputs)
+  float* act = xs + D * PW;                   // [L][H][PW]
+  const long long row0 = cta_row0 + (long long)cw * PW;
+  const int rows = (int)min((long long)PW, n - row0);
+  for (int i = lane; i < PW * D; i += 32) {
+    const int r = i / D, c = i - r * D;
+    cur[c * PW + r] = (r < rows) ? in[row0 * D + i] : 0.0f;
+  }
+  __syncwarp();
+  float ladj = 0.0f;
+  int it = 0;
+  for (int tt = 0; tt < T; ++tt) {
+    const int t = inverse ? (T - 1 - tt) : tt;
+    const bool rev = (t & 1);
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const int slot = it % NS;
+      mbar_wait(full + slot, (it / NS) & 1);
+      const float* w = ring + (size_t)slot * slot_floats;
+      const int k0 = chunks[4 * c], k1 = chunks[4 * c + 1];
+      for (int k = k0; k < k1; ++k) {
+        const int feat = rev ? (D - 1 - k) : k;
+        const int Ek = gstart[k];   // sorted units with degree <= k
+        float phi[TP];
+#pragma unroll
+        for (int cc = 0; cc < TP / 4; ++cc) {
+          float acc[4];
+          dot4s<LPP>(w, Ek, act + (size_t)(L - 1) * H * PW, p, q, acc);
+          w += 4 * Ek;
+          phi[4 * cc + 0] = acc[0]; phi[4 * cc + 1] = acc[1]; phi[4 * cc + 2] = acc[2]; phi[4 * cc + 3] = acc[3];
+        }
+#pragma unroll
+        for (int cc = 0; cc < TP / 4; ++cc) {
+          const float4 b = reinterpret_cast<const float4*>(w)[cc];
+          phi[4 * cc + 0] += b.x; phi[4 * cc + 1] += b.y; phi[4 * cc + 2] += b.z; phi[4 * cc + 3] += b.w;
+        }
+        w += TP;
+        const float v = cur[feat * PW + p];
+        float l;
+        const float res = UNI::apply(phi, v, inverse != 0, l);
+        ladj = inverse ? (ladj - l) : (ladj + l);
+        __syncwarp();  // every slice has read cur[feat] before it is overwritten
+        if (q == 0) {
+          xs[k * PW + p] = inverse ? res : v;
+          cur[feat * PW + p] = res;
+        }
+        __syncwarp();
+        const int g = k + 1;
+        if (g > ng) continue;
+        const int gs = gstart[g - 1], ge = gstart[g];
+        if (ge == gs) continue;
+        const int nch = nchunk[g - 1];
+        for (int l_ = 0; l_ < L; ++l_) {
+          const int nrows = (l_ == 0) ? g : ge;
+          const float* src = (l_ == 0) ? xs : act + (size_t)(l_ - 1) * H * PW;
+          float* dst = act + (size_t)l_ * H * PW;
+          const float* bias = w + (size_t)nch * nrows * 4;
+          for (int cc = 0; cc < nch; ++cc) {
+            float acc[4];
+            dot4s<LPP>(w, nrows, src, p, q, acc);
+            w += 4 * nrows;
+            const float4 b = reinterpret_cast<const float4*>(bias)[cc];
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int u = gs + 4 * cc + i;
+              if (u < ge && q == (i % LPP)) {
+                const float pre = acc[i] + bb[i];
+                dst[u * PW + p] = fmaxf(l_ == 0 ? pre : src[u * PW + p] + pre, 0.0f);   // residual hidden layers
+              }
+            }
+          }
+          w += 4 * nch;
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+    }
+  }
+  for (int i = lane; i < PW * D; i += 32) {
+    const int r = i / D, c = i - r * D;
+    if (r < rows) out[row0 * D + i] = cur[c * PW + r];
+  }
+  if (q == 0 && p < rows) ladj_out[row0 + p] = ladj;
+}
+
 __global__ void pack_kernel(const float* __restrict__ raw, const int* __restrict__ gather,
                             float* __restrict__ packed, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -301,6 +510,43 @@ static int launch_sweep(const float* packed, const int* meta, int meta_len, cons
   return 0;
 }
 
+
+template <class UNI>
+static int launch_stream(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in,
+                         float* out, float* ladj, long long n, int inverse, cudaStream_t st) {
+  const int D = hmeta[M_D], H = hmeta[M_H], L = hmeta[M_L];
+  const size_t fixed = (((size_t)meta_len * 4 + 15) & ~(size_t)15) + 2 * STREAM_STAGES * 8 + 256 +
+                       (size_t)STREAM_STAGES * hmeta[M_SLOT_FLOATS] * 4;
+  const size_t per_particle = (size_t)(2 * D + L * H) * 4;
+  const size_t budget = 227 * 1024;
+  PMC_REQUIRE(fixed + 8 * per_particle <= budget, "pmc_flow_sweep: flow too large for the stream kernel");
+  const int sms = sm_count();
+  const long long max_smem = (long long)((budget - fixed) / per_particle);
+  // lanes per particle: 8 unless a single wave would need more than 31 warps' worth of particles
+  const long long per_sm = (n + sms - 1) / sms;
+  int lpp = 8;
+  if (per_sm <= 8) lpp = 16;
+  const int pw = 32 / lpp;
+  long long cap = std::min<long long>(max_smem, 31LL * pw) / pw * pw;
+  if (cap < pw) { set_error("pmc_flow_sweep: shared memory too small for one tile"); return 3; }
+  long long waves = (per_sm + cap - 1) / cap;
+  long long ppc = (n + waves * sms - 1) / (waves * sms);
+  ppc = std::min(cap, (ppc + pw - 1) / pw * pw);
+  const long long grid = (n + ppc - 1) / ppc;
+  const int threads = 32 * (1 + (int)(ppc / pw));
+  const size_t smem = fixed + (size_t)ppc * per_particle;
+#define PMC_STREAM_CASE(LPPV)                                                                        \
+  case LPPV: {                                                                                       \
+    auto kern = made_sweep_stream_kernel<UNI, LPPV>;                                                 \
+    PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<(unsigned)grid, threads, smem, st>>>(stream, meta, meta_len, in, out, ladj, n, inverse, (int)ppc); \
+  } break;
+  switch (lpp) { PMC_STREAM_CASE(8) PMC_STREAM_CASE(16) }
+#undef PMC_STREAM_CASE
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace pmc
 
 using namespace pmc;
@@ -321,6 +567,11 @@ extern "C" int pmc_flow_sweep(const float* packed, const int32_t* meta, const in
   if (n == 0) return 0;
   const int* hm = meta_host;
   PMC_REQUIRE(hm[M_D] >= 2 && hm[M_H] >= 1 && hm[M_L] >= 1 && hm[M_T] >= 1, "pmc_flow_sweep: bad meta header");
+  if (hm[M_VERSION] == 2) {
+    PMC_REQUIRE(hm[M_KIND] == 0 || (hm[M_BINS] == 8 && hm[M_TOTAL] == 23), "pmc_flow_sweep: only bins=8 splines are built");
+    if (hm[M_KIND] == 0) return launch_stream<Affine>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
+    return launch_stream<Rqs>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
+  }
   if (hm[M_KIND] == 0) return launch_sweep<Affine>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
   PMC_REQUIRE(hm[M_BINS] == 8 && hm[M_TOTAL] == 23, "pmc_flow_sweep: only bins=8 splines are built");
   return launch_sweep<Rqs>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));

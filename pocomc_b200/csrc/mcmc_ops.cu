@@ -569,13 +569,13 @@ extern "C" int pmc_mh_accept_update(int32_t kind, double beta, double nu, float*
   return 0;
 }
 
-extern "C" int pmc_mcmc_finalize(int32_t kind, double* ctl, const double* partials, const float* pos32,
-                                 int32_t mean_mode, int32_t n_steps, int32_t n_max, int64_t n, int32_t d,
-                                 pmc_stream_t stream) {
+extern "C" int pmc_mcmc_finalize(int32_t kind, double* ctl, const double* partials, int64_t n_blocks,
+                                 const float* pos32, int32_t mean_mode, int32_t n_steps, int32_t n_max, int64_t n,
+                                 int32_t d, pmc_stream_t stream) {
   PMC_REQUIRE(ctl && partials && n > 0, "pmc_mcmc_finalize: bad arguments");
   PMC_REQUIRE(!(kind == PMC_KIND_TPCN_FLOW && mean_mode == 1) || pos32, "pmc_mcmc_finalize: mean_mode 1 needs theta");
   mcmc_finalize_kernel<<<1, 256, (size_t)(d + 4) * sizeof(double), as_stream(stream)>>>(
-      kind, ctl, partials, (int)mh_blocks(n), pos32, mean_mode, n_steps, n_max, n, d);
+      kind, ctl, partials, (int)(n_blocks > 0 ? n_blocks : mh_blocks(n)), pos32, mean_mode, n_steps, n_max, n, d);
   PMC_LAUNCH_CHECK();
   return 0;
 }

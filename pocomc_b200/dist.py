@@ -1,0 +1,82 @@
+"""Particle sharding across the GPUs of one box (one process per GPU, torch.distributed/NCCL).
+
+Rows (particles) are independent through the flow, proposal, reparameterisation and Metropolis
+kernels given replicated flow weights / geometry / scaler, so rank r owns a contiguous block of
+particles and the only per-MCMC-step exchange is the (D+4)-wide f64 reduction behind the sigma / mu
+adaptation and the stop rule (mcmc.py:152,156,170).  Discrete decisions
+downstream must not depend on the GPU count, so the reduction is NOT a ring all-reduce: every rank
+contributes its fixed-size per-256-row block partials, they are all-gathered in rank (= global
+particle) order and summed in that fixed order by every rank."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as td
+
+__all__ = ["init_from_env", "is_active", "world", "shard_range", "gather_blocks", "allreduce_sum_det"]
+
+
+def init_from_env(backend: str = None):
+    """torchrun-style initialisation (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*); no-op for one process."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1 or td.is_initialized():
+        return world()
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    td.init_process_group(backend=backend)
+    return world()
+
+
+def is_active() -> bool:
+    return td.is_available() and td.is_initialized() and td.get_world_size() > 1
+
+
+def world():
+    """(rank, world_size)."""
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(), td.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_total: int, rank: int, world_size: int, align: int = 1):
+    """[start, stop) of the contiguous block of rows owned by ``rank``; block boundaries are
+    multiples of ``align`` (256 = the accept kernel's rows-per-block keeps the block partials of a
+    sharded run identical to the single-GPU ones)."""
+    units = (n_total + align - 1) // align
+    base, extra = divmod(units, world_size)
+    start_u = rank * base + min(rank, extra)
+    stop_u = start_u + base + (1 if rank < extra else 0)
+    return min(start_u * align, n_total), min(stop_u * align, n_total)
+
+
+def gather_blocks(local: torch.Tensor, counts=None) -> torch.Tensor:
+    """All-gather per-rank [b_r, w] block partials into [sum_r b_r, w] in rank order.  ``counts``
+    (blocks per rank) may differ between ranks; equal counts take the single-collective path."""
+    if not is_active():
+        return local
+    ws = td.get_world_size()
+    if counts is None:
+        counts = [local.shape[0]] * ws
+    if len(set(counts)) == 1:
+        out = torch.empty((ws * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        td.all_gather_into_tensor(out, local.contiguous())
+        return out
+    parts = [torch.empty((c,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for c in counts]
+    td.all_gather(parts, local.contiguous())
+    return torch.cat(parts, dim=0)
+
+
+def allreduce_sum_det(values: torch.Tensor) -> torch.Tensor:
+    """Sum of a small per-rank vector with a rank-ordered (GPU-count independent given the same
+    per-rank values) association: gather then sum over the rank axis in order."""
+    if not is_active():
+        return values
+    g = gather_blocks(values.reshape(1, -1))
+    out = g[0].clone()
+    for r in range(1, g.shape[0]):
+        out += g[r]
+    return out.reshape(values.shape)

@@ -103,9 +103,17 @@ class MaskedAutoregressiveFlow(nn.Module):
                 bound = 1 / math.sqrt(wshape[1]) if wshape[1] > 0 else 0
                 nn.init.uniform_(b, -bound, bound)
         self.raw = nn.Parameter(raw)
-        self.register_buffer("gather", torch.from_numpy(lay.gather.copy()), persistent=False)
-        self.register_buffer("meta", torch.from_numpy(lay.meta.copy()), persistent=False)
-        self._meta_host = np.ascontiguousarray(lay.meta)
+        # kernel-side weight layout: the TMA-streamed consumption-order stream when the network fits the
+        # stream kernel's shared-memory budget, else the degree-sorted slab layout of the v1 kernel
+        if ML.stream_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind, lay.bins):
+            klay = ML.build_stream(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+            self.packed_numel = klay.numel
+        else:
+            klay = lay
+            self.packed_numel = lay.packed_numel
+        self.register_buffer("gather", torch.from_numpy(klay.gather.copy()), persistent=False)
+        self.register_buffer("meta", torch.from_numpy(klay.meta.copy()), persistent=False)
+        self._meta_host = np.ascontiguousarray(klay.meta)
         self._packed = None
         self._packed_key = None
         self._masks = None
@@ -143,9 +151,9 @@ class MaskedAutoregressiveFlow(nn.Module):
         key = (self.raw.data_ptr(), self.raw._version)
         if self._packed is None or self._packed_key != key:
             if self._packed is None or self._packed.device != self.raw.device:
-                self._packed = torch.empty(self.layout.packed_numel, dtype=torch.float32, device=self.raw.device)
+                self._packed = torch.empty(self.packed_numel, dtype=torch.float32, device=self.raw.device)
             _lib.call("pmc_flow_pack", _lib.ptr(self.raw.detach()), _lib.ptr(self.gather), _lib.ptr(self._packed),
-                      self.layout.packed_numel)
+                      self.packed_numel)
             self._packed_key = key
         return self._packed
 

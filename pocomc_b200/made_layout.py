@@ -37,6 +37,11 @@ META_HEADER = 32          # int32 slots before the tables
 M_D, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE, M_HP, M_MAXCH = range(11)
 M_OFF_GSTART, M_OFF_NCHUNK, M_OFF_SLOT, M_OFF_W0, M_OFF_WH, M_OFF_WO, M_OFF_B0, M_OFF_BH, M_OFF_BO, \
     M_RAW_TSTRIDE, M_BINS = range(11, 22)
+# stream (v2) layout extras
+M_VERSION, M_NCHUNKS, M_SLOT_FLOATS, M_OFF_CHUNKS = 22, 23, 24, 25
+STREAM_CHUNK_FLOATS = 6144        # target size of one TMA bulk copy (24 KB)
+STREAM_STAGES = 3                 # ring depth of the sweep kernel (keep in sync with flow_sweep.cu)
+STREAM_SMEM_BUDGET = 200 * 1024   # ring + 8 particles of activations must fit below this
 
 
 def hidden_width(n_dim: int) -> int:
@@ -196,3 +201,137 @@ def masks(layout: MadeLayout, t: int):
     mh = deg[None, :] <= deg[:, None]                        # [H, H]
     mo = np.repeat(deg[None, :] <= order[:, None], total, axis=0)   # [D*total, H]
     return [m0] + [mh] * (L - 1) + [mo]
+
+
+def useful_macs(layout: MadeLayout) -> int:
+    """Multiply-accumulates per particle of one degree-ordered sweep over all transforms =
+    nnz of the masks (the algorithmic minimum; the reference's inverse runs D+1 dense passes)."""
+    D, H, L = layout.n_dim, layout.n_hidden, layout.n_layers
+    deg = (np.arange(H) % (D - 1)) + 1
+    per_t = int(deg.sum())                                              # input layer: unit of degree g sees g inputs
+    le = np.array([(deg <= g).sum() for g in deg])
+    per_t += (L - 1) * int(le.sum())                                    # hidden layers: units of degree <= own
+    per_t += layout.total * int(sum((deg <= k).sum() for k in range(D)))   # outputs of order k see degree <= k
+    return per_t * layout.n_transforms
+
+
+@dataclass(frozen=True)
+class StreamLayout:
+    """Consumption-ordered weight stream for the TMA-fed sweep kernel (csrc/flow_sweep.cu, v2).
+
+    One transform = D stages; stage k holds, in the order the kernel reads them,
+      out hop  : TP/4 slabs [E_k rows][4] (outputs 4c..4c+3 of order position k) + bias [TP]
+      group g=k+1 (if it has units), nch = ceil(size/4) chunks of 4 units:
+        layer 0 : nch slabs [g rows][4] (input orders 0..g-1) + bias [4 nch]
+        layer l : nch slabs [E_g rows][4] (sorted units of degree <= g of layer l-1) + bias [4 nch]
+    Stages are grouped into chunks of ~24 KB; the kernel's producer warp streams the chunks
+    through a shared-memory ring with cp.async.bulk + mbarriers.  The chunk table is the same for
+    every transform: (k0, k1, float offset, float count)."""
+    tstride: int
+    slot_floats: int
+    chunks: np.ndarray     # [n_chunks, 4] int64
+    meta: np.ndarray       # int32
+    gather: np.ndarray     # int32 [T * tstride]
+
+    @property
+    def numel(self):
+        return int(self.gather.size)
+
+
+def stream_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int, bins: int = 8) -> bool:
+    """The stream kernel needs ring + activations of >= 8 particles in shared memory."""
+    total = 2 if kind == KIND_AFFINE else 3 * bins - 1
+    tp = (total + 3) // 4 * 4
+    wd = 4 * ((n_hidden + n_dim - 2) // max(n_dim - 1, 1) + 3) // 4 + 4
+    stage_max = n_hidden * tp + tp + n_layers * (n_hidden * wd + wd)
+    slot = max(stage_max, STREAM_CHUNK_FLOATS)
+    return STREAM_STAGES * slot * 4 + 8 * (2 * n_dim + n_layers * n_hidden) * 4 + 4096 <= STREAM_SMEM_BUDGET
+
+
+@lru_cache(maxsize=None)
+def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8) -> StreamLayout:
+    lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
+    D, H, L, T, total, tp = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.total, lay.tp
+    ng = D - 1
+    hperm, degree = lay.hperm, lay.degree
+    gstart = np.searchsorted(degree, np.arange(1, ng + 2), side="left").astype(np.int64)
+    gsize = np.diff(gstart)
+    nchunk = (gsize + 3) // 4
+    raw_off = np.concatenate([[0], np.cumsum([int(np.prod(sh)) for sh in lay.raw_sizes])]).astype(np.int64)
+
+    def transform_gather(t):
+        """list of per-stage int64 gather arrays (indices into raw, -1 = zero)."""
+        base_r = t * lay.raw_tstride
+        iperm = np.arange(D) if t % 2 == 0 else D - 1 - np.arange(D)
+        stages = []
+        for k in range(D):
+            parts = []
+            feat = iperm[k]
+            ek = int(gstart[k - 1 + 1]) if k >= 1 else 0          # units of degree <= k  (gstart[k] = #deg < k+1)
+            src = hperm[:ek]
+            wo, bo = base_r + raw_off[2 * L], base_r + raw_off[2 * L + 1]
+            for c in range(tp // 4):
+                blk = np.full((ek, 4), -1, np.int64)
+                for j in range(4):
+                    o = 4 * c + j
+                    if o < total:
+                        blk[:, j] = wo + (feat * total + o) * H + src
+                parts.append(blk.reshape(-1))
+            b = np.full(tp, -1, np.int64)
+            b[:total] = bo + feat * total + np.arange(total)
+            parts.append(b)
+            g = k + 1
+            if g <= ng and gsize[g - 1] > 0:
+                units = hperm[gstart[g - 1]:gstart[g]]
+                nch = int(nchunk[g - 1])
+                upad = np.full(4 * nch, -1, np.int64)
+                upad[:len(units)] = units
+                eg = int(gstart[g])
+                for l in range(L):
+                    wl, bl = base_r + raw_off[2 * l], base_r + raw_off[2 * l + 1]
+                    rows = iperm[np.arange(g)] if l == 0 else hperm[:eg]
+                    width = D if l == 0 else H
+                    for c in range(nch):
+                        blk = np.full((len(rows), 4), -1, np.int64)
+                        for j in range(4):
+                            u = upad[4 * c + j]
+                            if u >= 0:
+                                blk[:, j] = wl + u * width + rows
+                        parts.append(blk.reshape(-1))
+                    parts.append(np.where(upad >= 0, bl + upad, -1))
+            stages.append(np.concatenate(parts))
+        return stages
+
+    stages0 = transform_gather(0)
+    sizes = np.array([len(a) for a in stages0], np.int64)
+    assert np.all(sizes % 4 == 0)
+    chunks, k0, acc, off = [], 0, 0, 0
+    for k in range(D):
+        if acc > 0 and acc + sizes[k] > STREAM_CHUNK_FLOATS:
+            chunks.append((k0, k, off, acc))
+            off += acc
+            k0, acc = k, 0
+        acc += int(sizes[k])
+    chunks.append((k0, D, off, acc))
+    chunks = np.asarray(chunks, np.int64)
+    tstride = int(sizes.sum())
+    slot_floats = int(chunks[:, 3].max())
+    gather = np.concatenate([np.concatenate(transform_gather(t)) for t in range(T)])
+    assert gather.size == T * tstride
+
+    tables = [gstart, nchunk, chunks.reshape(-1)]
+    meta = np.zeros(META_HEADER, np.int64)
+    meta[[M_D, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE]] = [D, H, L, T, kind, total, tp, ng, tstride]
+    meta[M_MAXCH] = int(nchunk.max())
+    meta[M_RAW_TSTRIDE] = lay.raw_tstride
+    meta[M_BINS] = bins
+    meta[M_VERSION] = 2
+    meta[M_NCHUNKS] = len(chunks)
+    meta[M_SLOT_FLOATS] = slot_floats
+    pos = META_HEADER
+    for slot_id, tab in zip((M_OFF_GSTART, M_OFF_NCHUNK, M_OFF_CHUNKS), tables):
+        meta[slot_id] = pos
+        pos += len(tab)
+    meta = np.concatenate([meta] + [np.asarray(tb, np.int64) for tb in tables])
+    assert meta.max() < 2 ** 31 and gather.max() < 2 ** 31
+    return StreamLayout(tstride, slot_floats, chunks, meta.astype(np.int32), gather.astype(np.int32))

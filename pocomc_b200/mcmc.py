@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, config
+from . import _lib, config, dist
 from .flow import Flow
 
 KIND_TPCN_FLOW, KIND_RWM_FLOW, KIND_TPCN, KIND_RWM = 0, 1, 2, 3
@@ -59,6 +59,7 @@ class McmcEngine:
         self.n_max = int(option_dict.get('n_max'))
         self.n_steps = int(option_dict.get('n_steps'))
         self.progress_bar = option_dict.get('progress_bar')
+        self.sweep_events = option_dict.get('sweep_events')     # optional list: (start, stop) CUDA events per inverse sweep
         sigma = option_dict.get('proposal_scale')
         if self.tp:
             sigma = np.minimum(sigma, 0.99)
@@ -121,8 +122,17 @@ class McmcEngine:
         self.h_noise = torch.empty(n * (d + 2), dtype=torch.float64).pin_memory() if config.rng_mode == "host" else None
         self.rng_mode = config.rng_mode
         self.mean_mode = config.resolved_mean_mode()
-        self.seed = int(np.random.randint(0, 2 ** 62)) if self.rng_mode == "device" else 0
+        # particle sharding: option_dict['shard'] = (global offset of row 0, global particle count, blocks per rank)
+        shard = option_dict.get('shard')
+        self.sharded = shard is not None and dist.is_active()
+        self.row_offset, self.n_global, self.shard_blocks = (shard if shard is not None else (0, n, None))
+        if self.sharded:
+            self.mean_mode = 0
+        self.seed = 0
+        if self.rng_mode == "device":     # one draw from the host stream keys the Philox counters (same on every rank)
+            self.seed = int(option_dict['seed']) if option_dict.get('seed') is not None else int(np.random.randint(0, 2 ** 62))
         self.n_calls = 0
+        self.launches = 0       # libpmc_b200 kernels launched by this engine (bench.py's gpu_launches)
         self.step = 0
         self.sigma = float(sigma)
         self.accept = 0.0
@@ -143,7 +153,7 @@ class McmcEngine:
             hn[n:n + n * d] = np.random.randn(n, d).reshape(-1)
             self.z.copy_(self.h_noise[n:n + n * d].view(n, d), non_blocking=True)
         else:
-            _lib.call("pmc_rng_fill", C.c_uint64(self.seed), C.c_uint64(self.step + 1), 0,
+            _lib.call("pmc_rng_fill", C.c_uint64(self.seed), C.c_uint64(self.step + 1), int(self.row_offset),
                       (d + self.nu) / 2 if self.tp else 0.0, _lib.ptr(self.g), _lib.ptr(self.z), _lib.ptr(self.r), n, d)
 
     def propose(self):
@@ -161,7 +171,13 @@ class McmcEngine:
         """theta' -> u' (flow.inverse, mcmc.py:88) -> x', logdetj' (+ boundary conditions, :91-97)."""
         n, d = self.n, self.d
         if self.use_flow:
+            if self.sweep_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             self.module.sweep_into(self.prop32, self.u_p32, self.ldjf_p, inverse=True)
+            if self.sweep_events is not None:
+                e1.record()
+                self.sweep_events.append((e0, e1))
             src, is32 = self.u_p32, 1
         else:
             src, is32 = self.prop64, 0
@@ -211,8 +227,12 @@ class McmcEngine:
                   _lib.ptr(self.logl_p), _lib.ptr(self.logp_p), _lib.ptr(self.ldjf_p), _lib.ptr(self.m_cur),
                   _lib.ptr(self.m_prop), _lib.ptr(self.r), _lib.ptr(self.finite) if calls is None else None,
                   _lib.ptr(self.alpha), _lib.ptr(self.partials), n, d)
-        _lib.call("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(self.partials), _lib.ptr(self.theta),
-                  self.mean_mode, self.n_steps, self.n_max, n, d)
+        parts, n_blocks, n_all = self.partials, 0, n
+        if self.sharded:      # rank-ordered all-gather of the block partials, summed in fixed order by every rank
+            parts = dist.gather_blocks(self.partials.view(-1, d + 4), self.shard_blocks)
+            n_blocks, n_all = parts.shape[0], self.n_global
+        _lib.call("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(parts), n_blocks, _lib.ptr(self.theta),
+                  self.mean_mode, self.n_steps, self.n_max, n_all, d)
 
     def read_controller(self):
         self.ctl_host.copy_(self.ctl, non_blocking=True)
@@ -222,12 +242,28 @@ class McmcEngine:
         self.step, self.stop = int(c[CTL_STEP]), bool(c[CTL_STOP] != 0.0)
         return c
 
+    def reset_controller(self):
+        """Start another ``_mutate``-sized run from the current state: step, plateau counter and
+        stop flag cleared, sigma and mu kept (what successive Sampler._mutate calls at one beta do)."""
+        self.ctl[CTL_STEP:CTL_STOP + 1] = torch.tensor([0.0, float((self.logl + self.logp).mean().item()) if self.tp else
+                                                        float((self.logl + self.logp + self.logdetj).mean().item()), 0.0, 0.0],
+                                                       dtype=torch.float64, device=self.dev)
+        self.step, self.stop = 0, False
+
     def run(self):
+        self.loop()
+        return self.results()
+
+    def loop(self):
+        """MCMC steps until the plateau rule or n_max fires (mcmc.py:72-180); state stays on the GPU."""
         device_eval = self.loglike_device is not None and self.logprior_device is not None and not self.have_blobs
         while True:
             self.draw_noise()
             self.propose()
             self.pull_back()
+            # rng_fill (device mode) + propose + [sweep] + scaler + [prior + likelihood] + accept + finalize
+            self.launches += (1 if self.rng_mode == "device" else 0) + 2 + (1 if self.use_flow else 0) + 2 \
+                + (2 if device_eval else 0)
             if device_eval:
                 calls, blobs_p = self.evaluate_device()
             else:
@@ -250,6 +286,9 @@ class McmcEngine:
                     eff=self.sigma / (2.38 / np.sqrt(self.d))))
             if self.stop:
                 break
+
+    def results(self):
+        """Download the final state in the reference's result-dict layout (mcmc.py:182-183)."""
         return dict(u=self.u.cpu().numpy(), x=self.x.cpu().numpy(), logdetj=self.logdetj.cpu().numpy(),
                     logl=self.logl.cpu().numpy(), logp=self.logp.cpu().numpy(), blobs=self.blobs,
                     efficiency=self.sigma, accept=self.accept, steps=self.step, calls=self.n_calls,

@@ -114,3 +114,60 @@ def sweep(layout, packed, v, inverse):
                 act[l_, gs:ge] = np.maximum(r, 0).T
         cur = out
     return cur, ladj
+
+
+def pack_stream(stream, raw):
+    raw = np.asarray(raw, np.float32)
+    g = stream.gather
+    return np.where(g >= 0, raw[np.maximum(g, 0)], np.float32(0)).astype(np.float32)
+
+
+def sweep_stream(layout, stream, packed, x, inverse):
+    """Emulates made_sweep_stream_kernel: walks the consumption-order stream with a running offset."""
+    m = stream.meta
+    D, H, L, T, ng, tp = (int(m[i]) for i in (ML.M_D, ML.M_H, ML.M_L, ML.M_T, ML.M_NG, ML.M_TP))
+    gstart = m[m[ML.M_OFF_GSTART]:m[ML.M_OFF_GSTART] + ng + 1]
+    nchunk = m[m[ML.M_OFF_NCHUNK]:m[ML.M_OFF_NCHUNK] + ng]
+    chunks = m[m[ML.M_OFF_CHUNKS]:m[ML.M_OFF_CHUNKS] + 4 * m[ML.M_NCHUNKS]].reshape(-1, 4)
+    uni = affine if layout.kind == ML.KIND_AFFINE else rqs
+    cur = np.array(x, np.float32, copy=True)
+    n = len(cur)
+    ladj = np.zeros(n, np.float32)
+    for tt in range(T):
+        t = T - 1 - tt if inverse else tt
+        xs = np.zeros((n, D), np.float32)
+        act = np.zeros((L, n, H), np.float32)
+        for k0, k1, off, cnt in chunks:
+            w = packed[t * stream.tstride + off: t * stream.tstride + off + cnt]
+            pos = 0
+            for k in range(k0, k1):
+                feat = D - 1 - k if t % 2 else k
+                ek = int(gstart[k])
+                phi = np.zeros((n, tp), np.float32)
+                for c in range(tp // 4):
+                    slab = w[pos:pos + 4 * ek].reshape(ek, 4); pos += 4 * ek
+                    phi[:, 4 * c:4 * c + 4] = act[L - 1][:, :ek] @ slab
+                phi += w[pos:pos + tp]; pos += tp
+                v = cur[:, feat].copy()
+                res, l = uni(phi, v, inverse)
+                ladj = ladj - l if inverse else ladj + l
+                xs[:, k] = res if inverse else v
+                cur[:, feat] = res
+                g = k + 1
+                if g > ng or gstart[g] == gstart[g - 1]:
+                    continue
+                gs, ge, nch = int(gstart[g - 1]), int(gstart[g]), int(nchunk[g - 1])
+                for l_ in range(L):
+                    nrows = g if l_ == 0 else ge
+                    src = xs[:, :g] if l_ == 0 else act[l_ - 1][:, :ge]
+                    pre = np.zeros((n, 4 * nch), np.float32)
+                    for c in range(nch):
+                        slab = w[pos:pos + 4 * nrows].reshape(nrows, 4); pos += 4 * nrows
+                        pre[:, 4 * c:4 * c + 4] = src @ slab
+                    pre += w[pos:pos + 4 * nch]; pos += 4 * nch
+                    pre = pre[:, :ge - gs]
+                    if l_ > 0:
+                        pre = pre + act[l_ - 1][:, gs:ge]
+                    act[l_][:, gs:ge] = np.maximum(pre, 0)
+            assert pos == cnt
+    return cur, ladj

@@ -130,7 +130,7 @@ def test_single_step_operators_vs_oracle(golden):
     np.testing.assert_array_equal(st["logl"].cpu().numpy(), np.where(acc, logl_p, g["logl"]))
     # controller: sigma adaptation + stop rule vs the oracle formula
     ctl_d = t(np.concatenate([[sigma, 0, -1e300, 0, 0, 0, 0, 0, 0], np.zeros(7), mu]))
-    _lib.call("pmc_mcmc_finalize", 2, _lib.ptr(ctl_d), _lib.ptr(parts), None, 0, 3, 50, n, d)
+    _lib.call("pmc_mcmc_finalize", 2, _lib.ptr(ctl_d), _lib.ptr(parts), 0, None, 0, 3, 50, n, d)
     c = ctl_d.cpu().numpy()
     cap = 2.38 / d ** 0.5
     np.testing.assert_allclose(c[5], alpha_ref.mean(), rtol=1e-13)

@@ -6,7 +6,7 @@ import torch
 
 import flow_ref as F
 from pocomc_b200 import made_layout as ML
-from sweep_emul import pack, sweep
+from sweep_emul import pack, pack_stream, sweep, sweep_stream
 
 
 def _raw(flow):
@@ -38,6 +38,18 @@ def test_sweep_matches_oracle(preset, d):
     tol = 1e-4 if kind == "maf" else 5e-4
     np.testing.assert_allclose(xs, xi.numpy(), rtol=tol, atol=tol)
     np.testing.assert_allclose(lis, li.numpy(), rtol=tol, atol=tol)
+    # the TMA-stream layout (v2 kernel) walks the same arithmetic in consumption order
+    assert ML.stream_supported(d, F.hidden_width(d), 3, lay.kind)
+    st = ML.build_stream(d, F.hidden_width(d), 3, T, lay.kind)
+    sp = pack_stream(st, raw)
+    assert np.all(st.chunks[:, 2] % 4 == 0) and np.all(st.chunks[:, 3] % 4 == 0) and st.chunks[:, 3].max() == st.slot_floats
+    z2, l2 = sweep_stream(lay, st, sp, x.numpy(), inverse=False)
+    np.testing.assert_allclose(z2, zs, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(l2, ls, rtol=1e-5, atol=1e-5)
+    x2, li2 = sweep_stream(lay, st, sp, z.numpy(), inverse=True)
+    tol2 = 5e-3 if (d <= 5 and kind == "maf") else tol     # the x1.5 weights amplify fp32 summation-order noise
+    np.testing.assert_allclose(x2, xs, rtol=tol2, atol=tol2)
+    np.testing.assert_allclose(li2, lis, rtol=tol2, atol=tol2)
 
 
 def test_masks_match_oracle():
