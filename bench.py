@@ -253,12 +253,14 @@ def run_b200(args):
     th = threading.Thread(target=clocks_sampler, args=(stop_evt, clock_lines), daemon=True)
     th.start()
     barrier()
+    torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         device_step()
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     launches = eng.launches
     eng.launches = 0

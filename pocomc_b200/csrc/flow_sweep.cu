@@ -249,6 +249,7 @@ made_sweep_kernel(const float* __restrict__ packed, const int* __restrict__ meta
 // by one producer lane with cp.async.bulk (TMA 1-D bulk copy) + mbarrier complete_tx; the consumer
 // warps (PW particles x LPP reduction slices each) only ever touch shared memory inside a hop.
 constexpr int STREAM_STAGES = 3;   // ring depth; keep in sync with made_layout.STREAM_STAGES
+constexpr int STREAM_MAX_THREADS = 640;   // 1 producer + 19 consumer warps: leaves 102 registers per thread
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -276,38 +277,52 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// acc[0..3] = sum over rows s = q, q+LPP, ... < nrows of slab[s][0..3] * act[s][p]; slab and act in
-// shared memory (slab rows are 16 B -> the LPP slices of a warp read 16*LPP contiguous bytes).
+// Partial dot products of one 4-unit slab: acc[j] = sum over this lane's rows s = q, q+LPP, ... of
+// slab[s][j] * act[s][p].  `rows` is a multiple of 16 (the stream pads every slab with zero rows and
+// the activation arrays are zero-initialised / finite), so the loop has no tail.
 template <int LPP>
-__device__ __forceinline__ void dot4s(const float* slab, int nrows, const float* act, int p, int q, float (&acc)[4]) {
-  constexpr int PW = 32 / LPP;
+__device__ __forceinline__ void dot4_partial(const float4* __restrict__ wp, const float* __restrict__ ap, int rows,
+                                             float (&acc)[4]) {
+  constexpr int STEP = 16 / LPP;          // lane-rows per 16 slab rows (2 for LPP=8, 1 for LPP=16)
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-  const float4* wp = reinterpret_cast<const float4*>(slab) + q;
-  const float* ap = act + q * PW + p;
-  int s = q;
 #pragma unroll 2
-  for (; s + LPP < nrows; s += 2 * LPP) {
-    const float4 w0 = wp[0], w1 = wp[LPP];
-    const float x0 = ap[0], x1 = ap[32];
-    a0 = fmaf(w0.x, x0, a0); a1 = fmaf(w0.y, x0, a1); a2 = fmaf(w0.z, x0, a2); a3 = fmaf(w0.w, x0, a3);
-    b0 = fmaf(w1.x, x1, b0); b1 = fmaf(w1.y, x1, b1); b2 = fmaf(w1.z, x1, b2); b3 = fmaf(w1.w, x1, b3);
-    wp += 2 * LPP; ap += 64;
-  }
-  if (s < nrows) {
+  for (int s = 0; s < rows; s += 16) {
     const float4 w0 = wp[0];
     const float x0 = ap[0];
     a0 = fmaf(w0.x, x0, a0); a1 = fmaf(w0.y, x0, a1); a2 = fmaf(w0.z, x0, a2); a3 = fmaf(w0.w, x0, a3);
+    if (STEP == 2) {
+      const float4 w1 = wp[LPP];
+      const float x1 = ap[32];
+      b0 = fmaf(w1.x, x1, b0); b1 = fmaf(w1.y, x1, b1); b2 = fmaf(w1.z, x1, b2); b3 = fmaf(w1.w, x1, b3);
+    }
+    wp += 16; ap += 16 * (32 / LPP);
   }
   acc[0] = a0 + b0; acc[1] = a1 + b1; acc[2] = a2 + b2; acc[3] = a3 + b3;
+}
+
+// Sum the LPP slices of a particle.  Reduce-scatter: after the call every lane holds the complete sum
+// of ONE unit, index ((lane>>4)&1)*2 + ((lane>>3)&1) (7 shuffles+adds instead of a 24-instruction
+// butterfly over all four).
+template <int LPP>
+__device__ __forceinline__ float reduce_scatter4(const float (&acc)[4], int lane) {
+  const bool hi = lane & 16;
+  const float k0 = (hi ? acc[2] : acc[0]) + __shfl_xor_sync(FULL, hi ? acc[0] : acc[2], 16);
+  const float k1 = (hi ? acc[3] : acc[1]) + __shfl_xor_sync(FULL, hi ? acc[1] : acc[3], 16);
+  const bool mid = lane & 8;
+  float r = (mid ? k1 : k0) + __shfl_xor_sync(FULL, mid ? k0 : k1, 8);
+  r += __shfl_xor_sync(FULL, r, 4);
+  if (LPP == 16) r += __shfl_xor_sync(FULL, r, 2);
+  return r;
+}
+template <int LPP>
+__device__ __forceinline__ float butterfly(float v) {
 #pragma unroll
-  for (int o = PW; o < 32; o <<= 1) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
-  }
+  for (int o = 32 / LPP; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
 }
 
 template <class UNI, int LPP>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(STREAM_MAX_THREADS, 1)
 made_sweep_stream_kernel(const float* __restrict__ stream, const int* __restrict__ meta, int meta_len,
                          const float* __restrict__ in, float* __restrict__ out, float* __restrict__ ladj_out,
                          long long n, int inverse, int ppc) {
@@ -319,6 +334,7 @@ made_sweep_stream_kernel(const float* __restrict__ stream, const int* __restrict
   for (int i = threadIdx.x; i < meta_len; i += blockDim.x) sm[i] = meta[i];
   __syncthreads();
   const int D = sm[M_D], H = sm[M_H], L = sm[M_L], T = sm[M_T], ng = sm[M_NG];
+  const int Dp = (D + 15) & ~15, Hp = (H + 15) & ~15;      // padded row counts of the activation arrays
   const int tstride = sm[M_TSTRIDE], nchunks = sm[M_NCHUNKS], slot_floats = sm[M_SLOT_FLOATS];
   const int* gstart = sm + sm[M_OFF_GSTART];
   const int* nchunk = sm + sm[M_OFF_NCHUNK];
@@ -361,19 +377,23 @@ made_sweep_stream_kernel(const float* __restrict__ stream, const int* __restrict
   const int cw = warp - 1;
   if (cw >= active) return;
 
-  // ---- consumers
+  // ---- consumers: warp = PW particles x LPP reduction slices, lane = q * PW + p
   const int p = lane % PW, q = lane / PW;
-  const int per_warp = (2 * D + L * H) * PW;
+  const int per_warp = (D + Dp + L * Hp) * PW;
   float* cur = acts + (size_t)cw * per_warp;  // [D][PW] running vector (feature order)
-  float* xs = cur + D * PW;                   // [D][PW] data-side values by ORDER position (MLP inputs)
-  float* act = xs + D * PW;                   // [L][H][PW]
+  float* xs = cur + D * PW;                   // [Dp][PW] data-side values by ORDER position (MLP inputs)
+  float* act = xs + Dp * PW;                  // [L][Hp][PW]
   const long long row0 = cta_row0 + (long long)cw * PW;
   const int rows = (int)min((long long)PW, n - row0);
+  for (int i = lane; i < (Dp + L * Hp) * PW; i += 32) xs[i] = 0.0f;
   for (int i = lane; i < PW * D; i += 32) {
     const int r = i / D, c = i - r * D;
     cur[c * PW + r] = (r < rows) ? in[row0 * D + i] : 0.0f;
   }
   __syncwarp();
+  const int unit_i = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);           // unit this lane owns after a reduce-scatter
+  const bool writer = (LPP == 8) ? ((lane & 4) == 0) : ((lane & 6) == 0); // one lane per (unit, particle)
+  const float* act_last = act + (size_t)(L - 1) * Hp * PW + lane;          // + lane == q*PW + p
   float ladj = 0.0f;
   int it = 0;
   for (int tt = 0; tt < T; ++tt) {
@@ -382,25 +402,27 @@ made_sweep_stream_kernel(const float* __restrict__ stream, const int* __restrict
     for (int c = 0; c < nchunks; ++c, ++it) {
       const int slot = it % NS;
       mbar_wait(full + slot, (it / NS) & 1);
-      const float* w = ring + (size_t)slot * slot_floats;
+      const float4* w = reinterpret_cast<const float4*>(ring + (size_t)slot * slot_floats);
       const int k0 = chunks[4 * c], k1 = chunks[4 * c + 1];
       for (int k = k0; k < k1; ++k) {
         const int feat = rev ? (D - 1 - k) : k;
-        const int Ek = gstart[k];   // sorted units with degree <= k
+        const int Ek16 = (gstart[k] + 15) & ~15;   // sorted units with degree <= k, padded
         float phi[TP];
 #pragma unroll
         for (int cc = 0; cc < TP / 4; ++cc) {
           float acc[4];
-          dot4s<LPP>(w, Ek, act + (size_t)(L - 1) * H * PW, p, q, acc);
-          w += 4 * Ek;
-          phi[4 * cc + 0] = acc[0]; phi[4 * cc + 1] = acc[1]; phi[4 * cc + 2] = acc[2]; phi[4 * cc + 3] = acc[3];
+          dot4_partial<LPP>(w + q, act_last, Ek16, acc);
+          w += Ek16;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            phi[4 * cc + j] = (4 * cc + j < UNI::TOTAL) ? butterfly<LPP>(acc[j]) : 0.0f;
         }
 #pragma unroll
         for (int cc = 0; cc < TP / 4; ++cc) {
-          const float4 b = reinterpret_cast<const float4*>(w)[cc];
+          const float4 b = w[cc];
           phi[4 * cc + 0] += b.x; phi[4 * cc + 1] += b.y; phi[4 * cc + 2] += b.z; phi[4 * cc + 3] += b.w;
         }
-        w += TP;
+        w += TP / 4;
         const float v = cur[feat * PW + p];
         float l;
         const float res = UNI::apply(phi, v, inverse != 0, l);
@@ -416,27 +438,26 @@ made_sweep_stream_kernel(const float* __restrict__ stream, const int* __restrict
         const int gs = gstart[g - 1], ge = gstart[g];
         if (ge == gs) continue;
         const int nch = nchunk[g - 1];
+        const int g16 = (g + 15) & ~15, Eg16 = (ge + 15) & ~15;
+        const float* src = xs;
+        float* dst = act;
         for (int l_ = 0; l_ < L; ++l_) {
-          const int nrows = (l_ == 0) ? g : ge;
-          const float* src = (l_ == 0) ? xs : act + (size_t)(l_ - 1) * H * PW;
-          float* dst = act + (size_t)l_ * H * PW;
-          const float* bias = w + (size_t)nch * nrows * 4;
-          for (int cc = 0; cc < nch; ++cc) {
+          const int nrows = (l_ == 0) ? g16 : Eg16;
+          const float* bias = reinterpret_cast<const float*>(w + (size_t)nch * nrows);
+          int u = gs + unit_i;
+          for (int cc = 0; cc < nch; ++cc, u += 4) {
             float acc[4];
-            dot4s<LPP>(w, nrows, src, p, q, acc);
-            w += 4 * nrows;
-            const float4 b = reinterpret_cast<const float4*>(bias)[cc];
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int u = gs + 4 * cc + i;
-              if (u < ge && q == (i % LPP)) {
-                const float pre = acc[i] + bb[i];
-                dst[u * PW + p] = fmaxf(l_ == 0 ? pre : src[u * PW + p] + pre, 0.0f);   // residual hidden layers
-              }
+            dot4_partial<LPP>(w + q, src + lane, nrows, acc);
+            w += nrows;
+            float r = reduce_scatter4<LPP>(acc, lane) + bias[4 * cc + unit_i];
+            if (writer && u < ge) {
+              if (l_ > 0) r += src[u * PW + p];          // residual hidden layers
+              dst[u * PW + p] = fmaxf(r, 0.0f);
             }
           }
-          w += 4 * nch;
+          w += nch;
+          src = dst;
+          dst += Hp * PW;
           __syncwarp();
         }
       }
@@ -517,7 +538,7 @@ static int launch_stream(const float* stream, const int* meta, int meta_len, con
   const int D = hmeta[M_D], H = hmeta[M_H], L = hmeta[M_L];
   const size_t fixed = (((size_t)meta_len * 4 + 15) & ~(size_t)15) + 2 * STREAM_STAGES * 8 + 256 +
                        (size_t)STREAM_STAGES * hmeta[M_SLOT_FLOATS] * 4;
-  const size_t per_particle = (size_t)(2 * D + L * H) * 4;
+  const size_t per_particle = (size_t)(D + ((D + 15) & ~15) + L * ((H + 15) & ~15)) * 4;
   const size_t budget = 227 * 1024;
   PMC_REQUIRE(fixed + 8 * per_particle <= budget, "pmc_flow_sweep: flow too large for the stream kernel");
   const int sms = sm_count();
@@ -527,7 +548,7 @@ static int launch_stream(const float* stream, const int* meta, int meta_len, con
   int lpp = 8;
   if (per_sm <= 8) lpp = 16;
   const int pw = 32 / lpp;
-  long long cap = std::min<long long>(max_smem, 31LL * pw) / pw * pw;
+  long long cap = std::min<long long>(max_smem, (long long)(STREAM_MAX_THREADS / 32 - 1) * pw) / pw * pw;
   if (cap < pw) { set_error("pmc_flow_sweep: shared memory too small for one tile"); return 3; }
   long long waves = (per_sm + cap - 1) / cap;
   long long ppc = (n + waves * sms - 1) / (waves * sms);

@@ -220,6 +220,8 @@ class StreamLayout:
     """Consumption-ordered weight stream for the TMA-fed sweep kernel (csrc/flow_sweep.cu, v2).
 
     One transform = D stages; stage k holds, in the order the kernel reads them,
+      (every slab's row count is padded to a multiple of 16 with zero rows so the kernel's inner
+      loop has no tail; the activation arrays it multiplies them with are zero-initialised)
       out hop  : TP/4 slabs [E_k rows][4] (outputs 4c..4c+3 of order position k) + bias [TP]
       group g=k+1 (if it has units), nch = ceil(size/4) chunks of 4 units:
         layer 0 : nch slabs [g rows][4] (input orders 0..g-1) + bias [4 nch]
@@ -236,6 +238,10 @@ class StreamLayout:
     @property
     def numel(self):
         return int(self.gather.size)
+
+
+def _pad16(n: int) -> int:
+    return (int(n) + 15) // 16 * 16
 
 
 def stream_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int, bins: int = 8) -> bool:
@@ -271,11 +277,11 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
             src = hperm[:ek]
             wo, bo = base_r + raw_off[2 * L], base_r + raw_off[2 * L + 1]
             for c in range(tp // 4):
-                blk = np.full((ek, 4), -1, np.int64)
+                blk = np.full((_pad16(ek), 4), -1, np.int64)
                 for j in range(4):
                     o = 4 * c + j
                     if o < total:
-                        blk[:, j] = wo + (feat * total + o) * H + src
+                        blk[:ek, j] = wo + (feat * total + o) * H + src
                 parts.append(blk.reshape(-1))
             b = np.full(tp, -1, np.int64)
             b[:total] = bo + feat * total + np.arange(total)
@@ -292,11 +298,11 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
                     rows = iperm[np.arange(g)] if l == 0 else hperm[:eg]
                     width = D if l == 0 else H
                     for c in range(nch):
-                        blk = np.full((len(rows), 4), -1, np.int64)
+                        blk = np.full((_pad16(len(rows)), 4), -1, np.int64)
                         for j in range(4):
                             u = upad[4 * c + j]
                             if u >= 0:
-                                blk[:, j] = wl + u * width + rows
+                                blk[:len(rows), j] = wl + u * width + rows
                         parts.append(blk.reshape(-1))
                     parts.append(np.where(upad >= 0, bl + upad, -1))
             stages.append(np.concatenate(parts))

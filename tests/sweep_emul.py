@@ -144,9 +144,11 @@ def sweep_stream(layout, stream, packed, x, inverse):
                 feat = D - 1 - k if t % 2 else k
                 ek = int(gstart[k])
                 phi = np.zeros((n, tp), np.float32)
+                p16 = lambda v: (v + 15) // 16 * 16
                 for c in range(tp // 4):
-                    slab = w[pos:pos + 4 * ek].reshape(ek, 4); pos += 4 * ek
-                    phi[:, 4 * c:4 * c + 4] = act[L - 1][:, :ek] @ slab
+                    slab = w[pos:pos + 4 * p16(ek)].reshape(p16(ek), 4); pos += 4 * p16(ek)
+                    assert not slab[ek:].any()
+                    phi[:, 4 * c:4 * c + 4] = act[L - 1][:, :ek] @ slab[:ek]
                 phi += w[pos:pos + tp]; pos += tp
                 v = cur[:, feat].copy()
                 res, l = uni(phi, v, inverse)
@@ -162,8 +164,9 @@ def sweep_stream(layout, stream, packed, x, inverse):
                     src = xs[:, :g] if l_ == 0 else act[l_ - 1][:, :ge]
                     pre = np.zeros((n, 4 * nch), np.float32)
                     for c in range(nch):
-                        slab = w[pos:pos + 4 * nrows].reshape(nrows, 4); pos += 4 * nrows
-                        pre[:, 4 * c:4 * c + 4] = src @ slab
+                        slab = w[pos:pos + 4 * p16(nrows)].reshape(p16(nrows), 4); pos += 4 * p16(nrows)
+                        assert not slab[nrows:].any()
+                        pre[:, 4 * c:4 * c + 4] = src @ slab[:nrows]
                     pre += w[pos:pos + 4 * nch]; pos += 4 * nch
                     pre = pre[:, :ge - gs]
                     if l_ > 0:
