@@ -62,7 +62,7 @@ class Workload:
         self.bounds = np.array([dd.support() for dd in self.dists])
 
     def loglike(self, x):
-        return -0.5 * np.einsum("ki,ij,kj->k", x, self.prec, x) + self.c0
+        return -0.5 * np.sum((x @ self.prec) * x, axis=1) + self.c0
 
     def logprior(self, x):
         out = np.zeros(len(x))
@@ -269,7 +269,8 @@ def run_b200(args):
     accept_dev = eng.accept
 
     # ---- arm 2: end to end through the reference-facing kernel seam, host buffers ---------------
-    fd_host = dict(loglike=lambda x: (wl.loglike(x), None), logprior=wl.logprior, scaler=scaler, flow=flow,
+    prior = pc.Prior(wl.dists)          # what Sampler passes: prior.logpdf (device fast path for norm/uniform factors)
+    fd_host = dict(loglike=lambda x: (wl.loglike(x), None), logprior=prior.logpdf, scaler=scaler, flow=flow,
                    theta_geometry=geo, u_geometry=geo)
     od_host = dict(n_max=MCMC_STEPS, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / N_DIM ** 0.5, shard=shard, seed=1234)
 
@@ -292,8 +293,8 @@ def run_b200(args):
 
     per_call_h2d = n_local * (2 * N_DIM + 3) * 8
     per_call_d2h = n_local * (2 * N_DIM + 3) * 8
-    per_mcmc_d2h = n_local * (N_DIM * 8 + 1) + (M.CTL_MU + N_DIM) * 8
-    per_mcmc_h2d = n_local * 2 * 8
+    per_mcmc_d2h = n_local * (N_DIM * 8 + 1) + (M.CTL_MU + N_DIM) * 8     # x', finite mask, controller block
+    per_mcmc_h2d = n_local * 8                                             # logl' (log-prior evaluated on the GPU)
     h2d = per_call_h2d + MCMC_STEPS * per_mcmc_h2d
     d2h = per_call_d2h + MCMC_STEPS * per_mcmc_d2h
 
@@ -322,7 +323,7 @@ def run_b200(args):
                 vs_baseline=None, dtype="f32 flow / f64 SMC state", data="synthetic",
                 config=workload_config(world, MCMC_STEPS), clocks=summarise_clocks(clock_lines),
                 e2e=dict(value=e2e_value, unit="particle-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=1e3 * t_e2e / args.steps, rng="device Philox", callbacks="host numpy likelihood + scipy prior"),
+                         ms_per_step=1e3 * t_e2e / args.steps, rng="device Philox", callbacks="host numpy likelihood (black box); pc.Prior of scipy norm factors evaluated on the GPU"),
                 gpu_launches=launches, roofline=roofline, accept_rate=accept_dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -13,11 +13,16 @@ device_callbacks
     False (default): prior and likelihood are host black boxes like the reference's (x' crosses
     PCIe every MCMC step).  True: a likelihood object exposing ``device(x, finite, out)`` and a
     ``Prior`` of frozen scipy ``norm`` / ``uniform`` factors are evaluated on the GPU instead.
+device_prior
+    True (default): when the prior handed to the MCMC kernels is ``pocomc_b200.Prior.logpdf`` of
+    frozen scipy ``norm`` / ``uniform`` factors, log-prior values are computed on the GPU
+    (identical formula, f64); any other prior object is called on the host like the reference does.
 """
 import os
 
 rng_mode = os.environ.get("PMC_B200_RNG", "host")
 mean_mode = None  # None -> 1 for "host", 0 for "device"
+device_prior = os.environ.get("PMC_B200_DEVICE_PRIOR", "1") == "1"
 device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
 
 

@@ -52,6 +52,13 @@ class McmcEngine:
         self.log_prior = function_dict.get('logprior')
         self.loglike_device = function_dict.get('loglike_device')
         self.logprior_device = function_dict.get('logprior_device')
+        if self.logprior_device is None and config.device_prior:
+            # Sampler passes prior.logpdf (sampler.py:203); a pocomc_b200.Prior of norm/uniform factors has a device form
+            owner = getattr(self.log_prior, '__self__', None)
+            spec = owner.device_spec() if hasattr(owner, 'device_spec') else None
+            if spec is not None:
+                from .synthetic import DevicePrior
+                self.logprior_device = DevicePrior(*spec)
         self.scaler = function_dict.get('scaler')
         geometry = function_dict.get('theta_geometry' if self.use_flow else 'u_geometry')
         self.with_bc = (self.scaler.periodic is not None) or (self.scaler.reflective is not None)
@@ -185,28 +192,44 @@ class McmcEngine:
                   _lib.ptr(self.ldj_p), _lib.ptr(self.finite), n, d)
 
     def evaluate_host(self):
-        """Host black boxes on the finite rows only (mcmc.py:100-121)."""
+        """Host black boxes on the finite rows only (mcmc.py:100-121).  When the prior is a
+        ``pocomc_b200.Prior`` of frozen scipy norm / uniform factors it is evaluated on the GPU
+        (config.device_prior) and only the likelihood crosses the PCIe bus."""
         n = self.n
+        if self.logprior_device is not None:
+            self.logprior_device(self.x_p, self.finite, self.logp_p)       # also clears finite where logp' is not finite
         self.h_x.copy_(self.x_p, non_blocking=True)
         self.h_fin.copy_(self.finite, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         x_p = self.h_x.numpy()
-        mask = self.h_fin.numpy().astype(bool)
-        logp_p = np.full(n, -np.inf)
-        logp_p[mask] = self.log_prior(x_p[mask])
-        mask = mask & np.isfinite(logp_p)
-        logl_p = np.full(n, -np.inf)
-        blobs_p = None
-        if self.have_blobs:
-            blobs_p = np.empty(n, dtype=np.dtype((self.blobs[0].dtype, self.blobs[0].shape)))
-            logl_p[mask], blobs_p[mask] = self.log_like(x_p[mask])
-        else:
-            logl_p[mask], _ = self.log_like(x_p[mask])
-        calls = int(np.sum(mask))
+        mask = self.h_fin.numpy().view(np.bool_)
+        all_rows = bool(mask.all())
         hl = self.h_ll.numpy()
-        hl[0], hl[1] = logl_p, logp_p
+        if self.logprior_device is None:
+            logp_p = hl[1]
+            if all_rows:
+                logp_p[:] = self.log_prior(x_p)
+            else:
+                logp_p.fill(-np.inf)
+                logp_p[mask] = self.log_prior(x_p[mask])
+            ok = np.isfinite(logp_p)
+            if not ok.all():
+                mask = mask & ok
+                all_rows = False
+            self.logp_p.copy_(self.h_ll[1], non_blocking=True)
+        logl_p = hl[0]
+        blobs_p = None
+        if all_rows and not self.have_blobs:
+            logl_p[:], _ = self.log_like(x_p)
+        else:
+            logl_p.fill(-np.inf)
+            if self.have_blobs:
+                blobs_p = np.empty(n, dtype=np.dtype((self.blobs[0].dtype, self.blobs[0].shape)))
+                logl_p[mask], blobs_p[mask] = self.log_like(x_p[mask])
+            else:
+                logl_p[mask], _ = self.log_like(x_p[mask])
+        calls = n if all_rows else int(np.sum(mask))
         self.logl_p.copy_(self.h_ll[0], non_blocking=True)
-        self.logp_p.copy_(self.h_ll[1], non_blocking=True)
         return calls, blobs_p
 
     def evaluate_device(self):
