@@ -74,9 +74,16 @@ def load():
     return lib
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    global _cuda_ok
+    if _cuda_ok:
+        return
     if not torch.cuda.is_available():
         raise RuntimeError("pocomc_b200: no CUDA device -- the hot path is CUDA-only (sm_100a); there is no CPU fallback")
+    _cuda_ok = True
 
 
 def ptr(t):
@@ -85,7 +92,24 @@ def ptr(t):
 
 
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """raw cudaStream_t of torch's current stream on the current device (cheap: no Stream object)."""
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+_pinned = {}
+
+
+def pinned(tag: str, shape, dtype):
+    """Process-wide cache of pinned host staging buffers (cudaHostAlloc costs milliseconds; the MCMC
+    engine is rebuilt for every ``_mutate`` call).  One buffer per (tag, shape, dtype)."""
+    key = (tag, tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,))), dtype)
+    buf = _pinned.get(key)
+    if buf is None:
+        if len(_pinned) > 64:
+            _pinned.clear()
+        buf = torch.empty(key[1], dtype=dtype).pin_memory()
+        _pinned[key] = buf
+    return buf
 
 
 def check(code: int, what: str = ""):

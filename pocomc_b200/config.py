@@ -17,11 +17,17 @@ device_prior
     True (default): when the prior handed to the MCMC kernels is ``pocomc_b200.Prior.logpdf`` of
     frozen scipy ``norm`` / ``uniform`` factors, log-prior values are computed on the GPU
     (identical formula, f64); any other prior object is called on the host like the reference does.
+sweep_variant
+    ``"ffma"`` (default): the fp32-FMA TMA-stream sweep kernel.  ``"mma"``: experimental warp-MMA
+    sweep (mma.sync TF32 with a 3xTF32 split, passes the same parity tests) -- slower on B200 at the
+    benchmark sizes (505 us vs 344 us per 10 000-particle inverse) because 16 particles per warp and
+    1.8 KB of activations per particle leave ~1 warp per scheduler.  Read when a flow is constructed.
 """
 import os
 
 rng_mode = os.environ.get("PMC_B200_RNG", "host")
 mean_mode = None  # None -> 1 for "host", 0 for "device"
+sweep_variant = os.environ.get("PMC_B200_SWEEP", "ffma")
 device_prior = os.environ.get("PMC_B200_DEVICE_PRIOR", "1") == "1"
 device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
 

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, config
 from . import made_layout as ML
 from .tools import torch_double_to_float
 
@@ -106,7 +106,8 @@ class MaskedAutoregressiveFlow(nn.Module):
         # kernel-side weight layout: the TMA-streamed consumption-order stream when the network fits the
         # stream kernel's shared-memory budget, else the degree-sorted slab layout of the v1 kernel
         if ML.stream_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind, lay.bins):
-            klay = ML.build_stream(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+            klay = ML.build_stream(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins,
+                                   variant=config.sweep_variant)
             self.packed_numel = klay.numel
         else:
             klay = lay

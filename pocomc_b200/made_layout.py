@@ -254,8 +254,35 @@ def stream_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int, bins: 
     return STREAM_STAGES * slot * 4 + 8 * (2 * n_dim + n_layers * n_hidden) * 4 + 4096 <= STREAM_SMEM_BUDGET
 
 
+def _mma_slab(row_idx, col_idx_fn, n_cols):
+    """One hop's weights in mma.sync m16n8k8 B-fragment order: [n-tile][k-step][lane][2] with
+    lane = 4*g + t holding W[8*ks + t + 4*j][8*nt + g], j = 0, 1.  ``row_idx`` are the raw row keys
+    (K of them, padded with zero rows to a multiple of 8); ``col_idx_fn(c, rows)`` gives the raw indices
+    of column c for those rows (or None for a padding column)."""
+    K = len(row_idx)
+    K8 = (K + 7) // 8 * 8
+    NT = (n_cols + 7) // 8
+    dense = np.full((K8, NT * 8), -1, np.int64)
+    for c in range(n_cols):
+        col = col_idx_fn(c, row_idx)
+        if col is not None:
+            dense[:K, c] = col
+    lane = np.arange(32)
+    g, t = lane >> 2, lane & 3
+    out = np.empty((NT, K8 // 8, 32, 2), np.int64)
+    for nt in range(NT):
+        for ks in range(K8 // 8):
+            for j in range(2):
+                out[nt, ks, :, j] = dense[8 * ks + t + 4 * j, 8 * nt + g]
+    return out.reshape(-1)
+
+
 @lru_cache(maxsize=None)
-def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8) -> StreamLayout:
+def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8,
+                 variant: str = "ffma") -> StreamLayout:
+    """variant "ffma": slabs [rows16][4] for the fp32-FMA stream kernel; "mma": B-fragment-ordered
+    slabs for the warp-MMA (3xTF32 mma.sync) stream kernel."""
+    mma = variant == "mma"
     lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
     D, H, L, T, total, tp = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.total, lay.tp
     ng = D - 1
@@ -276,16 +303,23 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
             ek = int(gstart[k - 1 + 1]) if k >= 1 else 0          # units of degree <= k  (gstart[k] = #deg < k+1)
             src = hperm[:ek]
             wo, bo = base_r + raw_off[2 * L], base_r + raw_off[2 * L + 1]
-            for c in range(tp // 4):
+            if mma:
+                parts.append(_mma_slab(src, lambda c, rows: wo + (feat * total + c) * H + rows, total))
+                ntp = (total + 7) // 8 * 8
+                b = np.full(ntp, -1, np.int64)
+                b[:total] = bo + feat * total + np.arange(total)
+                parts.append(b)
+            for c in range(0 if mma else tp // 4):
                 blk = np.full((_pad16(ek), 4), -1, np.int64)
                 for j in range(4):
                     o = 4 * c + j
                     if o < total:
                         blk[:ek, j] = wo + (feat * total + o) * H + src
                 parts.append(blk.reshape(-1))
-            b = np.full(tp, -1, np.int64)
-            b[:total] = bo + feat * total + np.arange(total)
-            parts.append(b)
+            if not mma:
+                b = np.full(tp, -1, np.int64)
+                b[:total] = bo + feat * total + np.arange(total)
+                parts.append(b)
             g = k + 1
             if g <= ng and gsize[g - 1] > 0:
                 units = hperm[gstart[g - 1]:gstart[g]]
@@ -297,6 +331,13 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
                     wl, bl = base_r + raw_off[2 * l], base_r + raw_off[2 * l + 1]
                     rows = iperm[np.arange(g)] if l == 0 else hperm[:eg]
                     width = D if l == 0 else H
+                    if mma:
+                        parts.append(_mma_slab(rows, lambda c, rr, wl=wl, width=width: wl + units[c] * width + rr, len(units)))
+                        n8 = (len(units) + 7) // 8 * 8
+                        bb = np.full(n8, -1, np.int64)
+                        bb[:len(units)] = bl + units
+                        parts.append(bb)
+                        continue
                     for c in range(nch):
                         blk = np.full((_pad16(len(rows)), 4), -1, np.int64)
                         for j in range(4):
@@ -331,7 +372,7 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
     meta[M_MAXCH] = int(nchunk.max())
     meta[M_RAW_TSTRIDE] = lay.raw_tstride
     meta[M_BINS] = bins
-    meta[M_VERSION] = 2
+    meta[M_VERSION] = 3 if mma else 2
     meta[M_NCHUNKS] = len(chunks)
     meta[M_SLOT_FLOATS] = slot_floats
     pos = META_HEADER

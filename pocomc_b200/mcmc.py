@@ -102,7 +102,7 @@ class McmcEngine:
         ctl[CTL_SIGMA], ctl[CTL_BEST] = sigma, best
         ctl[CTL_MU:] = mu
         self.ctl = _f64(ctl, dev)
-        self.ctl_host = torch.empty(CTL_MU + d, dtype=torch.float64).pin_memory()
+        self.ctl_host = _lib.pinned('ctl', CTL_MU + d, torch.float64)
         # -- per-step buffers
         f64 = dict(dtype=torch.float64, device=dev)
         self.g = torch.empty(n, **f64) if self.tp else None
@@ -123,10 +123,10 @@ class McmcEngine:
         self.alpha = torch.empty(n, **f64)
         self.partials = torch.empty(int(_lib.load().pmc_mh_partials_size(n, d)), **f64)
         # pinned staging
-        self.h_x = torch.empty((n, d), dtype=torch.float64).pin_memory()
-        self.h_fin = torch.empty(n, dtype=torch.uint8).pin_memory()
-        self.h_ll = torch.empty((2, n), dtype=torch.float64).pin_memory()
-        self.h_noise = torch.empty(n * (d + 2), dtype=torch.float64).pin_memory() if config.rng_mode == "host" else None
+        self.h_x = _lib.pinned('x', (n, d), torch.float64)
+        self.h_fin = _lib.pinned('fin', n, torch.uint8)
+        self.h_ll = _lib.pinned('ll', (2, n), torch.float64)
+        self.h_noise = _lib.pinned('noise', n * (d + 2), torch.float64) if config.rng_mode == "host" else None
         self.rng_mode = config.rng_mode
         self.mean_mode = config.resolved_mean_mode()
         # particle sharding: option_dict['shard'] = (global offset of row 0, global particle count, blocks per rank)

@@ -174,3 +174,65 @@ def sweep_stream(layout, stream, packed, x, inverse):
                     act[l_][:, gs:ge] = np.maximum(pre, 0)
             assert pos == cnt
     return cur, ladj
+
+
+def _mma_dense(w, pos, K, n_cols):
+    """Inverse of made_layout._mma_slab: (dense [K8, NT*8] matrix, floats consumed)."""
+    K8, NT = (K + 7) // 8 * 8, (n_cols + 7) // 8
+    cnt = NT * (K8 // 8) * 64
+    blk = w[pos:pos + cnt].reshape(NT, K8 // 8, 32, 2)
+    dense = np.zeros((K8, NT * 8), np.float32)
+    lane = np.arange(32)
+    g, t = lane >> 2, lane & 3
+    for nt in range(NT):
+        for ks in range(K8 // 8):
+            for j in range(2):
+                dense[8 * ks + t + 4 * j, 8 * nt + g] = blk[nt, ks, :, j]
+    return dense, cnt
+
+
+def sweep_stream_mma(layout, stream, packed, x, inverse):
+    """Emulates the warp-MMA stream kernel's walk over the "mma" stream variant (fp32 arithmetic)."""
+    m = stream.meta
+    D, H, L, T, ng, total = (int(m[i]) for i in (ML.M_D, ML.M_H, ML.M_L, ML.M_T, ML.M_NG, ML.M_TOTAL))
+    gstart = m[m[ML.M_OFF_GSTART]:m[ML.M_OFF_GSTART] + ng + 1]
+    chunks = m[m[ML.M_OFF_CHUNKS]:m[ML.M_OFF_CHUNKS] + 4 * m[ML.M_NCHUNKS]].reshape(-1, 4)
+    uni = affine if layout.kind == ML.KIND_AFFINE else rqs
+    cur = np.array(x, np.float32, copy=True)
+    n = len(cur)
+    ladj = np.zeros(n, np.float32)
+    for tt in range(T):
+        t = T - 1 - tt if inverse else tt
+        xs = np.zeros((n, D), np.float32)
+        act = np.zeros((L, n, H), np.float32)
+        for k0, k1, off, cnt in chunks:
+            w = packed[t * stream.tstride + off: t * stream.tstride + off + cnt]
+            pos = 0
+            for k in range(k0, k1):
+                feat = D - 1 - k if t % 2 else k
+                ek = int(gstart[k])
+                dense, c = _mma_dense(w, pos, ek, total); pos += c
+                assert not dense[ek:].any() and not dense[:, total:].any()
+                ntp = (total + 7) // 8 * 8
+                phi = act[L - 1][:, :ek] @ dense[:ek] + w[pos:pos + ntp]; pos += ntp
+                v = cur[:, feat].copy()
+                res, l = uni(phi[:, :layout.tp], v, inverse)
+                ladj = ladj - l if inverse else ladj + l
+                xs[:, k] = res if inverse else v
+                cur[:, feat] = res
+                g = k + 1
+                if g > ng or gstart[g] == gstart[g - 1]:
+                    continue
+                gs, ge = int(gstart[g - 1]), int(gstart[g])
+                for l_ in range(L):
+                    nrows = g if l_ == 0 else ge
+                    src = xs[:, :g] if l_ == 0 else act[l_ - 1][:, :ge]
+                    dense, c = _mma_dense(w, pos, nrows, ge - gs); pos += c
+                    n8 = (ge - gs + 7) // 8 * 8
+                    pre = src @ dense[:nrows] + w[pos:pos + n8]; pos += n8
+                    pre = pre[:, :ge - gs]
+                    if l_ > 0:
+                        pre = pre + act[l_ - 1][:, gs:ge]
+                    act[l_][:, gs:ge] = np.maximum(pre, 0)
+            assert pos == cnt
+    return cur, ladj

@@ -65,6 +65,32 @@ def test_sweep_vs_oracle_sizes(preset, d, n):
     np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **tol)
 
 
+@pytest.mark.parametrize("preset,d,n", [("maf6", 32, 700), ("nsf3", 5, 100), ("maf3", 3, 17)])
+def test_warp_mma_variant_matches_oracle(preset, d, n):
+    """the opt-in warp-MMA (3xTF32 mma.sync) sweep meets the same fp32 parity bar as the FFMA kernel"""
+    from pocomc_b200 import config
+    torch.manual_seed(d + n)
+    ref = F.make_flow(d, preset)
+    old = config.sweep_variant
+    config.sweep_variant = "mma"
+    try:
+        f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
+    finally:
+        config.sweep_variant = old
+    assert int(f.flow._meta_host[22]) == 3
+    x = torch.randn(n, d)
+    with torch.no_grad():
+        z_ref, l_ref = ref().transform.call_and_ladj(x)
+        xi_ref, li_ref = ref().transform.inv.call_and_ladj(z_ref)
+        z, l = f.forward(x)
+        xi, li = f.inverse(z_ref)
+    tol = dict(rtol=5e-5, atol=5e-5) if preset.startswith("maf") else dict(rtol=5e-4, atol=5e-4)
+    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **tol)
+    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), **tol)
+    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), **tol)
+    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **tol)
+
+
 def test_flow_properties_like_reference_tests():
     """reference tests/test_flow.py: round trip 1e-5, ladj antisymmetry, f64 warning, 1-row batch, fit stays finite"""
     from pocomc_b200.flow import Flow

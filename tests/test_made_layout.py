@@ -6,7 +6,7 @@ import torch
 
 import flow_ref as F
 from pocomc_b200 import made_layout as ML
-from sweep_emul import pack, pack_stream, sweep, sweep_stream
+from sweep_emul import pack, pack_stream, sweep, sweep_stream, sweep_stream_mma
 
 
 def _raw(flow):
@@ -50,6 +50,16 @@ def test_sweep_matches_oracle(preset, d):
     tol2 = 5e-3 if (d <= 5 and kind == "maf") else tol     # the x1.5 weights amplify fp32 summation-order noise
     np.testing.assert_allclose(x2, xs, rtol=tol2, atol=tol2)
     np.testing.assert_allclose(li2, lis, rtol=tol2, atol=tol2)
+    # ... and the mma.sync B-fragment ordered variant (warp-MMA kernel)
+    sm = ML.build_stream(d, F.hidden_width(d), 3, T, lay.kind, variant="mma")
+    spm = pack_stream(sm, raw)
+    assert sm.meta[ML.M_VERSION] == 3 and np.all(sm.chunks[:, 2] % 4 == 0) and np.all(sm.chunks[:, 3] % 4 == 0)
+    z3, l3 = sweep_stream_mma(lay, sm, spm, x.numpy(), inverse=False)
+    np.testing.assert_allclose(z3, zs, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(l3, ls, rtol=1e-5, atol=1e-5)
+    x3, li3 = sweep_stream_mma(lay, sm, spm, z.numpy(), inverse=True)
+    np.testing.assert_allclose(x3, xs, rtol=tol2, atol=tol2)
+    np.testing.assert_allclose(li3, lis, rtol=tol2, atol=tol2)
 
 
 def test_masks_match_oracle():
