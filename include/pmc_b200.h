@@ -52,6 +52,30 @@ int pmc_flow_sweep(const float* packed, const int32_t* meta, const int32_t* meta
 int pmc_flow_base_logprob(const float* z, const float* ladj, float* logprob, int64_t n, int32_t d,
                           pmc_stream_t stream);
 
+/* ---- tensor-core (tcgen05) dense forward: Flow.forward / Flow.log_prob / training forward ----
+ * (flow.py:99-114,134-147 -> zuko transform.call_and_ladj: one masked-MLP pass per transform.)
+ * `packed` is the TF32 hi/lo weight image described by pocomc_b200.made_layout.build_tc; it is
+ * produced from the flat parameter blob by pmc_flow_tc_pack (gather codes: g >= 0 hi(raw[g]),
+ * -(g+2) lo(raw[g]), g | 2^30 plain copy, -1 zero).  passes = 3: 3xTF32 split, fp32 fidelity;
+ * passes = 1: plain TF32.  in/out [N, D] f32, ladj [N] f32; `meta_host` is a HOST table.        */
+int pmc_flow_tc_pack(const float* raw, const int32_t* gather, float* packed, int64_t n_packed,
+                     pmc_stream_t stream);
+int pmc_flow_forward_tc(const float* packed, const int32_t* meta_host, int32_t meta_len,
+                        const float* in, float* out, float* ladj, int64_t n, int32_t passes,
+                        pmc_stream_t stream);
+
+/* ---- Flow.fit optimiser step (flow.py:268,314-319) -------------------------------------------
+ * torch.nn.utils.clip_grad_norm_(max_norm = hyper[5]; <= 0 disables) followed by
+ * torch.optim.AdamW.step (amsgrad off) over the flat parameter blob, two launches.  `hyper` is a
+ * DEVICE array of 6 doubles {lr, beta1, beta2, eps, weight_decay, clip}; `step` a device int64 that
+ * the call increments (AdamW's t) -- both device-resident so the call can be replayed from a CUDA
+ * graph while the learning rate changes.  scratch: pmc_adamw_scratch_size() doubles.
+ * gnorm_out (may be NULL) receives the un-clipped gradient norm.                                 */
+int64_t pmc_adamw_scratch_size(void);
+int pmc_adamw_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const double* hyper, int64_t* step, double* scratch, float* gnorm_out,
+                        pmc_stream_t stream);
+
 /* ---- MCMC controller state ------------------------------------------------------------------
  * Device-resident f64 block shared by the step kernels so a whole MCMC step is host-sync free:
  * ctl[PMC_CTL_*] scalars followed by mu[D] at ctl[PMC_CTL_MU].                                 */

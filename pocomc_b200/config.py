@@ -22,12 +22,24 @@ sweep_variant
     sweep (mma.sync TF32 with a 3xTF32 split, passes the same parity tests) -- slower on B200 at the
     benchmark sizes (505 us vs 344 us per 10 000-particle inverse) because 16 particles per warp and
     1.8 KB of activations per particle leave ~1 warp per scheduler.  Read when a flow is constructed.
+forward_path
+    ``"tc"`` (default): ``Flow.forward`` / ``log_prob`` without a graph run on the tcgen05 dense kernel
+    (csrc/flow_tc.cu, 3xTF32 split = fp32 fidelity) when the flow is affine with H <= 128 and the batch
+    has at least ``tc_min_rows`` rows; ``"sweep"``: always the degree-ordered sweep kernel.
+fit_path
+    ``"graph"`` (default): every optimiser step of ``Flow.fit`` is one CUDA-graph launch (batch gather,
+    autograd forward/backward, fused clip + AdamW kernel, loss accumulation) -- same arithmetic and RNG
+    consumption as ``"eager"``, which issues the ops one by one.  Noise / L1 / L2 regularised fits
+    always take the eager path.
 """
 import os
 
 rng_mode = os.environ.get("PMC_B200_RNG", "host")
 mean_mode = None  # None -> 1 for "host", 0 for "device"
 sweep_variant = os.environ.get("PMC_B200_SWEEP", "ffma")
+fit_path = os.environ.get("PMC_B200_FIT", "graph")
+forward_path = os.environ.get("PMC_B200_FORWARD", "tc")
+tc_min_rows = int(os.environ.get("PMC_B200_TC_MIN_ROWS", "1"))
 device_prior = os.environ.get("PMC_B200_DEVICE_PRIOR", "1") == "1"
 device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
 

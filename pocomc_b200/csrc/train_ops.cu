@@ -1,0 +1,93 @@
+// Flow.fit optimiser step (pocomc/flow.py:268,314-319): torch.nn.utils.clip_grad_norm_ followed by
+// torch.optim.AdamW.step over the flow's single flat parameter blob, fused into two launches.
+// Hyper-parameters and the step counter live in device memory so the pair can sit inside a CUDA graph
+// whose replay follows learning-rate changes (ReduceLROnPlateau, flow.py:271-277,361) without re-capture.
+//
+// HBM-bound: per parameter read g, p, m, v and write p, m, v = 28 bytes (+4 for the norm pass).
+#include "common.cuh"
+#include <algorithm>
+
+namespace pmc {
+
+enum { HY_LR = 0, HY_BETA1, HY_BETA2, HY_EPS, HY_WD, HY_CLIP, HY_LEN };   // keep in sync with flow.py
+constexpr int NORM_BLOCKS = 296;                                           // 2 per SM; partials summed in fixed order
+
+__global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ partials,
+                                                          long long* __restrict__ step) {
+  double acc = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = (double)g[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += ws[i];
+    partials[blockIdx.x] = s;
+    if (blockIdx.x == 0) step[0] += 1;        // the AdamW step counter t (read by the update kernel)
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, long long n, const double* __restrict__ partials,
+                                                         int n_partials, const double* __restrict__ hyper,
+                                                         const long long* __restrict__ step, float* __restrict__ gnorm_out) {
+  __shared__ float s_coef;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_partials; ++i) s += partials[i];
+    const float total = (float)sqrt(s);                          // torch.linalg.vector_norm result is fp32
+    float coef = 1.0f;
+    if (hyper[HY_CLIP] > 0.0) {
+      coef = (float)hyper[HY_CLIP] / (total + 1e-6f);            // clip_grad_norm_: max_norm / (total_norm + 1e-6), clamped to 1
+      coef = fminf(coef, 1.0f);
+    }
+    s_coef = coef;
+    if (blockIdx.x == 0 && gnorm_out) gnorm_out[0] = total;
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  const double lr = hyper[HY_LR], b1 = hyper[HY_BETA1], b2 = hyper[HY_BETA2];
+  const double t = (double)step[0];
+  const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float eps = (float)hyper[HY_EPS];
+  const float decay = (float)(1.0 - lr * hyper[HY_WD]);
+  const float w1 = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * decay;                                     // param.mul_(1 - lr * weight_decay)
+    const float mi = m[i] + w1 * (gi - m[i]);                    // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(w2 * gi, gi, v[i] * fb2);              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);                              // param.addcdiv_(exp_avg, denom, value=-step_size)
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+}  // namespace pmc
+
+using namespace pmc;
+
+extern "C" int64_t pmc_adamw_scratch_size(void) { return NORM_BLOCKS; }
+
+extern "C" int pmc_adamw_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                   const double* hyper, int64_t* step, double* scratch, float* gnorm_out,
+                                   pmc_stream_t stream) {
+  PMC_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper && step && scratch && n > 0, "pmc_adamw_clip_step: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  int blocks = (int)std::min<long long>(NORM_BLOCKS, (n + 255) / 256);
+  grad_sqnorm_kernel<<<blocks, 256, 0, st>>>(grad, n, scratch, reinterpret_cast<long long*>(step));
+  PMC_LAUNCH_CHECK();
+  const int ublocks = grid_for(n, 256 * 4, 8);
+  adamw_clip_kernel<<<ublocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, scratch, blocks, hyper,
+                                              reinterpret_cast<const long long*>(step), gnorm_out);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}

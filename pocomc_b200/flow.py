@@ -118,15 +118,27 @@ class MaskedAutoregressiveFlow(nn.Module):
         self._packed = None
         self._packed_key = None
         self._masks = None
+        # tensor-core (tcgen05) image of the dense masked MLP for the forward direction
+        self._tc = None
+        if ML.tc_supported(lay.n_dim, lay.n_hidden, lay.kind):
+            self._tc = ML.build_tc(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+            self.register_buffer("tc_gather", torch.from_numpy(self._tc.gather.copy()), persistent=False)
+            self._tc_meta_host = np.ascontiguousarray(self._tc.meta)
+        self._tc_packed = None
+        self._tc_key = None
 
     # -- plumbing ---------------------------------------------------------------------------
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"], st["_packed_key"], st["_masks"] = None, None, None
+        st["_tc_packed"], st["_tc_key"] = None, None
+        st.pop("_fit_engine", None)
         return st
 
     def _apply(self, fn, *a, **k):
         self._packed, self._packed_key, self._masks = None, None, None
+        self._tc_packed, self._tc_key = None, None
+        self.__dict__.pop("_fit_engine", None)
         return super()._apply(fn, *a, **k)
 
     def ensure_cuda(self):
@@ -158,12 +170,45 @@ class MaskedAutoregressiveFlow(nn.Module):
             self._packed_key = key
         return self._packed
 
+    # -- inference: tensor-core dense forward ------------------------------------------------
+    def tc_available(self) -> bool:
+        return self._tc is not None
+
+    def packed_tc(self) -> torch.Tensor:
+        """TF32 hi/lo weight image (mask folded in) for csrc/flow_tc.cu; rebuilt when raw changes."""
+        self.ensure_cuda()
+        key = (self.raw.data_ptr(), self.raw._version)
+        if self._tc_packed is None or self._tc_key != key:
+            if self._tc_packed is None or self._tc_packed.device != self.raw.device:
+                self._tc_packed = torch.empty(self._tc.numel, dtype=torch.float32, device=self.raw.device)
+            _lib.call("pmc_flow_tc_pack", _lib.ptr(self.raw.detach()), _lib.ptr(self.tc_gather), _lib.ptr(self._tc_packed),
+                      self._tc.numel)
+            self._tc_key = key
+        return self._tc_packed
+
+    @torch.no_grad()
+    def forward_tc_into(self, src: torch.Tensor, out: torch.Tensor, ladj: torch.Tensor, passes: int = 3):
+        """data -> latent on tcgen05 (one dense masked-MLP pass per transform): CUDA f32 src/out [N, D], ladj [N]."""
+        if self._tc is None:
+            raise ValueError("this flow has no tensor-core forward (affine transforms, H in {32, 64, 128}, D <= 48)")
+        packed = self.packed_tc()
+        if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
+            raise ValueError("forward_tc_into needs a contiguous CUDA float32 input")
+        _lib.call("pmc_flow_forward_tc", _lib.ptr(packed), self._tc_meta_host.ctypes.data_as(_lib.C.c_void_p),
+                  int(self._tc_meta_host.size), _lib.ptr(src), _lib.ptr(out), _lib.ptr(ladj), src.shape[0], int(passes))
+
     # -- inference: sweep kernels -----------------------------------------------------------
     @torch.no_grad()
     def sweep(self, v: torch.Tensor, inverse: bool) -> Tuple[torch.Tensor, torch.Tensor]:
         """v [N, D] f32 (any device) -> (out [N, D], ladj [N]) on v's device."""
         if v.dim() != 2 or v.shape[1] != self.layout.n_dim:
             raise ValueError(f"expected input of shape (n, {self.layout.n_dim}), got {tuple(v.shape)}")
+        if not inverse and self._tc is not None and config.forward_path == "tc" and v.shape[0] >= config.tc_min_rows:
+            src = v.detach().to(self.raw.device, torch.float32).contiguous()
+            out = torch.empty_like(src)
+            ladj = torch.empty(src.shape[0], dtype=torch.float32, device=src.device)
+            self.forward_tc_into(src, out, ladj)
+            return out.to(v.device), ladj.to(v.device)
         packed = self.packed()
         src = v.detach().to(self.raw.device, torch.float32).contiguous()
         out = torch.empty_like(src)
@@ -183,26 +228,50 @@ class MaskedAutoregressiveFlow(nn.Module):
                   self._meta_host.ctypes.data_as(_lib.C.c_void_p), int(self._meta_host.size), _lib.ptr(src),
                   _lib.ptr(out), _lib.ptr(ladj), src.shape[0], 1 if inverse else 0)
 
+    def mark_dirty(self):
+        """``raw`` was updated in place by a kernel torch does not see (csrc/train_ops.cu): drop the packed copies."""
+        self._packed_key, self._tc_key = None, None
+
     # -- training: autograd graph over the same parameters -----------------------------------
-    def _dense_masks(self):
-        if self._masks is None or self._masks[0][0].device != self.raw.device:
-            self._masks = [[torch.from_numpy(m).to(self.raw.device, torch.float32) for m in ML.masks(self.layout, t)]
-                           for t in range(self.layout.n_transforms)]
+    def _flat_mask(self):
+        """MADE masks of every transform laid out like ``raw`` (1 for biases): one multiply per step
+        yields all masked weights (zuko MaskedLinear: F.linear(x, mask * weight, bias))."""
+        if self._masks is None or self._masks.device != self.raw.device:
+            lay, parts = self.layout, []
+            for t in range(lay.n_transforms):
+                for i, m in enumerate(ML.masks(lay, t)):
+                    parts.append(np.asarray(m, np.float32).reshape(-1))
+                    parts.append(np.ones(lay.raw_sizes[2 * i + 1][0], np.float32))
+            self._masks = torch.from_numpy(np.concatenate(parts)).to(self.raw.device)
+            assert self._masks.numel() == self.raw.numel()
         return self._masks
 
-    def forward_autograd(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """data -> latent with a graph (1 masked-MLP pass per transform, like zuko's forward)."""
+    def _views(self, flat: torch.Tensor, t: int):
+        lay, out, off = self.layout, [], t * self.layout.raw_tstride
+        for i in range(0, len(lay.raw_sizes), 2):
+            ws, bs = lay.raw_sizes[i], lay.raw_sizes[i + 1]
+            w = flat[off:off + ws[0] * ws[1]].view(ws)
+            off += ws[0] * ws[1]
+            b = flat[off:off + bs[0]]
+            off += bs[0]
+            out.append((w, b))
+        return out
+
+    def forward_autograd(self, x: torch.Tensor, raw: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """data -> latent with a graph (1 masked-MLP pass per transform, like zuko's forward).
+        ``raw``: differentiate with respect to this leaf (a detached alias of the blob) instead of the
+        module parameter."""
         self.ensure_cuda()
         lay = self.layout
         x = x.to(self.raw.device, torch.float32)
         ladj = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
-        masks = self._dense_masks()
+        masked = (self.raw if raw is None else raw) * self._flat_mask()
         for t in range(lay.n_transforms):
-            params = self.transform_params(t)
+            params = self._views(masked, t)
             h = x
             last = len(params) - 1
-            for i, ((w, b), m) in enumerate(zip(params, masks[t])):
-                y = F.linear(h, w * m, b)
+            for i, (w, b) in enumerate(params):
+                y = F.linear(h, w, b)
                 if i == 0:
                     h = torch.relu(y)
                 elif i < last:
@@ -276,6 +345,149 @@ def epoch_batches(n: int, batch_size: int, shuffle: bool):
     else:
         perm = torch.arange(n)
     return [perm[i:i + batch_size] for i in range(0, n, batch_size)]
+
+
+HY_LR, HY_BETA1, HY_BETA2, HY_EPS, HY_WD, HY_CLIP = range(6)     # csrc/train_ops.cu
+
+
+class _PlateauLR:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau(mode='min', threshold_mode='abs', cooldown=0) on a
+    plain float (flow.py:271-277,361); the new rate is written to the device hyper-parameter block."""
+
+    def __init__(self, lr, factor=0.2, patience=20, threshold=1e-4, min_lr=1e-6, eps=1e-8):
+        self.lr, self.factor, self.patience, self.threshold, self.min_lr, self.eps = lr, factor, patience, threshold, min_lr, eps
+        self.best, self.bad = math.inf, 0
+
+    def step(self, metric) -> bool:
+        if metric < self.best - self.threshold:
+            self.best, self.bad = metric, 0
+        else:
+            self.bad += 1
+        if self.bad > self.patience:
+            self.bad = 0
+            new = max(self.lr * self.factor, self.min_lr)
+            if self.lr - new > self.eps:
+                self.lr = new
+                return True
+        return False
+
+
+class _FitEngine:
+    """Device-resident state of ``Flow.fit``: training matrix, AdamW moments, hyper-parameters, the
+    epoch's batch index table, and ONE CUDA graph per (batch size, weighted) holding a whole optimiser
+    step -- batch gather, autograd forward/backward over the flat blob, gradient clipping + AdamW
+    (csrc/train_ops.cu), loss accumulation.  A batch costs one graph launch; ragged last batches reuse
+    the full-size graph with zero-weight padding rows."""
+    MAX_BATCHES = 512
+
+    def __init__(self, module: "MaskedAutoregressiveFlow"):
+        self.module = module
+        dev = module.raw.device
+        n = module.raw.numel()
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.hyper = torch.zeros(6, dtype=torch.float64, device=dev)
+        self.scratch = torch.empty(int(_lib.load().pmc_adamw_scratch_size()), dtype=torch.float64, device=dev)
+        self.gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.acc = torch.zeros((), dtype=torch.float64, device=dev)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.x = None
+        self.w = None
+        self.tables = {}        # B -> (idx_all [MAX_BATCHES, B] int64, mask_all [MAX_BATCHES, B] f32)
+        self.graphs = {}        # (B, weighted) -> CUDAGraph
+        self.launches = 0
+
+    def load(self, x: torch.Tensor, w):
+        """copy the training matrix (already shuffled like flow.py:229-234) into the static buffers"""
+        n, d = x.shape
+        if self.x is None or self.x.shape[0] < n:
+            cap = max(4096, 1 << (int(n) - 1).bit_length())
+            self.x = torch.zeros((cap, d), dtype=torch.float32, device=self.module.raw.device)
+            self.w = torch.zeros(cap, dtype=torch.float32, device=self.module.raw.device)
+            self.graphs.clear()                                   # graphs hold the old buffers
+        self.x[:n].copy_(x)
+        if w is not None:
+            self.w[:n].copy_(w)
+
+    def reset_optimizer(self, lr, weight_decay, clip):
+        self.m.zero_(); self.v.zero_(); self.step.zero_()
+        self.hyper.copy_(torch.tensor([lr, 0.9, 0.999, 1e-8, weight_decay, clip if clip is not None else 0.0], dtype=torch.float64))
+
+    def set_lr(self, lr):
+        self.hyper[HY_LR:HY_LR + 1].fill_(lr)
+
+    def _tables(self, B):
+        if B not in self.tables:
+            dev = self.module.raw.device
+            self.tables[B] = (torch.zeros((self.MAX_BATCHES, B), dtype=torch.int64, device=dev),
+                              torch.zeros((self.MAX_BATCHES, B), dtype=torch.float32, device=dev))
+        return self.tables[B]
+
+    def _body(self, B, weighted, optimise):
+        mod = self.module
+        idx_all, mask_all = self._tables(B)
+        idx = idx_all.index_select(0, self.cursor).view(B)
+        msk = mask_all.index_select(0, self.cursor).view(B)
+        xb = self.x.index_select(0, idx)
+        # a fresh leaf aliasing the blob: its autograd bookkeeping is born on the capturing stream and is
+        # independent of whatever graph the user built on ``module.raw`` before
+        leaf = mod.raw.detach().requires_grad_(True)
+        z, ladj = mod.forward_autograd(xb, raw=leaf)
+        lp = (-0.5 * z ** 2 - 0.5 * math.log(2 * math.pi)).sum(dim=-1) + ladj
+        if weighted:
+            wb = self.w.index_select(0, idx) * msk
+            loss = (-lp * wb * 1000.0).sum() / wb.sum()           # flow.py:307-310
+        else:
+            loss = -(lp * msk).sum()                              # flow.py:305
+        (g,) = torch.autograd.grad(loss, leaf)
+        if optimise:
+            _lib.call("pmc_adamw_clip_step", _lib.ptr(mod.raw), _lib.ptr(g), _lib.ptr(self.m), _lib.ptr(self.v), mod.raw.numel(),
+                      _lib.ptr(self.hyper), _lib.ptr(self.step), _lib.ptr(self.scratch), _lib.ptr(self.gnorm))
+            self.acc += loss.detach().double()
+            self.cursor += 1
+
+    def graph(self, B, weighted):
+        key = (B, bool(weighted))
+        if key not in self.graphs:
+            self._tables(B)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):                               # warm-up without touching any state
+                    self._body(B, weighted, optimise=False)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(B, weighted, optimise=True)
+            self.graphs[key] = g
+        return self.graphs[key]
+
+    def run_epoch(self, batches, B, weighted):
+        """batches: list of host index tensors (each <= B rows) into the training matrix; returns the
+        device scalar holding the summed batch losses."""
+        nb = len(batches)
+        if nb > self.MAX_BATCHES:
+            raise ValueError(f"more than {self.MAX_BATCHES} batches per epoch")
+        idx_all, mask_all = self._tables(B)
+        hi = _lib.pinned("fit_idx", (nb, B), torch.int64)
+        hm = _lib.pinned("fit_mask", (nb, B), torch.float32)
+        hi.zero_(); hm.zero_()
+        for i, b in enumerate(batches):
+            hi[i, :len(b)] = b
+            hm[i, :len(b)] = 1.0
+        g = self.graph(B, weighted)
+        idx_all[:nb].copy_(hi, non_blocking=True)
+        mask_all[:nb].copy_(hm, non_blocking=True)
+        self.cursor.zero_()
+        self.acc.zero_()
+        for _ in range(nb):
+            g.replay()
+        self.launches += nb
+        self.module.mark_dirty()
+        return self.acc
 
 
 class Flow:
@@ -358,11 +570,23 @@ class Flow:
         validation = validation_split > 0.0
         n_valid = n_samples - n_train
 
-        optimizer = torch.optim.AdamW(module.parameters(), learning_rate, weight_decay=weight_decay)
-        scheduler = None
-        if annealing:
-            scheduler = ReduceLROnPlateau(optimizer, mode='min', factor=0.2, patience=patience, threshold=0.0001,
-                                          threshold_mode='abs', min_lr=1e-6)
+        use_graph = (config.fit_path == "graph" and noise is None and laplace_scale is None and gaussian_scale is None
+                     and -(-n_train // max(int(batch_size), 1)) <= _FitEngine.MAX_BATCHES)
+        engine = None
+        if use_graph:
+            engine = module.__dict__.get("_fit_engine")
+            if engine is None:
+                engine = module.__dict__["_fit_engine"] = _FitEngine(module)
+            engine.load(x, weights)
+            engine.reset_optimizer(learning_rate, weight_decay, clip_grad_norm)
+            optimizer = None
+            scheduler = _PlateauLR(learning_rate, factor=0.2, patience=patience, threshold=0.0001, min_lr=1e-6) if annealing else None
+        else:
+            optimizer = torch.optim.AdamW(module.parameters(), learning_rate, weight_decay=weight_decay)
+            scheduler = None
+            if annealing:
+                scheduler = ReduceLROnPlateau(optimizer, mode='min', factor=0.2, patience=patience, threshold=0.0001,
+                                              threshold_mode='abs', min_lr=1e-6)
         history = dict(loss=[], val_loss=[])
         monitor = 'val_loss' if validation else 'loss'
         best_epoch, best_loss = 0, np.inf
@@ -386,14 +610,17 @@ class Flow:
 
         for epoch in range(epochs):
             module.train()
-            train_loss = torch.zeros((), dtype=torch.float64, device=dev)
-            for idx in epoch_batches(n_train, batch_size, shuffle):
-                optimizer.zero_grad(set_to_none=True)
-                loss = batch_loss(idx, 0)
-                loss.backward()
-                torch.nn.utils.clip_grad_norm_(module.parameters(), clip_grad_norm)
-                optimizer.step()
-                train_loss += loss.detach().double()
+            if engine is not None:
+                train_loss = engine.run_epoch(epoch_batches(n_train, batch_size, shuffle), int(batch_size), weights is not None)
+            else:
+                train_loss = torch.zeros((), dtype=torch.float64, device=dev)
+                for idx in epoch_batches(n_train, batch_size, shuffle):
+                    optimizer.zero_grad(set_to_none=True)
+                    loss = batch_loss(idx, 0)
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_(module.parameters(), clip_grad_norm)
+                    optimizer.step()
+                    train_loss += loss.detach().double()
             val_loss = None
             if validation:
                 module.eval()
@@ -407,7 +634,11 @@ class Flow:
                 val_loss = float(val_loss.item()) / n_valid
                 history['val_loss'].append(val_loss)
             if scheduler is not None:
-                scheduler.step(val_loss if validation else train_loss)
+                if engine is not None:
+                    if scheduler.step(val_loss if validation else train_loss):
+                        engine.set_lr(scheduler.lr)
+                else:
+                    scheduler.step(val_loss if validation else train_loss)
             if verbose > 1:
                 if validation:
                     print('Epoch %3d/%3d, train loss: %5.2f, val loss: %5.2f' % (epoch + 1, epochs, train_loss, val_loss))
@@ -419,6 +650,7 @@ class Flow:
             if epoch - best_epoch >= int(1.5 * patience):
                 with torch.no_grad():
                     module.raw.copy_(best_model)
+                module.mark_dirty()
                 if verbose > 0:
                     print('Finished early after %3d epochs' % best_epoch)
                     print('Best loss achieved %5.2f' % best_loss)

@@ -382,3 +382,89 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
     meta = np.concatenate([meta] + [np.asarray(tb, np.int64) for tb in tables])
     assert meta.max() < 2 ** 31 and gather.max() < 2 ** 31
     return StreamLayout(tstride, slot_floats, chunks, meta.astype(np.int32), gather.astype(np.int32))
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) layout of the DENSE masked MLP: Flow.forward / log_prob / training forward
+# ---------------------------------------------------------------------------------------------
+TC_D, TC_H, TC_L, TC_T, TC_KIND, TC_KX, TC_NOUT, TC_TSTRIDE, TC_BIAS_OFF, TC_NCHUNKS, TC_SLOT_BYTES, TC_VERSION, TC_LEN = range(13)
+TC_KCHUNK = 32            # k extent of one streamed weight chunk (keep in sync with csrc/flow_tc.cu)
+TC_BIAS_FLAG = 1 << 30    # gather entries copied unsplit (biases)
+
+
+@dataclass(frozen=True)
+class TcLayout:
+    """Weight image of csrc/flow_tc.cu.  Per transform, for every linear layer l = 0..L (K_l = D padded
+    to 8 for l = 0 else H; N_l = 2D padded to 16 for l = L else H) and every k-chunk of <= 32 columns:
+    a TF32 ``hi`` image and a ``lo`` image, each in the no-swizzle K-major UMMA layout
+    ``[k/4][N_l][4]`` (16-byte chunk of 4 consecutive k for output row n at (k/4)*N_l*16 + n*16), the
+    MADE mask folded in (masked entries are 0).  The last chunk of a layer ends with the bias k-step
+    ``[2][N_l][4]`` whose k = 0 / k = 1 entries are hi(b) / lo(b) (multiplied on the tensor core by a
+    constant (1, 1, 0, ...) A block).  ``gather`` codes: >= 0 hi(raw[g]); -(g+2) lo(raw[g]);
+    g | 2^30 plain copy; -1 zero."""
+    tstride: int
+    bias_off: int
+    slot_bytes: int
+    n_chunks: int
+    meta: np.ndarray
+    gather: np.ndarray
+
+    @property
+    def numel(self):
+        return int(self.gather.size)
+
+
+def tc_supported(n_dim: int, n_hidden: int, kind: int) -> bool:
+    return kind == KIND_AFFINE and n_hidden in (32, 64, 128) and 2 <= n_dim <= 48 and 2 * n_dim <= 128
+
+
+@lru_cache(maxsize=None)
+def build_tc(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8) -> TcLayout:
+    if not tc_supported(n_dim, n_hidden, kind):
+        raise ValueError("flow not supported by the tensor-core forward kernel")
+    lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
+    D, H, L, T, total = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.total
+    Kx = (D + 7) // 8 * 8
+    Nout = (D * total + 15) // 16 * 16
+    raw_off = np.concatenate([[0], np.cumsum([int(np.prod(s)) for s in lay.raw_sizes])]).astype(np.int64)
+    parts_all = []
+    n_chunks = 0
+    max_chunk = 0
+    for t in range(T):
+        base_r = t * lay.raw_tstride
+        mks = masks(lay, t)
+        parts = []
+        for l in range(L + 1):
+            K_true, K = (D, Kx) if l == 0 else (H, H)
+            N_true, N = (D * total, Nout) if l == L else (H, H)
+            w_off = base_r + raw_off[2 * l]
+            idx = np.full((N, K), -1, np.int64)                      # raw index of W_l[n, k], -1 where masked / padding
+            rr, cc = np.nonzero(mks[l])
+            idx[rr, cc] = w_off + rr * K_true + cc
+            for c0 in range(0, K, TC_KCHUNK):
+                kc = min(TC_KCHUNK, K - c0)
+                blk = idx[:, c0:c0 + kc].reshape(N, kc // 4, 4).transpose(1, 0, 2).reshape(-1)   # [k/4][N][4]
+                parts.append(blk)                                    # hi image
+                parts.append(np.where(blk >= 0, -(blk + 2), -1))     # lo image
+                nbytes = 2 * kc * N * 4
+                if c0 + kc >= K:                                     # bias k-step [2][N][4]: k = 0 -> hi(b), k = 1 -> lo(b)
+                    bidx = base_r + raw_off[2 * l + 1] + np.arange(N_true)
+                    bb = np.full((2, N, 4), -1, np.int64)
+                    bb[0, :N_true, 0] = bidx
+                    bb[0, :N_true, 1] = -(bidx + 2)
+                    parts.append(bb.reshape(-1))
+                    nbytes += N * 32
+                max_chunk = max(max_chunk, nbytes)
+                if t == 0:
+                    n_chunks += 1
+        w_floats = int(sum(len(a) for a in parts))
+        parts_all.append(np.concatenate(parts))
+    tstride = len(parts_all[0])
+    assert tstride % 4 == 0 and w_floats % 4 == 0
+    gather = np.concatenate(parts_all)
+    slot_bytes = (max_chunk + 1023) // 1024 * 1024
+    meta = np.zeros(TC_LEN, np.int64)
+    meta[[TC_D, TC_H, TC_L, TC_T, TC_KIND, TC_KX, TC_NOUT, TC_TSTRIDE, TC_BIAS_OFF, TC_NCHUNKS, TC_SLOT_BYTES, TC_VERSION]] = \
+        [D, H, L, T, kind, Kx, Nout, tstride, w_floats, n_chunks, slot_bytes, 100]
+    assert np.abs(gather).max() < 2 ** 31
+    return TcLayout(tstride, w_floats, slot_bytes, n_chunks, meta.astype(np.int32), gather.astype(np.int32))

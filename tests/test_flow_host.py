@@ -44,3 +44,23 @@ def test_epoch_batches_replicates_dataloader(shuffle):
         for a, b in zip(e_ref, e):
             assert torch.equal(a, b)
     assert torch.equal(after_ref, after)
+
+
+def test_plateau_lr_mirrors_torch_scheduler():
+    """_PlateauLR (used by the CUDA-graph fit path) follows torch's ReduceLROnPlateau(mode='min',
+    factor=0.2, threshold=1e-4, threshold_mode='abs', min_lr=1e-6) decision for decision."""
+    import numpy as np
+    import torch
+    from torch.optim.lr_scheduler import ReduceLROnPlateau
+    from pocomc_b200.flow import _PlateauLR
+    rng = np.random.default_rng(5)
+    losses = np.concatenate([np.linspace(3, 1, 15), 1 + 0.01 * rng.normal(size=60), np.linspace(1, 0.5, 10), np.full(40, 0.5)])
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], 1e-3)
+    ref = ReduceLROnPlateau(opt, mode='min', factor=0.2, patience=3, threshold=0.0001, threshold_mode='abs', min_lr=1e-6)
+    mine = _PlateauLR(1e-3, factor=0.2, patience=3, threshold=0.0001, min_lr=1e-6)
+    for v in losses:
+        ref.step(float(v))
+        mine.step(float(v))
+        assert abs(opt.param_groups[0]['lr'] - mine.lr) < 1e-15
+    assert mine.lr < 1e-3

@@ -158,3 +158,63 @@ def test_fit_matches_reference_history(golden, tag):
     np.testing.assert_allclose(hist["val_loss"], g[f"{tag}_val_loss"], rtol=2e-4)
     final = np.concatenate([p.reshape(-1) for p in flow_param_list(g, f"{tag}_final_")])
     np.testing.assert_allclose(f.flow.raw.detach().cpu().numpy(), final, rtol=2e-2, atol=2e-4)
+
+
+@pytest.mark.parametrize("preset,d,n", [("maf6", 32, 1000), ("maf3", 4, 33), ("maf6", 10, 257), ("maf12", 21, 128),
+                                        ("maf3", 42, 129), ("maf6", 32, 20000), ("maf3", 2, 1)])
+def test_tensor_core_forward_matches_oracle(preset, d, n):
+    """csrc/flow_tc.cu (tcgen05, A operand in TMEM, 3xTF32 split) against the oracle's dense forward and
+    against the FFMA sweep kernel: fp32 parity bar 5e-5 like the sweep (tolerance stated here)."""
+    from pocomc_b200 import config
+    torch.manual_seed(d * 11 + n)
+    ref = F.make_flow(d, preset)
+    f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
+    assert f.flow.tc_available()
+    x = torch.randn(n, d) * 1.3
+    with torch.no_grad():
+        z_ref, l_ref = ref().transform.call_and_ladj(x)
+    xd = x.cuda()
+    z = torch.empty_like(xd)
+    l = torch.empty(n, dtype=torch.float32, device="cuda")
+    f.flow.forward_tc_into(xd, z, l, passes=3)
+    tol = dict(rtol=5e-5, atol=5e-5)
+    np.testing.assert_allclose(z.cpu().numpy(), z_ref.numpy(), **tol)
+    np.testing.assert_allclose(l.cpu().numpy(), l_ref.numpy(), **tol)
+    zs, ls = f.flow.sweep(xd, False) if config.forward_path == "sweep" else (None, None)
+    old = config.forward_path
+    config.forward_path = "sweep"
+    try:
+        zs, ls = f.flow.sweep(xd, False)
+    finally:
+        config.forward_path = old
+    np.testing.assert_allclose(z.cpu().numpy(), zs.cpu().numpy(), **tol)
+    np.testing.assert_allclose(l.cpu().numpy(), ls.cpu().numpy(), **tol)
+    # plain TF32 (passes = 1) is only TF32-accurate: loose bar, documents the precision trade
+    f.flow.forward_tc_into(xd, z, l, passes=1)
+    assert np.max(np.abs(z.cpu().numpy() - z_ref.numpy())) < 0.05 * max(1.0, float(z_ref.abs().max()))
+
+
+@pytest.mark.parametrize("weighted,annealing", [(True, False), (False, True)])
+def test_graph_fit_matches_eager_fit(weighted, annealing):
+    """The CUDA-graph optimiser step (fused clip + AdamW kernel, padded ragged batches) reproduces the
+    eager torch.optim.AdamW / clip_grad_norm_ path: same loss history to 1e-5, same weights to 1e-5."""
+    from pocomc_b200 import config
+    from pocomc_b200.flow import Flow
+    torch.manual_seed(2)
+    data = torch.randn(700, 5) * torch.tensor([1.0, 2.0, 0.5, 1.5, 1.0]) + 0.3
+    w = torch.rand(700) + 0.1 if weighted else None
+    hist, final = {}, {}
+    for path in ("eager", "graph"):
+        config.fit_path = path
+        try:
+            torch.manual_seed(7)
+            f = Flow(5, "maf3")
+            torch.manual_seed(9)
+            hist[path] = f.fit(data, weights=w, validation_split=0.6, epochs=12, batch_size=128, patience=1 if annealing else 30,
+                               annealing=annealing, shuffle=True, clip_grad_norm=1.0, learning_rate=2e-3)
+            final[path] = f.flow.raw.detach().cpu().numpy().copy()
+        finally:
+            config.fit_path = "graph"
+    np.testing.assert_allclose(hist["graph"]["loss"], hist["eager"]["loss"], rtol=1e-5)
+    np.testing.assert_allclose(hist["graph"]["val_loss"], hist["eager"]["val_loss"], rtol=1e-5)
+    np.testing.assert_allclose(final["graph"], final["eager"], rtol=1e-4, atol=1e-5)
