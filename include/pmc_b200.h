@@ -76,6 +76,23 @@ int pmc_adamw_clip_step(float* param, const float* grad, float* exp_avg, float* 
                         const double* hyper, int64_t* step, double* scratch, float* gnorm_out,
                         pmc_stream_t stream);
 
+/* ---- fused training step of Flow.fit (flow.py:301-319) for MAF ---------------------------------
+ * One mini-batch: weighted negative log-likelihood (flow.py:305-310) and, if `backward`, its gradient
+ * with respect to every flow parameter, written to the flat blob `grad` (masked entries untouched:
+ * keep the buffer zero-initialised).  `packed` = fp32 weight images described by
+ * pocomc_b200.made_layout.build_train (built from the blob by pmc_flow_pack with that layout's gather
+ * table); `meta_host`, HOST table of the same layout; `tiles` / `wmap` device copies of its tile list and
+ * gradient scatter maps.  Batch b = *cursor takes rows idx[b*bp .. b*bp+bp) of the training matrix
+ * xdata [rows, D] (wdata [rows] sample weights or NULL), mask = 0 marks padding rows; bp % 32 == 0.
+ * loss_partials receives bp/32 partial sums (loss = their sum, in index order); logprob (may be NULL)
+ * the per-row log-probability.  scratch: pmc_flow_train_scratch_size(meta_host, bp) floats.          */
+int64_t pmc_flow_train_scratch_size(const int32_t* meta_host, int64_t bp);
+int pmc_flow_train_step(const float* packed, const int32_t* meta_host, int32_t meta_len,
+                        const float* xdata, const float* wdata, const int64_t* idx, const float* mask,
+                        const int64_t* cursor, int64_t bp, float* scratch, double* loss_partials,
+                        float* logprob, const int32_t* tiles, const int32_t* wmap, float* grad,
+                        int32_t backward, pmc_stream_t stream);
+
 /* ---- MCMC controller state ------------------------------------------------------------------
  * Device-resident f64 block shared by the step kernels so a whole MCMC step is host-sync free:
  * ctl[PMC_CTL_*] scalars followed by mu[D] at ctl[PMC_CTL_MU].                                 */

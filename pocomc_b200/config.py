@@ -31,12 +31,17 @@ fit_path
     autograd forward/backward, fused clip + AdamW kernel, loss accumulation) -- same arithmetic and RNG
     consumption as ``"eager"``, which issues the ops one by one.  Noise / L1 / L2 regularised fits
     always take the eager path.
+fit_kernels
+    ``"fused"`` (default): MAF flows with H <= 128 train on the hand-written forward/backward kernels of
+    csrc/flow_train.cu (5 launches per optimiser step inside the graph); ``"autograd"``: torch autograd
+    over the flat blob (always used for spline flows).
 """
 import os
 
 rng_mode = os.environ.get("PMC_B200_RNG", "host")
 mean_mode = None  # None -> 1 for "host", 0 for "device"
 sweep_variant = os.environ.get("PMC_B200_SWEEP", "ffma")
+fit_kernels = os.environ.get("PMC_B200_FIT_KERNELS", "fused")
 fit_path = os.environ.get("PMC_B200_FIT", "graph")
 forward_path = os.environ.get("PMC_B200_FORWARD", "tc")
 tc_min_rows = int(os.environ.get("PMC_B200_TC_MIN_ROWS", "1"))

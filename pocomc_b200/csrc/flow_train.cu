@@ -1,0 +1,449 @@
+// Fused training step of Flow.fit (pocomc/flow.py:301-319) for zuko MAF: for one mini-batch computes the
+// weighted negative log-likelihood and its gradient with respect to every flow parameter.
+//
+// The reference builds this with torch autograd over ~70 small ops per transform; the batch is at most
+// 512 rows (sampler.py:289), so the step is launch- and latency-bound, not throughput-bound.  Here:
+//
+//   flow_train_fb_kernel : one CTA per 32 batch rows runs the WHOLE forward chain (T transforms x (L+1)
+//       masked linear layers + affine map) and the WHOLE input-gradient chain back, fp32 FMA.  Weight
+//       images (mask folded in, transposed as each GEMM wants them; built by pmc_flow_pack from the
+//       flat blob) stream through a double-buffered shared-memory slot with 1-D bulk copies
+//       (cp.async.bulk + mbarrier), one image per layer, prefetched a layer ahead.  Activations live in
+//       shared memory transposed ([feature][row]) so the inner product loop is one broadcast LDS.128
+//       plus conflict-free LDS.32s per k.  Activations / pre-activation gradients are also written to a
+//       global scratch for the weight-gradient pass.
+//   flow_train_wgrad_kernel : grouped GEMM dW = dpre^T . input over the whole batch, one 32x32 tile of
+//       one layer per CTA, scattered straight into the flat gradient blob (no atomics, deterministic).
+//
+// Arithmetic matches the autograd path operation for operation (fp32, same association up to the
+// order of the k-loop); parity is tested against the oracle's gradients.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <algorithm>
+
+namespace pmc {
+
+using namespace tc;
+
+enum { TR_D = 0, TR_DP, TR_H, TR_L, TR_T, TR_NO, TR_TSTRIDE, TR_BIAS_OFF, TR_RAW_TSTRIDE, TR_MAP_TSTRIDE, TR_NTILES, TR_VERSION, TR_LEN };
+
+constexpr int TR_ROWS = 32;       // batch rows per CTA
+constexpr int TR_LDA = 36;        // row stride of the transposed activation buffers (floats)
+constexpr float TR_LOG_SLOPE_ABS = 6.90775527898213705205f;   // |log(1e-3)|, zuko MonotonicAffineTransform
+constexpr float TR_HALF_LOG_2PI = 0.91893853320467274178f;
+
+struct TrainParams {
+  const float* packed;
+  const float* xdata;        // [rows][D] training matrix
+  const float* wdata;        // [rows] sample weights (weighted) or nullptr
+  const long long* idx;      // [n_batches][Bp] row indices of every batch of the epoch
+  const float* mask;         // [n_batches][Bp] 1 for real rows, 0 for padding
+  const long long* cursor;   // device scalar: which batch
+  float* X;                  // [T+1][Bp][Dp] transform inputs (X[T] = latent)
+  float* S;                  // [T][Bp][Dp] raw log-scales
+  float* Hs;                 // [T][L][Bp][H] hidden activations
+  float* Gh;                 // [T][L][Bp][H] gradients w.r.t. hidden pre-activations
+  float* Go;                 // [T][Bp][No] gradients w.r.t. the output layer (shift | scale_raw)
+  double* loss_partials;     // [grid] per-CTA loss sums
+  float* logprob;            // [Bp] per-row log-probability (may be nullptr)
+  int Bp, D, Dp, H, L, T, No, tstride, bias_off;
+  int weighted, backward;
+};
+
+// acc[i][j] = sum_k At[k][4 ty + i] * W[k][tx + 32 j]
+template <int TN>
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ At, int K, const float* __restrict__ W, int ty, int tx,
+                                          float (&acc)[4][4]) {
+  constexpr int N = 32 * TN;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const float* a = At + 4 * ty;
+  const float* w = W + tx;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 av = *reinterpret_cast<const float4*>(a + k * TR_LDA);
+    float wv[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) wv[j] = w[k * N + 32 * j];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      acc[0][j] = fmaf(av.x, wv[j], acc[0][j]);
+      acc[1][j] = fmaf(av.y, wv[j], acc[1][j]);
+      acc[2][j] = fmaf(av.z, wv[j], acc[2][j]);
+      acc[3][j] = fmaf(av.w, wv[j], acc[3][j]);
+    }
+  }
+}
+__device__ __forceinline__ void gemm_any(int tn, const float* At, int K, const float* W, int ty, int tx, float (&acc)[4][4]) {
+  if (tn == 4) gemm_tile<4>(At, K, W, ty, tx, acc);
+  else if (tn == 2) gemm_tile<2>(At, K, W, ty, tx, acc);
+  else gemm_tile<1>(At, K, W, ty, tx, acc);
+}
+
+__global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full[2];
+  __shared__ float crow[TR_ROWS];
+  __shared__ double lossrow[TR_ROWS];
+  __shared__ float red[8];
+  const int D = p.D, Dp = p.Dp, H = p.H, L = p.L, T = p.T, No = p.No, Bp = p.Bp;
+  const int wmax = max(max(D * H, H * H), max(H * No, H * Dp));
+  const int brows = max(H, No);
+  float* wbuf0 = reinterpret_cast<float*>(smem_raw);
+  float* wbuf1 = wbuf0 + wmax;
+  float* bufA = wbuf1 + wmax;
+  float* bufB = bufA + brows * TR_LDA;
+  float* xT = bufB + brows * TR_LDA;
+  float* gT = xT + Dp * TR_LDA;
+
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  const int row0 = blockIdx.x * TR_ROWS;
+  const int n_img = (p.backward ? 2 : 1) * T * (L + 1);
+  const int fwd_img = T * (L + 1);
+  const int bwd_base = D * H + (L - 1) * H * H + H * No;
+
+  auto img = [&](int s, int& off, int& n) {
+    if (s < fwd_img) {
+      const int t = s / (L + 1), l = s - t * (L + 1);
+      off = t * p.tstride + (l == 0 ? 0 : D * H + (l - 1) * H * H);
+      n = (l == 0) ? D * H : (l < L ? H * H : H * No);
+    } else {
+      const int q = s - fwd_img;
+      const int tb = T - 1 - q / (L + 1), j = q % (L + 1);
+      off = tb * p.tstride + bwd_base + (j == 0 ? 0 : No * H + (j - 1) * H * H);
+      n = (j == 0) ? No * H : (j < L ? H * H : H * Dp);
+    }
+  };
+  auto issue = [&](int s) {
+    int off, n;
+    img(s, off, n);
+    mbar_expect_tx(full + (s & 1), (uint32_t)n * 4u);
+    bulk_g2s((s & 1) ? wbuf1 : wbuf0, p.packed + off, (uint32_t)n * 4u, full + (s & 1));
+  };
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_init(full + 1, 1);
+    mbar_fence_init();
+    issue(0);
+    if (n_img > 1) issue(1);
+  }
+
+  // ---- batch rows, loss coefficients c_r (flow.py:305-310) ----
+  const long long cur = p.cursor[0];
+  const long long* bidx = p.idx + cur * Bp;
+  const float* bmask = p.mask + cur * Bp;
+  float sumw = 1.0f;
+  if (p.weighted) {
+    float s = 0.f;
+    for (int r = tid; r < Bp; r += 256) s += p.wdata[bidx[r]] * bmask[r];
+    s = warp_sum(s);
+    if (tx == 0) red[ty] = s;
+    __syncthreads();
+    sumw = 0.f;
+    for (int i = 0; i < 8; ++i) sumw += red[i];
+  }
+  if (tid < TR_ROWS) {
+    const int r = row0 + tid;
+    const float m = bmask[r];
+    crow[tid] = p.weighted ? (p.wdata[bidx[r]] * m * 1000.0f / sumw) : m;
+  }
+  for (int i = tid; i < TR_ROWS * Dp; i += 256) {
+    const int r = i / Dp, d = i - r * Dp;
+    const float v = (d < D) ? p.xdata[bidx[row0 + r] * D + d] : 0.f;
+    xT[d * TR_LDA + r] = v;
+    p.X[((size_t)0 * Bp + row0 + r) * Dp + d] = v;
+  }
+  __syncthreads();
+
+  const int tnH = H / 32, tnO = No / 32, tnD = Dp / 32;
+  float acc[4][4];
+  float ladj_p[4] = {0.f, 0.f, 0.f, 0.f};
+  float znew[4][2];
+  int s = 0;
+  // =========================== forward ===========================
+  for (int t = 0; t < T; ++t) {
+    const float* bias = p.packed + (size_t)t * p.tstride + p.bias_off;
+    float* in = xT;
+    float* out = bufA;
+    for (int l = 0; l < L; ++l) {
+      mbar_wait(full + (s & 1), (s >> 1) & 1);
+      gemm_any(tnH, in, l == 0 ? D : H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
+      float* hs = p.Hs + ((size_t)(t * L + l) * Bp + row0 + 4 * ty) * H;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= tnH) continue;
+        const int c = tx + 32 * j;
+        const float b = __ldg(bias + l * H + c);
+        float h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = acc[i][j] + b;
+          if (l > 0) v += in[c * TR_LDA + 4 * ty + i];        // residual block
+          h[i] = fmaxf(v, 0.f);
+          hs[(size_t)i * H + c] = h[i];
+        }
+        *reinterpret_cast<float4*>(out + c * TR_LDA + 4 * ty) = make_float4(h[0], h[1], h[2], h[3]);
+      }
+      __syncthreads();
+      if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+      ++s;
+      in = out;
+      out = (out == bufA) ? bufB : bufA;
+    }
+    // output layer + affine map
+    mbar_wait(full + (s & 1), (s >> 1) & 1);
+    gemm_any(tnO, in, H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
+    const float* bo = bias + L * H;
+#pragma unroll
+  #pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+      if (jj >= tnD) continue;
+      const int d = tx + 32 * jj;
+      const float bs = __ldg(bo + d), br = __ldg(bo + Dp + d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float z = 0.f;
+        if (d < D) {
+          const float shift = acc[i][jj] + bs, sraw = ((tnD == 1) ? acc[i][jj + 1] : acc[i][(jj + 2) & 3]) + br;
+          const float ls = sraw / (1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS);
+          z = fmaf(xT[d * TR_LDA + 4 * ty + i], expf(ls), shift);
+          ladj_p[i] += ls;
+          p.S[((size_t)t * Bp + row0 + 4 * ty + i) * Dp + d] = sraw;
+        }
+        znew[i][jj] = z;
+      }
+    }
+    __syncthreads();                                           // every thread has read xT and the weight slot
+    if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+    ++s;
+#pragma unroll
+  #pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+      if (jj >= tnD) continue;
+      const int d = tx + 32 * jj;
+      *reinterpret_cast<float4*>(xT + d * TR_LDA + 4 * ty) = make_float4(znew[0][jj], znew[1][jj], znew[2][jj], znew[3][jj]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p.X[((size_t)(t + 1) * Bp + row0 + 4 * ty + i) * Dp + d] = znew[i][jj];
+    }
+    __syncthreads();
+  }
+  // ---- log-probability and loss ----
+  {
+    float sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+#pragma unroll
+  #pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+      if (jj >= tnD) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sq[i] = fmaf(znew[i][jj], znew[i][jj], sq[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float sl = warp_sum(ladj_p[i]), ss = warp_sum(sq[i]);
+      if (tx == 0) {
+        const float lp = -0.5f * ss - (float)D * TR_HALF_LOG_2PI + sl;
+        const int r = 4 * ty + i;
+        lossrow[r] = (crow[r] != 0.f) ? -(double)crow[r] * (double)lp : 0.0;
+        if (p.logprob) p.logprob[row0 + r] = lp;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double sum = 0.0;
+      for (int r = 0; r < TR_ROWS; ++r) sum += lossrow[r];
+      p.loss_partials[blockIdx.x] = sum;
+    }
+  }
+  if (!p.backward) return;
+  // =========================== backward ===========================
+  // d loss / d z_T = c_r z ; d loss / d ladj = -c_r
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+      if (jj >= tnD) continue;
+    const int d = tx + 32 * jj;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gT[d * TR_LDA + 4 * ty + i] = crow[4 * ty + i] * znew[i][jj];
+  }
+  __syncthreads();
+  for (int t = T - 1; t >= 0; --t) {
+    float gxd[4][2];
+    // affine map backward -> gradient of the output layer (shift | scale_raw) as the next GEMM's input
+#pragma unroll
+  #pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+      if (jj >= tnD) continue;
+      const int d = tx + 32 * jj;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 4 * ty + i;
+        float gshift = 0.f, gsraw = 0.f, gx = 0.f;
+        if (d < D) {
+          const size_t o = ((size_t)t * Bp + row0 + r) * Dp + d;
+          const float gz = gT[d * TR_LDA + r];
+          const float x = p.X[o], sraw = p.S[o];
+          const float den = 1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS;
+          const float e = expf(sraw / den);
+          gshift = gz;
+          gsraw = (gz * x * e - crow[r]) / (den * den);
+          gx = gz * e;
+        }
+        gxd[i][jj] = gx;
+        bufA[d * TR_LDA + r] = gshift;
+        bufA[(Dp + d) * TR_LDA + r] = gsraw;
+        float* go = p.Go + ((size_t)t * Bp + row0 + r) * No;
+        go[d] = gshift;
+        go[Dp + d] = gsraw;
+      }
+    }
+    __syncthreads();
+    float* in = bufA;
+    float* out = bufB;
+    for (int j = 0; j < L; ++j) {                              // images B_o, B_{L-1}, ..., B_1
+      const int lh = L - 1 - j;                                // hidden layer whose pre-activation gradient comes out
+      mbar_wait(full + (s & 1), (s >> 1) & 1);
+      gemm_any(tnH, in, j == 0 ? No : H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
+      const float* hs = p.Hs + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
+      float* gh = p.Gh + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        if (jn >= tnH) continue;
+        const int c = tx + 32 * jn;
+        float g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = acc[i][jn];
+          if (j > 0) v += in[c * TR_LDA + 4 * ty + i];         // residual path
+          g[i] = (hs[(size_t)i * H + c] > 0.f) ? v : 0.f;      // ReLU
+          gh[(size_t)i * H + c] = g[i];
+        }
+        *reinterpret_cast<float4*>(out + c * TR_LDA + 4 * ty) = make_float4(g[0], g[1], g[2], g[3]);
+      }
+      __syncthreads();
+      if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+      ++s;
+      float* tmp = in; in = out; out = tmp;
+    }
+    // image B_0: gradient w.r.t. the transform input through the hyper-network + the direct path
+    mbar_wait(full + (s & 1), (s >> 1) & 1);
+    gemm_any(tnD, in, H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
+#pragma unroll
+  #pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+      if (jj >= tnD) continue;
+      const int d = tx + 32 * jj;
+      *reinterpret_cast<float4*>(gT + d * TR_LDA + 4 * ty) =
+          make_float4(gxd[0][jj] + acc[0][jj], gxd[1][jj] + acc[1][jj], gxd[2][jj] + acc[2][jj], gxd[3][jj] + acc[3][jj]);
+    }
+    __syncthreads();
+    if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+    ++s;
+  }
+}
+
+// dW_l[n][k] = sum_r dpre_l[r][n] * input_l[r][k], db_l[n] = sum_r dpre_l[r][n]; one 32 x 32 tile per CTA
+__global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams p, const int* __restrict__ tiles,
+                                                               const int* __restrict__ wmap, int map_tstride,
+                                                               float* __restrict__ grad) {
+  __shared__ float dp[32][33], in[32][33];
+  const int t = tiles[4 * blockIdx.x], l = tiles[4 * blockIdx.x + 1], n0 = tiles[4 * blockIdx.x + 2], k0 = tiles[4 * blockIdx.x + 3];
+  const int D = p.D, H = p.H, L = p.L, No = p.No, Bp = p.Bp, Dp = p.Dp;
+  const int n_img = (l < L) ? H : No, k_true = (l == 0) ? D : H;
+  const float* dpre = (l < L) ? p.Gh + (size_t)(t * L + l) * Bp * H : p.Go + (size_t)t * Bp * No;
+  const float* inp = (l == 0) ? p.X + (size_t)t * Bp * Dp : p.Hs + (size_t)(t * L + (l - 1)) * Bp * H;
+  const int ldk = (l == 0) ? Dp : H;
+  int moff = 0;
+  for (int q = 0; q < l; ++q) moff += H * (q == 0 ? D : H) + H;
+  const int* map = wmap + (size_t)t * map_tstride + moff;
+  const int* bmap = map + n_img * k_true;
+  const int tid = threadIdx.x, a = tid >> 4, b = tid & 15;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, bacc[2] = {0.f, 0.f};
+  for (int r0 = 0; r0 < Bp; r0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + 256 * q, rr = e >> 5, c = e & 31;
+      dp[rr][c] = dpre[(size_t)(r0 + rr) * n_img + n0 + c];
+      in[rr][c] = (k0 + c < k_true) ? inp[(size_t)(r0 + rr) * ldk + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const float d0 = dp[rr][2 * a], d1 = dp[rr][2 * a + 1], i0 = in[rr][2 * b], i1 = in[rr][2 * b + 1];
+      acc[0][0] = fmaf(d0, i0, acc[0][0]); acc[0][1] = fmaf(d0, i1, acc[0][1]);
+      acc[1][0] = fmaf(d1, i0, acc[1][0]); acc[1][1] = fmaf(d1, i1, acc[1][1]);
+      bacc[0] += d0; bacc[1] += d1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int n = n0 + 2 * a + i;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = k0 + 2 * b + j;
+      if (k < k_true) {
+        const int m = map[n * k_true + k];
+        if (m >= 0) grad[m] = acc[i][j];
+      }
+    }
+    if (k0 == 0 && b == 0) {
+      const int m = bmap[n];
+      if (m >= 0) grad[m] = bacc[i];
+    }
+  }
+}
+
+static size_t train_smem(int D, int Dp, int H, int No) {
+  const size_t wmax = (size_t)std::max(std::max(D * H, H * H), std::max(H * No, H * Dp));
+  const size_t brows = (size_t)std::max(H, No);
+  return (2 * wmax + 2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4;
+}
+
+}  // namespace pmc
+
+using namespace pmc;
+
+// floats of scratch for a padded batch of Bp rows: X | S | Hs | Gh | Go
+extern "C" int64_t pmc_flow_train_scratch_size(const int32_t* meta_host, int64_t bp) {
+  const int64_t Dp = meta_host[TR_DP], H = meta_host[TR_H], L = meta_host[TR_L], T = meta_host[TR_T], No = meta_host[TR_NO];
+  return (T + 1) * bp * Dp + T * bp * Dp + 2 * T * L * bp * H + T * bp * No;
+}
+
+extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host, int32_t meta_len, const float* xdata,
+                                   const float* wdata, const int64_t* idx, const float* mask, const int64_t* cursor, int64_t bp,
+                                   float* scratch, double* loss_partials, float* logprob, const int32_t* tiles,
+                                   const int32_t* wmap, float* grad, int32_t backward, pmc_stream_t stream) {
+  PMC_REQUIRE(packed && meta_host && xdata && idx && mask && cursor && scratch && loss_partials, "pmc_flow_train_step: null pointer");
+  PMC_REQUIRE(meta_len >= TR_LEN && meta_host[TR_VERSION] == 200, "pmc_flow_train_step: not a training layout table");
+  PMC_REQUIRE(bp > 0 && bp % TR_ROWS == 0, "pmc_flow_train_step: padded batch must be a multiple of 32 rows");
+  PMC_REQUIRE(!backward || (tiles && wmap && grad), "pmc_flow_train_step: backward needs tiles, wmap and grad");
+  const int* m = meta_host;
+  TrainParams p;
+  p.packed = packed; p.xdata = xdata; p.wdata = wdata;
+  p.idx = reinterpret_cast<const long long*>(idx); p.mask = mask; p.cursor = reinterpret_cast<const long long*>(cursor);
+  p.Bp = (int)bp; p.D = m[TR_D]; p.Dp = m[TR_DP]; p.H = m[TR_H]; p.L = m[TR_L]; p.T = m[TR_T]; p.No = m[TR_NO];
+  p.tstride = m[TR_TSTRIDE]; p.bias_off = m[TR_BIAS_OFF];
+  p.weighted = wdata ? 1 : 0; p.backward = backward ? 1 : 0;
+  PMC_REQUIRE((p.H == 32 || p.H == 64 || p.H == 128) && p.Dp % 32 == 0 && p.Dp <= 64 && p.No == 2 * p.Dp && p.D >= 2 && p.D <= p.Dp && p.L >= 1,
+              "pmc_flow_train_step: unsupported flow shape");
+  const size_t bpz = (size_t)bp;
+  p.X = scratch;
+  p.S = p.X + (size_t)(p.T + 1) * bpz * p.Dp;
+  p.Hs = p.S + (size_t)p.T * bpz * p.Dp;
+  p.Gh = p.Hs + (size_t)p.T * p.L * bpz * p.H;
+  p.Go = p.Gh + (size_t)p.T * p.L * bpz * p.H;
+  p.loss_partials = loss_partials; p.logprob = logprob;
+  const size_t smem = train_smem(p.D, p.Dp, p.H, p.No);
+  PMC_REQUIRE(smem <= 220 * 1024, "pmc_flow_train_step: shared memory budget exceeded");
+  cudaStream_t st = as_stream(stream);
+  PMC_TRY(cudaFuncSetAttribute(flow_train_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  flow_train_fb_kernel<<<(unsigned)(bp / TR_ROWS), 256, smem, st>>>(p);
+  PMC_LAUNCH_CHECK();
+  if (backward) {
+    flow_train_wgrad_kernel<<<(unsigned)m[TR_NTILES], 256, 0, st>>>(p, tiles, wmap, m[TR_MAP_TSTRIDE], grad);
+    PMC_LAUNCH_CHECK();
+  }
+  return 0;
+}

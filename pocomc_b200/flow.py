@@ -394,9 +394,22 @@ class _FitEngine:
         self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.x = None
         self.w = None
-        self.tables = {}        # B -> (idx_all [MAX_BATCHES, B] int64, mask_all [MAX_BATCHES, B] f32)
-        self.graphs = {}        # (B, weighted) -> CUDAGraph
+        self.tables = {}        # Bp -> (idx_all [MAX_BATCHES, Bp] int64, mask_all [MAX_BATCHES, Bp] f32)
+        self.graphs = {}        # (Bp, weighted, train) -> CUDAGraph
         self.launches = 0
+        # hand-written forward/backward (csrc/flow_train.cu) when the flow shape is built, else autograd
+        lay = module.layout
+        self.fused = config.fit_kernels == "fused" and ML.train_supported(lay.n_dim, lay.n_hidden, lay.kind)
+        if self.fused:
+            tl = ML.build_train(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+            self.tl = tl
+            self.tl_meta = np.ascontiguousarray(tl.meta)
+            self.tl_gather = torch.from_numpy(tl.gather.copy()).to(dev)
+            self.tl_wmap = torch.from_numpy(tl.wmap.copy()).to(dev)
+            self.tl_tiles = torch.from_numpy(tl.tiles.copy()).to(dev)
+            self.tl_packed = torch.empty(tl.numel, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(n, dtype=torch.float32, device=dev)      # masked entries stay 0
+            self.fscratch = {}      # Bp -> (scratch floats, loss partials)
 
     def load(self, x: torch.Tensor, w):
         """copy the training matrix (already shuffled like flow.py:229-234) into the static buffers"""
@@ -424,6 +437,49 @@ class _FitEngine:
                               torch.zeros((self.MAX_BATCHES, B), dtype=torch.float32, device=dev))
         return self.tables[B]
 
+    def _body_fused(self, B, weighted, train):
+        """pack -> fused forward (+ backward + weight gradients) -> clip + AdamW: 5 launches (+3 bookkeeping)"""
+        mod = self.module
+        idx_all, mask_all = self._tables(B)
+        if B not in self.fscratch:
+            nfl = int(_lib.load().pmc_flow_train_scratch_size(self.tl_meta.ctypes.data_as(_lib.C.c_void_p), B))
+            self.fscratch[B] = (torch.empty(nfl, dtype=torch.float32, device=mod.raw.device),
+                                torch.zeros(B // 32, dtype=torch.float64, device=mod.raw.device))
+        scratch, partials = self.fscratch[B]
+        _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
+        _lib.call("pmc_flow_train_step", _lib.ptr(self.tl_packed), self.tl_meta.ctypes.data_as(_lib.C.c_void_p),
+                  int(self.tl_meta.size), _lib.ptr(self.x), _lib.ptr(self.w) if weighted else None, _lib.ptr(idx_all),
+                  _lib.ptr(mask_all), _lib.ptr(self.cursor), B, _lib.ptr(scratch), _lib.ptr(partials), None,
+                  _lib.ptr(self.tl_tiles), _lib.ptr(self.tl_wmap), _lib.ptr(self.grad), 1 if train else 0)
+        if train:
+            _lib.call("pmc_adamw_clip_step", _lib.ptr(mod.raw), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
+                      mod.raw.numel(), _lib.ptr(self.hyper), _lib.ptr(self.step), _lib.ptr(self.scratch), _lib.ptr(self.gnorm))
+        self.acc += partials.sum()
+        self.cursor += 1
+
+    def loss_and_grad(self, rows: torch.Tensor, weighted: bool):
+        """(loss, gradient blob) of one batch on the fused kernels, no parameter update (tests / diagnostics)."""
+        assert self.fused
+        B = (len(rows) + 31) // 32 * 32
+        idx_all, mask_all = self._tables(B)
+        idx_all[0].zero_(); mask_all[0].zero_()
+        idx_all[0, :len(rows)] = rows.to(idx_all.device)
+        mask_all[0, :len(rows)] = 1.0
+        self.cursor.zero_(); self.acc.zero_()
+        self.grad.zero_()
+        mod = self.module
+        if B not in self.fscratch:
+            nfl = int(_lib.load().pmc_flow_train_scratch_size(self.tl_meta.ctypes.data_as(_lib.C.c_void_p), B))
+            self.fscratch[B] = (torch.empty(nfl, dtype=torch.float32, device=mod.raw.device),
+                                torch.zeros(B // 32, dtype=torch.float64, device=mod.raw.device))
+        scratch, partials = self.fscratch[B]
+        _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
+        _lib.call("pmc_flow_train_step", _lib.ptr(self.tl_packed), self.tl_meta.ctypes.data_as(_lib.C.c_void_p),
+                  int(self.tl_meta.size), _lib.ptr(self.x), _lib.ptr(self.w) if weighted else None, _lib.ptr(idx_all),
+                  _lib.ptr(mask_all), _lib.ptr(self.cursor), B, _lib.ptr(scratch), _lib.ptr(partials), None,
+                  _lib.ptr(self.tl_tiles), _lib.ptr(self.tl_wmap), _lib.ptr(self.grad), 1)
+        return float(partials.sum().item()), self.grad.clone()
+
     def _body(self, B, weighted, optimise):
         mod = self.module
         idx_all, mask_all = self._tables(B)
@@ -447,38 +503,49 @@ class _FitEngine:
             self.acc += loss.detach().double()
             self.cursor += 1
 
-    def graph(self, B, weighted):
-        key = (B, bool(weighted))
+    def graph(self, B, weighted, train=True):
+        key = (B, bool(weighted), bool(train))
         if key not in self.graphs:
             self._tables(B)
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                for _ in range(2):                               # warm-up without touching any state
-                    self._body(B, weighted, optimise=False)
+                if not self.fused:
+                    for _ in range(2):                           # warm-up without touching any state
+                        self._body(B, weighted, optimise=False)
+                else:
+                    self.fscratch.get(B) or self._body_fused(B, weighted, train=False)   # allocate outside the capture
+                    self.acc.zero_(); self.cursor.zero_()
             cur.wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._body(B, weighted, optimise=True)
+                if self.fused:
+                    self._body_fused(B, weighted, train)
+                else:
+                    self._body(B, weighted, optimise=True)
             self.graphs[key] = g
         return self.graphs[key]
 
-    def run_epoch(self, batches, B, weighted):
-        """batches: list of host index tensors (each <= B rows) into the training matrix; returns the
-        device scalar holding the summed batch losses."""
+    def run_epoch(self, batches, B, weighted, train=True, offset=0):
+        """batches: list of host index tensors (each <= B rows) into the training matrix (shifted by
+        ``offset``); returns the device scalar holding the summed batch losses.  ``train=False`` (fused
+        kernels only) evaluates the loss without touching the parameters."""
         nb = len(batches)
         if nb > self.MAX_BATCHES:
             raise ValueError(f"more than {self.MAX_BATCHES} batches per epoch")
+        nrows = B
+        B = (B + 31) // 32 * 32                                  # the kernels work on 32-row tiles; extra rows are padding
         idx_all, mask_all = self._tables(B)
         hi = _lib.pinned("fit_idx", (nb, B), torch.int64)
         hm = _lib.pinned("fit_mask", (nb, B), torch.float32)
         hi.zero_(); hm.zero_()
         for i, b in enumerate(batches):
-            hi[i, :len(b)] = b
+            hi[i, :len(b)] = b + offset
             hm[i, :len(b)] = 1.0
-        g = self.graph(B, weighted)
+        assert all(len(b) <= nrows for b in batches)
+        g = self.graph(B, weighted, train)
         idx_all[:nb].copy_(hi, non_blocking=True)
         mask_all[:nb].copy_(hm, non_blocking=True)
         self.cursor.zero_()
@@ -486,7 +553,8 @@ class _FitEngine:
         for _ in range(nb):
             g.replay()
         self.launches += nb
-        self.module.mark_dirty()
+        if train:
+            self.module.mark_dirty()
         return self.acc
 
 
@@ -622,12 +690,18 @@ class Flow:
                     optimizer.step()
                     train_loss += loss.detach().double()
             val_loss = None
+            if engine is not None and engine.fused:
+                train_loss = train_loss.clone()                  # engine.acc is reused by the validation pass
             if validation:
                 module.eval()
-                val_loss = torch.zeros((), dtype=torch.float64, device=dev)
-                with torch.no_grad():       # no graph needed: validation runs on the sweep kernel
-                    for idx in epoch_batches(n_valid, batch_size, shuffle):
-                        val_loss += batch_loss(idx, n_train).double()
+                if engine is not None and engine.fused:
+                    val_loss = engine.run_epoch(epoch_batches(n_valid, batch_size, shuffle), int(batch_size), weights is not None,
+                                                train=False, offset=n_train)
+                else:
+                    val_loss = torch.zeros((), dtype=torch.float64, device=dev)
+                    with torch.no_grad():       # no graph needed: validation runs on the forward kernels
+                        for idx in epoch_batches(n_valid, batch_size, shuffle):
+                            val_loss += batch_loss(idx, n_train).double()
             train_loss = float(train_loss.item()) / n_train          # one sync per epoch
             history['loss'].append(train_loss)
             if validation:

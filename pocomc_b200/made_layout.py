@@ -468,3 +468,112 @@ def build_tc(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: 
         [D, H, L, T, kind, Kx, Nout, tstride, w_floats, n_chunks, slot_bytes, 100]
     assert np.abs(gather).max() < 2 ** 31
     return TcLayout(tstride, w_floats, slot_bytes, n_chunks, meta.astype(np.int32), gather.astype(np.int32))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused training step (csrc/flow_train.cu): fp32 weight images for forward / input-gradient GEMMs and
+# scatter maps for the weight-gradient GEMMs
+# ---------------------------------------------------------------------------------------------
+TR_D, TR_DP, TR_H, TR_L, TR_T, TR_NO, TR_TSTRIDE, TR_BIAS_OFF, TR_RAW_TSTRIDE, TR_MAP_TSTRIDE, TR_NTILES, TR_VERSION, TR_LEN = range(13)
+
+
+@dataclass(frozen=True)
+class TrainLayout:
+    """Per transform (float offsets, every image a multiple of 4 floats):
+      forward images  F_0 [D][H], F_1..F_{L-1} [H][H], F_o [H][No]      F_l[k][n] = (W_l * mask_l)[n][k]
+      backward images B_o [No][H], B_{L-1}..B_1 [H][H], B_0 [H][Dp]      B_l[n][k] = (W_l * mask_l)[n][k]
+      biases b_0..b_{L-1} [H], b_o [No]
+    Output columns are permuted: column c = d + Dp*s holds shift (s = 0) / scale_raw (s = 1) of feature d
+    (Dp = D rounded up to 32, No = 2 Dp), so one thread owns both parameters of a feature.
+    ``gather``: packed[i] = raw[gather[i]] (-1 -> 0): the existing pmc_flow_pack kernel builds the image.
+    ``wmap``: per transform, for every weight-gradient GEMM in the order layer 0..L, an int32 map
+    [N_img][K_img] -> index into the flat gradient blob (-1: masked or padding), followed by the bias map
+    [N_img].  ``tiles``: (t, l, n0, k0) of every 32x32 output tile of the weight-gradient GEMMs."""
+    tstride: int
+    bias_off: int
+    map_tstride: int
+    meta: np.ndarray
+    gather: np.ndarray
+    wmap: np.ndarray
+    tiles: np.ndarray
+
+    @property
+    def numel(self):
+        return int(self.gather.size)
+
+
+def train_supported(n_dim: int, n_hidden: int, kind: int) -> bool:
+    return kind == KIND_AFFINE and n_hidden in (32, 64, 128) and 2 <= n_dim <= 64
+
+
+@lru_cache(maxsize=None)
+def build_train(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8) -> TrainLayout:
+    if not train_supported(n_dim, n_hidden, kind):
+        raise ValueError("flow not supported by the fused training kernels")
+    lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
+    D, H, L, T = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms
+    Dp = (D + 31) // 32 * 32
+    No = 2 * Dp
+    raw_off = np.concatenate([[0], np.cumsum([int(np.prod(s)) for s in lay.raw_sizes])]).astype(np.int64)
+    # permuted output column c -> raw output row (2 d + s) or -1
+    col2row = np.full(No, -1, np.int64)
+    for s_ in range(2):
+        col2row[s_ * Dp + np.arange(D)] = 2 * np.arange(D) + s_
+    gathers, maps, tiles = [], [], []
+    bias_off = None
+    for t in range(T):
+        base_r = t * lay.raw_tstride
+        mks = masks(lay, t)
+        idx = []                                           # per layer: raw index of (W*mask)[n][k] in IMAGE coords, -1 elsewhere
+        for l in range(L + 1):
+            K_true = D if l == 0 else H
+            w_off = base_r + raw_off[2 * l]
+            if l < L:
+                full = np.where(mks[l], w_off + np.arange(H)[:, None] * K_true + np.arange(K_true)[None, :], -1)   # [H][K_true]
+            else:
+                full = np.full((No, H), -1, np.int64)
+                ok = col2row >= 0
+                rows = col2row[ok]
+                full[ok] = np.where(mks[l][rows], w_off + rows[:, None] * H + np.arange(H)[None, :], -1)
+            idx.append(full)
+        parts = []
+        for l in range(L + 1):                             # forward images [K][N]
+            parts.append(idx[l].T.reshape(-1))
+        for l in range(L, -1, -1):                         # backward images [N][K] (layer 0 padded to Dp columns)
+            if l == 0:
+                b0 = np.full((H, Dp), -1, np.int64)
+                b0[:, :D] = idx[0]
+                parts.append(b0.reshape(-1))
+            else:
+                parts.append(idx[l].reshape(-1))
+        wf = int(sum(len(a) for a in parts))
+        bmaps = []
+        for l in range(L + 1):
+            b_off = base_r + raw_off[2 * l + 1]
+            if l < L:
+                bm = b_off + np.arange(H)
+            else:
+                bm = np.where(col2row >= 0, b_off + col2row, -1)
+            parts.append(bm)
+            bmaps.append(bm)
+        if bias_off is None:
+            bias_off = wf
+        gathers.append(np.concatenate(parts))
+        mp = []
+        for l in range(L + 1):
+            mp.append(idx[l].reshape(-1))                  # [N_img][K_true]
+            mp.append(bmaps[l])
+            N_img, K_true = idx[l].shape
+            for n0 in range(0, N_img, 32):
+                for k0 in range(0, K_true, 32):
+                    tiles.append((t, l, n0, k0))
+        maps.append(np.concatenate(mp))
+    tstride = len(gathers[0])
+    assert tstride % 4 == 0 and bias_off % 4 == 0
+    gather = np.concatenate(gathers)
+    wmap = np.concatenate(maps)
+    meta = np.zeros(TR_LEN, np.int64)
+    meta[[TR_D, TR_DP, TR_H, TR_L, TR_T, TR_NO, TR_TSTRIDE, TR_BIAS_OFF, TR_RAW_TSTRIDE, TR_MAP_TSTRIDE, TR_NTILES, TR_VERSION]] = \
+        [D, Dp, H, L, T, No, tstride, bias_off, lay.raw_tstride, len(maps[0]), len(tiles), 200]
+    return TrainLayout(tstride, bias_off, len(maps[0]), meta.astype(np.int32), gather.astype(np.int32), wmap.astype(np.int32),
+                       np.asarray(tiles, np.int32).reshape(-1, 4))
