@@ -13,6 +13,10 @@ disabled.  particle-steps/s = particles x MCMC steps / time.
   e2e   : the reference-facing call `pocomc_b200.mcmc.preconditioned_pcn(state_dict, function_dict,
           option_dict)` with HOST numpy buffers, the likelihood and the scipy prior as host black
           boxes (x' D2H and logl'/logp' H2D every MCMC step), state H2D and result D2H per call.
+  aux   : untimed-region extras on rank 0 at N=1 -- the tcgen05 dense flow forward (issued TFLOP/s against the
+          measured tensor peak), one Flow.fit optimiser step on the fused training kernels, and a FULL
+          Sampler.run() of BASELINE configs[0] (10-D Rosenbrock, 1000 particles) whose logZ is compared with
+          the unmodified reference's (tests/golden/rosen10.json) -- the "logZ abs-err vs ref" half of the metric.
   --impl reference : the reference's own CPU path for the same call.  pocoMC is pure Python and
           needs the third-party zuko (absent here and on the GPU box), so the arm runs the in-repo
           CPU oracle port (oracle/smc_ref.py + oracle/zuko) on all host threads.
@@ -310,7 +314,7 @@ def run_b200(args):
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     achieved_tf = flop / (sweep_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
-                    traffic=None, kernel="made_sweep_kernel<Affine> (flow inverse, degree-ordered sweep)",
+                    traffic=None, kernel="made_sweep_stream_kernel<Affine> (flow inverse, degree-ordered sweep)",
                     peak_source="MEASURED_PEAKS.json bf16 burst" if peaks else "fallback 1.59 PFLOP/s",
                     flop_per_launch=flop, avg_launch_ms=sweep_ms,
                     note="fp32 FMA sweep on CUDA cores; 2*nnz(masks) useful FLOP per particle; share of step = "
@@ -325,6 +329,10 @@ def run_b200(args):
                 e2e=dict(value=e2e_value, unit="particle-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=1e3 * t_e2e / args.steps, rng="device Philox", callbacks="host numpy likelihood (black box); pc.Prior of scipy norm factors evaluated on the GPU"),
                 gpu_launches=launches, roofline=roofline, accept_rate=accept_dev)
+    line["roofline"].update(fp32_fma_peak_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
+                            frac_of_fp32_fma_peak=achieved_tf / (148 * 128 * 2 * 1.965e9 / 1e12))
+    if rank == 0 and world == 1 and not args.no_aux:
+        line["aux"] = aux_measurements(flow, peaks)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         params = [p.detach().cpu().numpy() for _, p in sorted(flow_param_arrays(flow))]
@@ -338,6 +346,101 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+
+# ---------------------------------------------------------------------------------------------
+# auxiliary measurements (rank 0, N = 1): tensor-core forward, training step, full-run logZ
+# ---------------------------------------------------------------------------------------------
+def aux_measurements(flow, peaks):
+    import torch
+    import pocomc_b200 as pc
+    from pocomc_b200.flow import _FitEngine
+    out = {}
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # (1) Flow.forward on tcgen05 (csrc/flow_tc.cu): 1 M particles >> L2, 3xTF32
+    mod = flow.flow
+    if mod.tc_available():
+        n = 1 << 20
+        x = torch.randn(n, N_DIM, device="cuda")
+        z = torch.empty_like(x)
+        l = torch.empty(n, device="cuda")
+        lay = mod.layout
+        kx, nout, h = (N_DIM + 7) // 8 * 8, (2 * N_DIM + 15) // 16 * 16, lay.n_hidden
+        # issued MMA FLOP per particle: per transform 3 passes x 2 x (Kx*H + (L-1)*H*H + H*Nout) + the bias k-steps
+        per_t = 2 * (kx * h + (lay.n_layers - 1) * h * h + h * nout) + 2 * 8 * (lay.n_layers * h + nout)
+        ms3 = timeit(lambda: mod.forward_tc_into(x, z, l, 3), 10)
+        ms_sweep = timeit(lambda: mod.sweep_into(x[:100_000], z[:100_000], l[:100_000], False), 3) * (n / 100_000)
+        issued = 3 * per_t * lay.n_transforms * n / (ms3 * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        out["flow_forward_tcgen05"] = dict(particles=n, ms=ms3, particles_per_s=n / (ms3 * 1e-3), issued_tflops=issued,
+                                           useful_tflops=issued / 3, frac_of_bf16_peak=issued / peak,
+                                           frac_of_tf32_peak=issued / (peak / 2), sweep_kernel_ms_extrapolated=ms_sweep,
+                                           note="kind::tf32 MMAs, 3-pass split for fp32 fidelity; TF32 peak taken as half the measured bf16 peak")
+        del x, z, l
+    # (2) one optimiser step of Flow.fit (batch 512) on the fused kernels inside a CUDA graph
+    try:
+        f2 = pc.Flow(N_DIM, FLOW)
+        eng = _FitEngine(f2.flow)
+        xt = torch.randn(8192, N_DIM, device="cuda")
+        wt = torch.rand(8192, device="cuda") + 0.1
+        eng.load(xt, wt)
+        eng.reset_optimizer(1e-3, 0.0, 1.0)
+        batches = [torch.arange(i, i + 512) for i in range(0, 8192, 512)]
+        eng.run_epoch(batches, 512, True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            eng.run_epoch(batches, 512, True)
+        torch.cuda.synchronize()
+        out["fit_step"] = dict(batch=512, flow=FLOW, n_dim=N_DIM, us_per_optimizer_step=(time.perf_counter() - t0) / 80 * 1e6,
+                               path="fused forward/backward + grouped weight-gradient GEMM + clip/AdamW, one CUDA graph launch"
+                               if eng.fused else "autograd in a CUDA graph")
+    except Exception as e:      # diagnostics only
+        out["fit_step"] = dict(error=repr(e))
+    # (3) full Sampler.run() of BASELINE configs[0]; logZ against the unmodified reference
+    try:
+        from scipy.stats import uniform
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "rosen10.json")))["runs"]
+
+        def rosen(x):
+            return -np.sum(10.0 * (x[:, ::2] ** 2.0 - x[:, 1::2]) ** 2.0 + (x[:, ::2] - 1.0) ** 2.0, axis=1)
+
+        runs = []
+        for rep in range(2):                                   # the first run pays graph capture / page-in
+            smp = pc.Sampler(pc.Prior([uniform(-10.0, 20.0)] * 10), rosen, vectorize=True, n_active=1000, n_effective=2000,
+                             flow="maf6", random_state=0)
+            t0 = time.perf_counter()
+            smp.run(n_total=4096, n_evidence=4096, progress=False)
+            wall = time.perf_counter() - t0
+            logz, err = smp.evidence()
+            steps = int(np.sum(smp.results["steps"]))
+            runs.append((wall, float(logz), float(err), steps))
+        wall, logz, err, steps = runs[-1]
+        ref_logz = float(np.mean([g["logz"] for g in gold]))
+        out["full_run"] = dict(workload="BASELINE configs[0]: 10-D Rosenbrock, U(-10,10)^10, n_active=1000, n_effective=2000, maf6, n_total=4096",
+                               rng_mode=pc.config.rng_mode, seconds=wall, first_run_seconds=runs[0][0], mcmc_steps=steps, particle_steps_per_s=1000 * steps / wall,
+                               logz=logz, logz_err=err, reference_logz=[g["logz"] for g in gold],
+                               reference_logz_err=[g["logz_err"] for g in gold], logz_abs_err=abs(logz - ref_logz),
+                               reference_cpu_seconds=[g["wall_s"] for g in gold], reference_cpu_cores=gold[0]["cores"],
+                               reference_particle_steps_per_s=[g["particle_steps_per_s"] for g in gold],
+                               note="reference = unmodified pocomc on the build container's CPU (oracle/make_golden_rosen.py); "
+                                    "both logZ carry the sampler's own Monte-Carlo error (logz_err)")
+    except Exception as e:
+        out["full_run"] = dict(error=repr(e))
+    return out
 
 
 def flow_param_arrays(flow):
@@ -356,6 +459,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the untimed auxiliary measurements (tcgen05 forward, fit step, full run)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

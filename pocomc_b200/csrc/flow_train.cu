@@ -48,6 +48,7 @@ struct TrainParams {
   float* logprob;            // [Bp] per-row log-probability (may be nullptr)
   int Bp, D, Dp, H, L, T, No, tstride, bias_off;
   int weighted, backward;
+  int ns;                    // weight ring depth (2..8 slots of the largest image)
 };
 
 // acc[i][j] = sum_k At[k][4 ty + i] * W[k][tx + 32 j]
@@ -84,31 +85,32 @@ __device__ __forceinline__ void gemm_any(int tn, const float* At, int K, const f
 
 __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t full[2];
+  __shared__ uint64_t full[8];
   __shared__ float crow[TR_ROWS];
   __shared__ double lossrow[TR_ROWS];
   __shared__ float red[8];
   const int D = p.D, Dp = p.Dp, H = p.H, L = p.L, T = p.T, No = p.No, Bp = p.Bp;
-  const int wmax = max(max(D * H, H * H), max(H * No, H * Dp));
+  const int wmax = max(max((D + 1) * H, (H + 1) * H), max((H + 1) * No, H * Dp));
   const int brows = max(H, No);
-  float* wbuf0 = reinterpret_cast<float*>(smem_raw);
-  float* wbuf1 = wbuf0 + wmax;
-  float* bufA = wbuf1 + wmax;
+  const int NS = p.ns;
+  float* wring = reinterpret_cast<float*>(smem_raw);
+  float* bufA = wring + (size_t)NS * wmax;
   float* bufB = bufA + brows * TR_LDA;
   float* xT = bufB + brows * TR_LDA;
   float* gT = xT + Dp * TR_LDA;
+  uint32_t* relu_bits = reinterpret_cast<uint32_t*>(gT + Dp * TR_LDA);   // [T*L][256]: (h > 0) of this thread's 4 x 4 outputs
 
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   const int row0 = blockIdx.x * TR_ROWS;
   const int n_img = (p.backward ? 2 : 1) * T * (L + 1);
   const int fwd_img = T * (L + 1);
-  const int bwd_base = D * H + (L - 1) * H * H + H * No;
+  const int bwd_base = (D + 1) * H + (L - 1) * (H + 1) * H + (H + 1) * No;
 
   auto img = [&](int s, int& off, int& n) {
     if (s < fwd_img) {
       const int t = s / (L + 1), l = s - t * (L + 1);
-      off = t * p.tstride + (l == 0 ? 0 : D * H + (l - 1) * H * H);
-      n = (l == 0) ? D * H : (l < L ? H * H : H * No);
+      off = t * p.tstride + (l == 0 ? 0 : (D + 1) * H + (l - 1) * (H + 1) * H);
+      n = (l == 0) ? (D + 1) * H : (l < L ? (H + 1) * H : (H + 1) * No);      // weights [K][N] then bias [N]
     } else {
       const int q = s - fwd_img;
       const int tb = T - 1 - q / (L + 1), j = q % (L + 1);
@@ -119,15 +121,13 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   auto issue = [&](int s) {
     int off, n;
     img(s, off, n);
-    mbar_expect_tx(full + (s & 1), (uint32_t)n * 4u);
-    bulk_g2s((s & 1) ? wbuf1 : wbuf0, p.packed + off, (uint32_t)n * 4u, full + (s & 1));
+    mbar_expect_tx(full + (s % NS), (uint32_t)n * 4u);
+    bulk_g2s(wring + (size_t)(s % NS) * wmax, p.packed + off, (uint32_t)n * 4u, full + (s % NS));
   };
   if (tid == 0) {
-    mbar_init(full, 1);
-    mbar_init(full + 1, 1);
+    for (int i = 0; i < NS; ++i) mbar_init(full + i, 1);
     mbar_fence_init();
-    issue(0);
-    if (n_img > 1) issue(1);
+    for (int i = 0; i < NS && i < n_img; ++i) issue(i);
   }
 
   // ---- batch rows, loss coefficients c_r (flow.py:305-310) ----
@@ -164,44 +164,50 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   int s = 0;
   // =========================== forward ===========================
   for (int t = 0; t < T; ++t) {
-    const float* bias = p.packed + (size_t)t * p.tstride + p.bias_off;
     float* in = xT;
     float* out = bufA;
     for (int l = 0; l < L; ++l) {
-      mbar_wait(full + (s & 1), (s >> 1) & 1);
-      gemm_any(tnH, in, l == 0 ? D : H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
+      mbar_wait(full + (s % NS), (s / NS) & 1);
+      const int Kl = (l == 0) ? D : H;
+      const float* wimg = wring + (size_t)(s % NS) * wmax;
+      gemm_any(tnH, in, Kl, wimg, ty, tx, acc);
+      const float* bias = wimg + Kl * H;                      // bias rides behind the weights in the same bulk copy
       float* hs = p.Hs + ((size_t)(t * L + l) * Bp + row0 + 4 * ty) * H;
+      uint32_t bits = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j >= tnH) continue;
         const int c = tx + 32 * j;
-        const float b = __ldg(bias + l * H + c);
+        const float b = bias[c];
         float h[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float v = acc[i][j] + b;
           if (l > 0) v += in[c * TR_LDA + 4 * ty + i];        // residual block
           h[i] = fmaxf(v, 0.f);
+          bits |= (h[i] > 0.f ? 1u : 0u) << (4 * i + j);
           hs[(size_t)i * H + c] = h[i];
         }
         *reinterpret_cast<float4*>(out + c * TR_LDA + 4 * ty) = make_float4(h[0], h[1], h[2], h[3]);
       }
+      relu_bits[(t * L + l) * 256 + tid] = bits;
       __syncthreads();
-      if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+      if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
       ++s;
       in = out;
       out = (out == bufA) ? bufB : bufA;
     }
     // output layer + affine map
-    mbar_wait(full + (s & 1), (s >> 1) & 1);
-    gemm_any(tnO, in, H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
-    const float* bo = bias + L * H;
+    mbar_wait(full + (s % NS), (s / NS) & 1);
+    const float* wimg_o = wring + (size_t)(s % NS) * wmax;
+    gemm_any(tnO, in, H, wimg_o, ty, tx, acc);
+    const float* bo = wimg_o + H * No;
 #pragma unroll
   #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
       if (jj >= tnD) continue;
       const int d = tx + 32 * jj;
-      const float bs = __ldg(bo + d), br = __ldg(bo + Dp + d);
+      const float bs = bo[d], br = bo[Dp + d];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float z = 0.f;
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       }
     }
     __syncthreads();                                           // every thread has read xT and the weight slot
-    if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+    if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
     ++s;
 #pragma unroll
   #pragma unroll
@@ -268,8 +274,30 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     for (int i = 0; i < 4; ++i) gT[d * TR_LDA + 4 * ty + i] = crow[4 * ty + i] * znew[i][jj];
   }
   __syncthreads();
+  // transform inputs / raw log-scales of the affine backward are prefetched one transform ahead so the
+  // global-memory latency never sits on the layer chain
+  float xn[4][2], sn[4][2];
+  auto prefetch_xs = [&](int t) {
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      if (jj >= tnD) continue;
+      const int d = tx + 32 * jj;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const size_t o = ((size_t)t * Bp + row0 + 4 * ty + i) * Dp + d;
+        xn[i][jj] = (d < D) ? p.X[o] : 0.f;
+        sn[i][jj] = (d < D) ? p.S[o] : 0.f;
+      }
+    }
+  };
+  prefetch_xs(T - 1);
   for (int t = T - 1; t >= 0; --t) {
-    float gxd[4][2];
+    float gxd[4][2], xc[4][2], sc[4][2];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xc[i][jj] = xn[i][jj]; sc[i][jj] = sn[i][jj]; }
+    if (t > 0) prefetch_xs(t - 1);
     // affine map backward -> gradient of the output layer (shift | scale_raw) as the next GEMM's input
 #pragma unroll
   #pragma unroll
@@ -281,9 +309,8 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
         const int r = 4 * ty + i;
         float gshift = 0.f, gsraw = 0.f, gx = 0.f;
         if (d < D) {
-          const size_t o = ((size_t)t * Bp + row0 + r) * Dp + d;
           const float gz = gT[d * TR_LDA + r];
-          const float x = p.X[o], sraw = p.S[o];
+          const float x = xc[i][jj], sraw = sc[i][jj];
           const float den = 1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS;
           const float e = expf(sraw / den);
           gshift = gz;
@@ -303,9 +330,9 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float* out = bufB;
     for (int j = 0; j < L; ++j) {                              // images B_o, B_{L-1}, ..., B_1
       const int lh = L - 1 - j;                                // hidden layer whose pre-activation gradient comes out
-      mbar_wait(full + (s & 1), (s >> 1) & 1);
-      gemm_any(tnH, in, j == 0 ? No : H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
-      const float* hs = p.Hs + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
+      mbar_wait(full + (s % NS), (s / NS) & 1);
+      gemm_any(tnH, in, j == 0 ? No : H, wring + (size_t)(s % NS) * wmax, ty, tx, acc);
+      const uint32_t bits = relu_bits[(t * L + lh) * 256 + tid];
       float* gh = p.Gh + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
 #pragma unroll
       for (int jn = 0; jn < 4; ++jn) {
@@ -316,19 +343,19 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
         for (int i = 0; i < 4; ++i) {
           float v = acc[i][jn];
           if (j > 0) v += in[c * TR_LDA + 4 * ty + i];         // residual path
-          g[i] = (hs[(size_t)i * H + c] > 0.f) ? v : 0.f;      // ReLU
+          g[i] = ((bits >> (4 * i + jn)) & 1u) ? v : 0.f;       // ReLU
           gh[(size_t)i * H + c] = g[i];
         }
         *reinterpret_cast<float4*>(out + c * TR_LDA + 4 * ty) = make_float4(g[0], g[1], g[2], g[3]);
       }
       __syncthreads();
-      if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+      if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
       ++s;
       float* tmp = in; in = out; out = tmp;
     }
     // image B_0: gradient w.r.t. the transform input through the hyper-network + the direct path
-    mbar_wait(full + (s & 1), (s >> 1) & 1);
-    gemm_any(tnD, in, H, (s & 1) ? wbuf1 : wbuf0, ty, tx, acc);
+    mbar_wait(full + (s % NS), (s / NS) & 1);
+    gemm_any(tnD, in, H, wring + (size_t)(s % NS) * wmax, ty, tx, acc);
 #pragma unroll
   #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
@@ -338,7 +365,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
           make_float4(gxd[0][jj] + acc[0][jj], gxd[1][jj] + acc[1][jj], gxd[2][jj] + acc[2][jj], gxd[3][jj] + acc[3][jj]);
     }
     __syncthreads();
-    if (tid == 0) { fence_proxy_async(); if (s + 2 < n_img) issue(s + 2); }
+    if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
     ++s;
   }
 }
@@ -360,14 +387,25 @@ __global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams
   const int* bmap = map + n_img * k_true;
   const int tid = threadIdx.x, a = tid >> 4, b = tid & 15;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, bacc[2] = {0.f, 0.f};
+  float pd[4], pi[4];                                          // next chunk, fetched while the current one is reduced
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + 256 * q, rr = e >> 5, c = e & 31;
+      pd[q] = dpre[(size_t)(r0 + rr) * n_img + n0 + c];
+      pi[q] = (k0 + c < k_true) ? inp[(size_t)(r0 + rr) * ldk + k0 + c] : 0.f;
+    }
+  };
+  fetch(0);
   for (int r0 = 0; r0 < Bp; r0 += 32) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int e = tid + 256 * q, rr = e >> 5, c = e & 31;
-      dp[rr][c] = dpre[(size_t)(r0 + rr) * n_img + n0 + c];
-      in[rr][c] = (k0 + c < k_true) ? inp[(size_t)(r0 + rr) * ldk + k0 + c] : 0.f;
+      dp[rr][c] = pd[q];
+      in[rr][c] = pi[q];
     }
     __syncthreads();
+    if (r0 + 32 < Bp) fetch(r0 + 32);
 #pragma unroll 8
     for (int rr = 0; rr < 32; ++rr) {
       const float d0 = dp[rr][2 * a], d1 = dp[rr][2 * a + 1], i0 = in[rr][2 * b], i1 = in[rr][2 * b + 1];
@@ -395,10 +433,13 @@ __global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams
   }
 }
 
-static size_t train_smem(int D, int Dp, int H, int No) {
-  const size_t wmax = (size_t)std::max(std::max(D * H, H * H), std::max(H * No, H * Dp));
+static size_t train_smem(int D, int Dp, int H, int No, int T, int L, int& ns) {
+  const size_t wmax = (size_t)std::max(std::max((D + 1) * H, (H + 1) * H), std::max((H + 1) * No, H * Dp));
   const size_t brows = (size_t)std::max(H, No);
-  return (2 * wmax + 2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4;
+  const size_t act = (2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4 + (size_t)T * L * 256 * 4;
+  // small networks: a deeper ring lets the bulk copies run several layers ahead of the (latency-bound) chain
+  ns = (int)std::min<size_t>(8, std::max<size_t>(2, (200 * 1024 - act) / (wmax * 4)));
+  return (size_t)ns * wmax * 4 + act;
 }
 
 }  // namespace pmc
@@ -435,7 +476,7 @@ extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host
   p.Gh = p.Hs + (size_t)p.T * p.L * bpz * p.H;
   p.Go = p.Gh + (size_t)p.T * p.L * bpz * p.H;
   p.loss_partials = loss_partials; p.logprob = logprob;
-  const size_t smem = train_smem(p.D, p.Dp, p.H, p.No);
+  const size_t smem = train_smem(p.D, p.Dp, p.H, p.No, p.T, p.L, p.ns);
   PMC_REQUIRE(smem <= 220 * 1024, "pmc_flow_train_step: shared memory budget exceeded");
   cudaStream_t st = as_stream(stream);
   PMC_TRY(cudaFuncSetAttribute(flow_train_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -480,9 +480,9 @@ TR_D, TR_DP, TR_H, TR_L, TR_T, TR_NO, TR_TSTRIDE, TR_BIAS_OFF, TR_RAW_TSTRIDE, T
 @dataclass(frozen=True)
 class TrainLayout:
     """Per transform (float offsets, every image a multiple of 4 floats):
-      forward images  F_0 [D][H], F_1..F_{L-1} [H][H], F_o [H][No]      F_l[k][n] = (W_l * mask_l)[n][k]
+      forward images  F_0 [D][H], F_1..F_{L-1} [H][H], F_o [H][No]      F_l[k][n] = (W_l * mask_l)[n][k],
+                      each followed by its bias [N] (one bulk copy brings both)
       backward images B_o [No][H], B_{L-1}..B_1 [H][H], B_0 [H][Dp]      B_l[n][k] = (W_l * mask_l)[n][k]
-      biases b_0..b_{L-1} [H], b_o [No]
     Output columns are permuted: column c = d + Dp*s holds shift (s = 0) / scale_raw (s = 1) of feature d
     (Dp = D rounded up to 32, No = 2 Dp), so one thread owns both parameters of a feature.
     ``gather``: packed[i] = raw[gather[i]] (-1 -> 0): the existing pmc_flow_pack kernel builds the image.
@@ -536,9 +536,14 @@ def build_train(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kin
                 rows = col2row[ok]
                 full[ok] = np.where(mks[l][rows], w_off + rows[:, None] * H + np.arange(H)[None, :], -1)
             idx.append(full)
+        bmaps = []
+        for l in range(L + 1):
+            b_off = base_r + raw_off[2 * l + 1]
+            bmaps.append(b_off + np.arange(H) if l < L else np.where(col2row >= 0, b_off + col2row, -1))
         parts = []
-        for l in range(L + 1):                             # forward images [K][N]
+        for l in range(L + 1):                             # forward images [K][N] followed by the bias [N]
             parts.append(idx[l].T.reshape(-1))
+            parts.append(bmaps[l])
         for l in range(L, -1, -1):                         # backward images [N][K] (layer 0 padded to Dp columns)
             if l == 0:
                 b0 = np.full((H, Dp), -1, np.int64)
@@ -547,15 +552,6 @@ def build_train(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kin
             else:
                 parts.append(idx[l].reshape(-1))
         wf = int(sum(len(a) for a in parts))
-        bmaps = []
-        for l in range(L + 1):
-            b_off = base_r + raw_off[2 * l + 1]
-            if l < L:
-                bm = b_off + np.arange(H)
-            else:
-                bm = np.where(col2row >= 0, b_off + col2row, -1)
-            parts.append(bm)
-            bmaps.append(bm)
         if bias_off is None:
             bias_off = wf
         gathers.append(np.concatenate(parts))
