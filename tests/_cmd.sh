@@ -1,3 +1,3 @@
-timeout 300 python tests/run_profile.py rosen10 1000 2>&1 | tail -1
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/train_launches.csv python tests/train_bench.py profile > /dev/null 2>&1
-python profiles/summarise.py launches gpurun_out/train_launches.csv
+timeout 100 python tests/sweep_bench.py 2>&1 | tail -2
+N=100000 timeout 100 python tests/sweep_bench.py 2>&1 | tail -2
+timeout 300 python -m pytest tests/test_gpu_flow.py -x -q -k "sweep_vs_oracle or goldens" 2>&1 | tail -2
