@@ -14,7 +14,8 @@ import os
 import torch
 import torch.distributed as td
 
-__all__ = ["init_from_env", "is_active", "world", "shard_range", "gather_blocks", "allreduce_sum_det"]
+__all__ = ["init_from_env", "is_active", "world", "shard_range", "shard_counts", "gather_blocks", "allreduce_sum_det",
+           "allreduce_sum_int"]
 
 
 def init_from_env(backend: str = None):
@@ -53,11 +54,24 @@ def shard_range(n_total: int, rank: int, world_size: int, align: int = 1):
     return min(start_u * align, n_total), min(stop_u * align, n_total)
 
 
+def shard_counts(n_total: int, world_size: int, align: int = 1):
+    """Rows owned by every rank under ``shard_range``."""
+    return [b - a for a, b in (shard_range(n_total, r, world_size, align) for r in range(world_size))]
+
+
+def _host_staged(t: torch.Tensor) -> bool:
+    """gloo (the CPU / single-GPU test backend) has no all-gather for CUDA tensors: stage through the host."""
+    return t.is_cuda and td.get_backend() == "gloo"
+
+
 def gather_blocks(local: torch.Tensor, counts=None) -> torch.Tensor:
-    """All-gather per-rank [b_r, w] block partials into [sum_r b_r, w] in rank order.  ``counts``
-    (blocks per rank) may differ between ranks; equal counts take the single-collective path."""
+    """All-gather per-rank [b_r, w] rows (block partials, mutated particles) into [sum_r b_r, w] in
+    rank order.  ``counts`` (rows per rank) may differ between ranks; equal counts take the
+    single-collective path."""
     if not is_active():
         return local
+    if _host_staged(local):
+        return gather_blocks(local.cpu(), counts).to(local.device)
     ws = td.get_world_size()
     if counts is None:
         counts = [local.shape[0]] * ws
@@ -65,9 +79,13 @@ def gather_blocks(local: torch.Tensor, counts=None) -> torch.Tensor:
         out = torch.empty((ws * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         td.all_gather_into_tensor(out, local.contiguous())
         return out
-    parts = [torch.empty((c,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for c in counts]
-    td.all_gather(parts, local.contiguous())
-    return torch.cat(parts, dim=0)
+    # ragged: one equal-size collective over rows padded to the largest shard, padding dropped afterwards
+    cmax = max(counts)
+    padded = torch.zeros((cmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((ws * cmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    td.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * cmax:r * cmax + c] for r, c in enumerate(counts)], dim=0)
 
 
 def allreduce_sum_det(values: torch.Tensor) -> torch.Tensor:
@@ -80,3 +98,13 @@ def allreduce_sum_det(values: torch.Tensor) -> torch.Tensor:
     for r in range(1, g.shape[0]):
         out += g[r]
     return out.reshape(values.shape)
+
+
+def allreduce_sum_int(value: int) -> int:
+    """Exact sum of one integer per rank (likelihood-call counters)."""
+    if not is_active():
+        return int(value)
+    dev = "cpu" if td.get_backend() == "gloo" else torch.device("cuda", torch.cuda.current_device())
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    td.all_reduce(t)
+    return int(t.item())

@@ -379,6 +379,7 @@ class _FitEngine:
     (csrc/train_ops.cu), loss accumulation.  A batch costs one graph launch; ragged last batches reuse
     the full-size graph with zero-weight padding rows."""
     MAX_BATCHES = 512
+    _staging_free = None    # CUDA event: the last upload out of the shared pinned batch tables has completed
 
     def __init__(self, module: "MaskedAutoregressiveFlow"):
         self.module = module
@@ -540,6 +541,11 @@ class _FitEngine:
         idx_all, mask_all = self._tables(B)
         hi = _lib.pinned("fit_idx", (nb, B), torch.int64)
         hm = _lib.pinned("fit_mask", (nb, B), torch.float32)
+        # the staging buffers are shared by every epoch (and engine): the previous epoch's asynchronous upload must
+        # have left them before the host refills them (a busy GPU delays that copy well past this point)
+        ev = _FitEngine._staging_free
+        if ev is not None:
+            ev.synchronize()
         hi.zero_(); hm.zero_()
         for i, b in enumerate(batches):
             hi[i, :len(b)] = b + offset
@@ -548,6 +554,8 @@ class _FitEngine:
         g = self.graph(B, weighted, train)
         idx_all[:nb].copy_(hi, non_blocking=True)
         mask_all[:nb].copy_(hm, non_blocking=True)
+        _FitEngine._staging_free = torch.cuda.Event()
+        _FitEngine._staging_free.record()
         self.cursor.zero_()
         self.acc.zero_()
         for _ in range(nb):

@@ -98,6 +98,15 @@ class McmcEngine:
         # -- controller block
         logl0, logp0, ldj0 = (np.asarray(state_dict.get(k), dtype=np.float64) for k in ('logl', 'logp', 'logdetj'))
         best = np.mean(logl0 + logp0) if self.tp else np.mean(logl0 + logp0 + ldj0)   # mcmc.py:70 / 243
+        shard = option_dict.get('shard')
+        if shard is not None and dist.is_active():
+            # the plateau tracker starts from the mean over ALL particles (mcmc.py:70 / 243): the caller that holds the
+            # full arrays hands it over (bit-identical to a single-GPU run); otherwise rank-ordered sum of shard sums
+            if option_dict.get('best0') is not None:
+                best = float(option_dict['best0'])
+            else:
+                tot = logl0 + logp0 if self.tp else logl0 + logp0 + ldj0
+                best = float(dist.allreduce_sum_det(torch.tensor([np.sum(tot)], dtype=torch.float64, device=dev))[0].item()) / shard[1]
         ctl = np.zeros(CTL_MU + d)
         ctl[CTL_SIGMA], ctl[CTL_BEST] = sigma, best
         ctl[CTL_MU:] = mu
@@ -130,7 +139,6 @@ class McmcEngine:
         self.rng_mode = config.rng_mode
         self.mean_mode = config.resolved_mean_mode()
         # particle sharding: option_dict['shard'] = (global offset of row 0, global particle count, blocks per rank)
-        shard = option_dict.get('shard')
         self.sharded = shard is not None and dist.is_active()
         self.row_offset, self.n_global, self.shard_blocks = (shard if shard is not None else (0, n, None))
         if self.sharded:
@@ -153,11 +161,14 @@ class McmcEngine:
         """N gammas then N*D normals (mcmc.py:80,85 / 253), host stream or Philox."""
         n, d = self.n, self.d
         if self.rng_mode == "host":
+            # sharded: every rank walks the same global stream (identical seeds) and keeps its own rows, so the
+            # trajectory of a particle does not depend on the number of GPUs
             hn = self.h_noise.numpy()
+            ng, lo = (self.n_global, self.row_offset) if self.sharded else (n, 0)
             if self.tp:
-                hn[:n] = np.random.standard_gamma((d + self.nu) / 2, size=n)   # == gamma(a, s_k)/s_k draw for draw
+                hn[:n] = np.random.standard_gamma((d + self.nu) / 2, size=ng)[lo:lo + n]   # == gamma(a, s_k)/s_k draw for draw
                 self.g.copy_(self.h_noise[:n], non_blocking=True)
-            hn[n:n + n * d] = np.random.randn(n, d).reshape(-1)
+            hn[n:n + n * d] = np.random.randn(ng, d)[lo:lo + n].reshape(-1)
             self.z.copy_(self.h_noise[n:n + n * d].view(n, d), non_blocking=True)
         else:
             _lib.call("pmc_rng_fill", C.c_uint64(self.seed), C.c_uint64(self.step + 1), int(self.row_offset),
@@ -242,7 +253,8 @@ class McmcEngine:
         n, d = self.n, self.d
         if self.rng_mode == "host":
             hn = self.h_noise.numpy()
-            hn[n + n * d:] = np.random.rand(n)                                   # mcmc.py:137
+            ng, lo = (self.n_global, self.row_offset) if self.sharded else (n, 0)
+            hn[n + n * d:] = np.random.rand(ng)[lo:lo + n]                       # mcmc.py:137
             self.r.copy_(self.h_noise[n + n * d:], non_blocking=True)
         _lib.call("pmc_mh_accept_update", self.kind, self.beta, self.nu, _lib.ptr(self.theta), _lib.ptr(self.u),
                   _lib.ptr(self.x), _lib.ptr(self.logdetj), _lib.ptr(self.logl), _lib.ptr(self.logp), _lib.ptr(self.ldjf),

@@ -15,7 +15,7 @@ import dill
 import numpy as np
 import torch
 
-from . import _lib, config
+from . import _lib, config, dist
 from .flow import Flow
 from .geometry import Geometry
 from .mcmc import pcn, preconditioned_pcn, preconditioned_rwm, rwm
@@ -171,7 +171,7 @@ class Sampler:
             self.pbar.update_stats(self._history_stats())
         else:
             t0 = self.t
-            self.progress = progress
+            self.progress = progress and dist.world()[0] == 0          # sharded runs: rank 0 owns the progress bar
             self.pbar = ProgressBar(self.progress)
             self.pbar.update_stats(dict(beta=0.0, calls=self.calls, ESS=self.n_effective, logZ=0.0, logP=0.0,
                                         acc=0.0, steps=0, eff=0.0))
@@ -264,7 +264,10 @@ class Sampler:
                            proposal_scale=self.proposal_scale)
         kernel = {(True, "tpcn"): preconditioned_pcn, (True, "rwm"): preconditioned_rwm,
                   (False, "tpcn"): pcn, (False, "rwm"): rwm}[(bool(self.preconditioned), self.sample)]
-        results = kernel(state_dict, function_dict, option_dict)
+        if dist.is_active() and self.n_active >= dist.world()[1]:
+            results = self._mutate_sharded(kernel, state_dict, function_dict, option_dict)
+        else:
+            results = kernel(state_dict, function_dict, option_dict)
         for key in ("u", "x", "logdetj", "logl", "logp"):
             current_particles[key] = results.get(key).copy()
         if self.have_blobs:
@@ -276,6 +279,41 @@ class Sampler:
         self.calls = current_particles.get("calls")
         self.proposal_scale = results.get('proposal_scale')
         return current_particles
+
+    def _mutate_sharded(self, kernel, state_dict, function_dict, option_dict):
+        """One process per GPU: every rank holds the same replicated sampler (same
+        ``random_state``, same history, same flow) and mutates only its contiguous block of the active
+        particles -- so the host likelihood is called on 1/G of the rows per rank.  Per MCMC step the
+        ranks exchange the fixed-size block partials behind sigma / mu / stop rule (mcmc.McmcEngine);
+        per temperature step ONE rank-ordered all-gather returns the mutated rows to every rank.
+        Shard boundaries are multiples of the accept kernel's 256-row blocks whenever every rank can
+        get at least one block, which makes the run bit-identical to the single-GPU one (host RNG,
+        mean_mode 0)."""
+        rank, ws = dist.world()
+        n, d = state_dict["x"].shape
+        align = 256 if n // 256 >= ws else 1
+        lo, hi = dist.shard_range(n, rank, ws, align)
+        counts = dist.shard_counts(n, ws, align)
+        lib = _lib.load()
+        blocks = [int(lib.pmc_mh_partials_size(c, d)) // (d + 4) for c in counts]
+        tp = self.sample == "tpcn"
+        tot = state_dict["logl"] + state_dict["logp"] + (0.0 if tp else state_dict["logdetj"])
+        local = {k: (v[lo:hi] if isinstance(v, np.ndarray) else v) for k, v in state_dict.items()}
+        opts = dict(option_dict, shard=(lo, n, blocks), best0=float(np.mean(tot)),
+                    progress_bar=option_dict["progress_bar"] if rank == 0 else None)
+        res = kernel(local, function_dict, opts)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pack = np.concatenate([res["u"], res["x"], res["logdetj"][:, None], res["logl"][:, None], res["logp"][:, None]], axis=1)
+        full = dist.gather_blocks(torch.from_numpy(pack).to(dev), counts).cpu().numpy()
+        out = dict(res)
+        out["u"], out["x"] = np.ascontiguousarray(full[:, :d]), np.ascontiguousarray(full[:, d:2 * d])
+        out["logdetj"], out["logl"], out["logp"] = (np.ascontiguousarray(full[:, 2 * d + i]) for i in range(3))
+        out["calls"] = dist.allreduce_sum_int(res["calls"])
+        if self.have_blobs:
+            parts = [None] * ws
+            torch.distributed.all_gather_object(parts, res["blobs"])
+            out["blobs"] = np.concatenate(parts, axis=0)
+        return out
 
     def _train(self, current_particles):
         """sampler.py:636-678."""

@@ -38,6 +38,13 @@ def _worker(rank, world, port, out):
     ok &= eq.shape == (4, 3) and bool((eq[:2] == 0).all()) and bool((eq[2:] == 1).all())
     s = dist.allreduce_sum_det(torch.tensor([1.0 + rank, 0.1 * (rank + 1)], dtype=torch.float64))
     ok &= bool(torch.equal(s, torch.tensor([1.0, 0.1], dtype=torch.float64) + torch.tensor([2.0, 0.2], dtype=torch.float64)))
+    # rows of mutated particles come back in global order (Sampler._mutate_sharded), call counters add up exactly
+    rows_all = rng.normal(size=(n, 2 * d + 3))
+    cnt = dist.shard_counts(n, world, 256)
+    ok &= sum(cnt) == n and cnt[rank] == b - a
+    back = dist.gather_blocks(torch.from_numpy(rows_all[a:b].copy()), cnt)
+    ok &= np.array_equal(back.numpy(), rows_all)
+    ok &= dist.allreduce_sum_int(10 ** 12 + rank) == 2 * 10 ** 12 + 1
     out[rank] = bool(ok)
     td.destroy_process_group()
 
