@@ -21,7 +21,11 @@ sweep_variant
     ``"ffma"`` (default): the fp32-FMA TMA-stream sweep kernel.  ``"mma"``: experimental warp-MMA
     sweep (mma.sync TF32 with a 3xTF32 split, passes the same parity tests) -- slower on B200 at the
     benchmark sizes (505 us vs 344 us per 10 000-particle inverse) because 16 particles per warp and
-    1.8 KB of activations per particle leave ~1 warp per scheduler.  Read when a flow is constructed.
+    1.8 KB of activations per particle leave ~1 warp per scheduler.  ``"block"``: experimental blocked
+    sweep (csrc/flow_block.cu) for affine flows: the dense part of every degree block on mma.sync
+    (3xTF32), the triangular part hop by hop with register/shuffle hand-over; half the instructions of
+    ``"ffma"`` but 359 us vs 331 us per 10 000-particle inverse (2.25 serial warps per scheduler at
+    68 particles per SM).  Read when a flow is constructed.
 forward_path
     ``"tc"`` (default): ``Flow.forward`` / ``log_prob`` without a graph run on the tcgen05 dense kernel
     (csrc/flow_tc.cu, 3xTF32 split = fp32 fidelity) when the flow is affine with H <= 128 and the batch

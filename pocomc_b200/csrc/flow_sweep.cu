@@ -874,6 +874,12 @@ static int launch_mma(const float* stream, const int* meta, int meta_len, const 
 
 }  // namespace pmc
 
+namespace pmc {
+// csrc/flow_block.cu: blocked sweep (dense part on mma.sync, triangular part as short fp32 dots)
+int launch_block(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in, float* out,
+                 float* ladj, long long n, int inverse, cudaStream_t st);
+}
+
 using namespace pmc;
 
 extern "C" int pmc_flow_pack(const float* raw, const int32_t* gather, float* packed, int64_t n, pmc_stream_t stream) {
@@ -892,6 +898,8 @@ extern "C" int pmc_flow_sweep(const float* packed, const int32_t* meta, const in
   if (n == 0) return 0;
   const int* hm = meta_host;
   PMC_REQUIRE(hm[M_D] >= 2 && hm[M_H] >= 1 && hm[M_L] >= 1 && hm[M_T] >= 1, "pmc_flow_sweep: bad meta header");
+  if (hm[M_VERSION] == 4)
+    return launch_block(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
   if (hm[M_VERSION] == 3) {
     PMC_REQUIRE(hm[M_KIND] == 0 || (hm[M_BINS] == 8 && hm[M_TOTAL] == 23), "pmc_flow_sweep: only bins=8 splines are built");
     if (hm[M_KIND] == 0) return launch_mma<Affine>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));

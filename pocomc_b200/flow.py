@@ -105,9 +105,15 @@ class MaskedAutoregressiveFlow(nn.Module):
         self.raw = nn.Parameter(raw)
         # kernel-side weight layout: the TMA-streamed consumption-order stream when the network fits the
         # stream kernel's shared-memory budget, else the degree-sorted slab layout of the v1 kernel
-        if ML.stream_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind, lay.bins):
+        self._pack_entry = "pmc_flow_pack"
+        if config.sweep_variant == "block" and ML.block_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind):
+            # blocked sweep (csrc/flow_block.cu): dense part of every degree block on the warp tensor path
+            klay = ML.build_block(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+            self.packed_numel = klay.numel
+            self._pack_entry = "pmc_flow_tc_pack"                  # TF32 hi / lo images of the dense weights
+        elif ML.stream_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind, lay.bins):
             klay = ML.build_stream(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins,
-                                   variant=config.sweep_variant)
+                                   variant="mma" if config.sweep_variant == "mma" else "ffma")
             self.packed_numel = klay.numel
         else:
             klay = lay
@@ -165,7 +171,7 @@ class MaskedAutoregressiveFlow(nn.Module):
         if self._packed is None or self._packed_key != key:
             if self._packed is None or self._packed.device != self.raw.device:
                 self._packed = torch.empty(self.packed_numel, dtype=torch.float32, device=self.raw.device)
-            _lib.call("pmc_flow_pack", _lib.ptr(self.raw.detach()), _lib.ptr(self.gather), _lib.ptr(self._packed),
+            _lib.call(self._pack_entry, _lib.ptr(self.raw.detach()), _lib.ptr(self.gather), _lib.ptr(self._packed),
                       self.packed_numel)
             self._packed_key = key
         return self._packed

@@ -236,3 +236,137 @@ def sweep_stream_mma(layout, stream, packed, x, inverse):
                     act[l_][:, gs:ge] = np.maximum(pre, 0)
             assert pos == cnt
     return cur, ladj
+
+
+# ---------------------------------------------------------------------------------------------
+# blocked sweep (csrc/flow_block.cu): interpreter over made_layout.build_block's program
+# ---------------------------------------------------------------------------------------------
+def pack_block(block, raw):
+    """pmc_flow_tc_pack's codes: >= 0 hi(raw[g]) (13 low mantissa bits cleared), -(g+2) lo = raw - hi,
+    g | 2^30 plain copy, -1 zero."""
+    raw = np.asarray(raw, np.float32)
+    g = block.gather.astype(np.int64)
+    out = np.zeros(g.size, np.float32)
+    plain = g >= ML.BLOCK_PLAIN
+    out[plain] = raw[g[plain] - ML.BLOCK_PLAIN]
+    hi_all = (raw.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    hi = (g >= 0) & ~plain
+    out[hi] = hi_all[g[hi]]
+    lo = g <= -2
+    idx = -g[lo] - 2
+    out[lo] = raw[idx] - hi_all[idx]
+    return out
+
+
+def sweep_block(block, packed, x, inverse):
+    """Executes the op program exactly like the kernel's consumer warp (8 particles at a time), with
+    the kernel's array strides and fragment orders; arithmetic in fp32/fp64 numpy."""
+    m = block.meta
+    D, L, T = (int(m[i]) for i in (ML.M_D, ML.M_L, ML.M_T))
+    nops, sx, so = int(m[ML.M_NOPS]), int(m[ML.M_SX]), int(m[ML.M_SO])
+    sh = int(m[ML.M_HPB]) + 4
+    prog = m[m[ML.M_OFF_PROG]:m[ML.M_OFF_PROG] + 8 * nops].reshape(nops, 8)
+    chunks = m[m[ML.M_OFF_CHUNKS]:m[ML.M_OFF_CHUNKS] + 4 * m[ML.M_NCHUNKS]].reshape(-1, 4)
+    lane = np.arange(32)
+    fr, fc = lane >> 2, lane & 3
+    x = np.asarray(x, np.float32)
+    n_all = len(x)
+    out_all = np.zeros_like(x)
+    ladj_all = np.zeros(n_all, np.float32)
+    for row0 in range(0, n_all, 8):
+        rows = min(8, n_all - row0)
+        cur = np.zeros((D, 8), np.float32)
+        cur[:, :rows] = x[row0:row0 + rows].T
+        xs = np.zeros((8, sx), np.float32)
+        act = np.zeros((L, 8, sh), np.float32)
+        ph = np.zeros((8, so), np.float32)
+        arrays = [xs] + [act[l] for l in range(L)] + [ph]
+        ladj = np.zeros(8, np.float32)
+        for tt in range(T):
+            t = T - 1 - tt if inverse else tt
+            ci = -1
+            w, pos = None, 0
+            acc = None
+            onew = np.zeros((8, 2))
+            for op in prog:
+                typ, a, b, c, d, e, _, flags = (int(v) for v in op)
+                if flags & ML.BF_NEWCHUNK:
+                    assert w is None or pos == len(w), (pos, len(w))
+                    ci += 1
+                    off, cnt = int(chunks[ci, 2]), int(chunks[ci, 3])
+                    w = packed[t * block.tstride + off: t * block.tstride + off + cnt]
+                    pos = 0
+                if typ == ML.OP_MMA:
+                    nt = int(op[6])
+                    if flags & ML.BF_FIRST:
+                        acc = w[pos:pos + 128 * nt].reshape(nt, 32, 4).astype(np.float64); pos += 128 * nt
+                    src = arrays[a]
+                    for ks in range(c):
+                        B = src[:, b + 8 * ks: b + 8 * ks + 8].T.astype(np.float64)        # [k][particle]
+                        for tl in range(nt):
+                            ah = w[pos:pos + 128].reshape(32, 4); al = w[pos + 128:pos + 256].reshape(32, 4); pos += 256
+                            A = np.zeros((16, 8), np.float64)
+                            A[fr, fc] = ah[:, 0].astype(np.float64) + al[:, 0]; A[fr + 8, fc] = ah[:, 1].astype(np.float64) + al[:, 1]
+                            A[fr, fc + 4] = ah[:, 2].astype(np.float64) + al[:, 2]; A[fr + 8, fc + 4] = ah[:, 3].astype(np.float64) + al[:, 3]
+                            C = A @ B                                                       # [16 units][8 particles]
+                            acc[tl, :, 0] += C[fr, 2 * fc]; acc[tl, :, 1] += C[fr, 2 * fc + 1]
+                            acc[tl, :, 2] += C[fr + 8, 2 * fc]; acc[tl, :, 3] += C[fr + 8, 2 * fc + 1]
+                    if flags & ML.BF_LAST:
+                        dst = arrays[d]
+                        for tl in range(nt):
+                            r0 = e + 16 * tl
+                            dst[2 * fc, r0 + fr] = acc[tl, :, 0]; dst[2 * fc + 1, r0 + fr] = acc[tl, :, 1]
+                            dst[2 * fc, r0 + fr + 8] = acc[tl, :, 2]; dst[2 * fc + 1, r0 + fr + 8] = acc[tl, :, 3]
+                elif typ == ML.OP_STEP:
+                    k, c_ = a & 0xFFFF, a >> 16
+                    out_old, pbj = b & 0xFFFF, b >> 16
+                    u0, cnt_u = c & 0xFFFF, c >> 16
+                    l0_d0, l0_r = d & 0xFFFF, d >> 16
+                    lh = e
+                    P4 = (cnt_u + 3) // 4 * 4
+
+                    def take(nfl):
+                        nonlocal pos
+                        v = w[pos:pos + nfl].astype(np.float64); pos += nfl
+                        return v
+
+                    def old_dot(src, r0, nrows, slots):
+                        wv = take(nrows * slots).reshape(nrows // 4, slots, 4)
+                        xv = src[:, r0:r0 + nrows].reshape(8, nrows // 4, 4).astype(np.float64)
+                        return np.einsum("pgr,gsr->ps", xv, wv)
+
+                    if flags & ML.BF_BLOCKFIRST:
+                        onew = np.zeros((8, 2))
+                    phi = ph[:, c_:c_ + 2].astype(np.float64) + onew
+                    if out_old:
+                        phi = phi + old_dot(act[L - 1], pbj, out_old, 2)
+                    feat = D - 1 - k if t % 2 else k
+                    v = cur[feat].copy()
+                    res, l = affine(phi.astype(np.float32), v, inverse)
+                    ladj = (ladj - l if inverse else ladj + l).astype(np.float32)
+                    xk = res if inverse else v
+                    xs[:, k] = xk
+                    cur[feat] = res
+                    onew = np.zeros((8, 2))
+                    if cnt_u:
+                        pre = act[0][:, u0:u0 + P4].astype(np.float64)
+                        if l0_r:
+                            pre = pre + old_dot(xs, l0_d0, l0_r, P4)
+                        pre = pre + xk[:, None].astype(np.float64) * take(P4)[None, :]
+                        h = np.maximum(pre, 0).astype(np.float32)
+                        act[0][:, u0:u0 + P4] = h
+                        for l_ in range(1, L):
+                            pre = act[l_][:, u0:u0 + P4].astype(np.float64) + h
+                            if lh:
+                                pre = pre + old_dot(act[l_ - 1], pbj, lh, P4)
+                            pre = pre + h.astype(np.float64) @ take(P4 * P4).reshape(P4, P4).T
+                            h = np.maximum(pre, 0).astype(np.float32)
+                            act[l_][:, u0:u0 + P4] = h
+                        if flags & ML.BF_NEXTOUT:
+                            onew = h.astype(np.float64) @ take(2 * P4).reshape(2, P4).T
+                else:
+                    raise AssertionError(typ)
+            assert pos == len(w) and ci == len(chunks) - 1
+        out_all[row0:row0 + rows] = cur[:, :rows].T
+        ladj_all[row0:row0 + rows] = ladj[:rows]
+    return out_all, ladj_all

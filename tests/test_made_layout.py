@@ -76,3 +76,31 @@ def test_masks_match_oracle():
 def test_one_dim_rejected():
     with pytest.raises(ValueError):
         ML.build_layout(1, 32, 3, 3, ML.KIND_AFFINE)
+
+
+@pytest.mark.parametrize("preset,d", [("maf3", 16), ("maf6", 32), ("maf3", 20), ("maf3", 33), ("maf3", 50)])
+def test_block_program_matches_oracle(preset, d):
+    """The blocked sweep's op program + weight stream (made_layout.build_block), executed by a numpy
+    interpreter that mirrors csrc/flow_block.cu (array strides, MMA fragment orders, hi/lo split),
+    reproduces the zuko oracle's forward and (D+1)-pass inverse."""
+    from sweep_emul import pack_block, sweep_block
+    torch.manual_seed(d)
+    flow = F.make_flow(d, preset)
+    kind, T = F.PRESETS[preset]
+    H = F.hidden_width(d)
+    assert ML.block_supported(d, H, 3, ML.KIND_AFFINE)
+    blk = ML.build_block(d, H, 3, T, ML.KIND_AFFINE)
+    raw = _raw(flow)
+    assert blk.meta[ML.M_VERSION] == 4 and blk.chunks[:, 3].max() == blk.slot_floats <= ML.BLOCK_CHUNK_FLOATS + 2048
+    assert np.all(blk.chunks[:, 2] % 4 == 0) and np.all(blk.chunks[:, 3] % 4 == 0)
+    packed = pack_block(blk, raw)
+    x = (torch.randn(11, d) * 1.3).float()
+    with torch.no_grad():
+        z, ladj = flow().transform.call_and_ladj(x)
+        xi, li = flow().transform.inv.call_and_ladj(z)
+    zs, ls = sweep_block(blk, packed, x.numpy(), inverse=False)
+    np.testing.assert_allclose(zs, z.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(ls, ladj.numpy(), rtol=1e-4, atol=2e-5)
+    xb, lb = sweep_block(blk, packed, z.numpy(), inverse=True)
+    np.testing.assert_allclose(xb, xi.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(lb, li.numpy(), rtol=1e-4, atol=1e-4)
