@@ -66,7 +66,7 @@ class Workload:
         self.bounds = np.array([dd.support() for dd in self.dists])
 
     def loglike(self, x):
-        return -0.5 * np.sum((x @ self.prec) * x, axis=1) + self.c0
+        return -0.5 * np.einsum("ij,ij->i", x @ self.prec, x) + self.c0
 
     def logprior(self, x):
         out = np.zeros(len(x))

@@ -48,18 +48,15 @@ struct TrainParams {
   float* logprob;            // [Bp] per-row log-probability (may be nullptr)
   int Bp, D, Dp, H, L, T, No, tstride, bias_off;
   int weighted, backward;
-  int ns;                    // weight ring depth (2..8 slots of the largest image)
+  int ns;                    // weight ring depth (2..8 slots)
+  int wslot;                 // floats per ring slot: the largest image, or less -- images then stream in k-chunks
 };
 
-// acc[i][j] = sum_k At[k][4 ty + i] * W[k][tx + 32 j]
+// acc[i][j] += sum_k At[k][4 ty + i] * W[k][tx + 32 j]   (k over the rows of one streamed chunk of the image)
 template <int TN>
 __device__ __forceinline__ void gemm_tile(const float* __restrict__ At, int K, const float* __restrict__ W, int ty, int tx,
-                                          float (&acc)[4][4]) {
+                                          float (&acc)[4][8]) {
   constexpr int N = 32 * TN;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const float* a = At + 4 * ty;
   const float* w = W + tx;
 #pragma unroll 4
@@ -77,8 +74,9 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ At, int K, c
     }
   }
 }
-__device__ __forceinline__ void gemm_any(int tn, const float* At, int K, const float* W, int ty, int tx, float (&acc)[4][4]) {
-  if (tn == 4) gemm_tile<4>(At, K, W, ty, tx, acc);
+__device__ __forceinline__ void gemm_any(int tn, const float* At, int K, const float* W, int ty, int tx, float (&acc)[4][8]) {
+  if (tn == 8) gemm_tile<8>(At, K, W, ty, tx, acc);
+  else if (tn == 4) gemm_tile<4>(At, K, W, ty, tx, acc);
   else if (tn == 2) gemm_tile<2>(At, K, W, ty, tx, acc);
   else gemm_tile<1>(At, K, W, ty, tx, acc);
 }
@@ -90,7 +88,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   __shared__ double lossrow[TR_ROWS];
   __shared__ float red[8];
   const int D = p.D, Dp = p.Dp, H = p.H, L = p.L, T = p.T, No = p.No, Bp = p.Bp;
-  const int wmax = max(max((D + 1) * H, (H + 1) * H), max((H + 1) * No, H * Dp));
+  const int wmax = p.wslot;
   const int brows = max(H, No);
   const int NS = p.ns;
   float* wring = reinterpret_cast<float*>(smem_raw);
@@ -98,7 +96,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   float* bufB = bufA + brows * TR_LDA;
   float* xT = bufB + brows * TR_LDA;
   float* gT = xT + Dp * TR_LDA;
-  uint32_t* relu_bits = reinterpret_cast<uint32_t*>(gT + Dp * TR_LDA);   // [T*L][256]: (h > 0) of this thread's 4 x 4 outputs
+  uint32_t* relu_bits = reinterpret_cast<uint32_t*>(gT + Dp * TR_LDA);   // [T*L][256]: (h > 0) of this thread's 4 x 8 outputs
 
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   const int row0 = blockIdx.x * TR_ROWS;
@@ -106,29 +104,67 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   const int fwd_img = T * (L + 1);
   const int bwd_base = (D + 1) * H + (L - 1) * (H + 1) * H + (H + 1) * No;
 
-  auto img = [&](int s, int& off, int& n) {
+  // image s of the step: float offset, K rows of N floats, bias row behind the last weight row (forward images)
+  auto img = [&](int s, int& off, int& K, int& N, int& bias) {
     if (s < fwd_img) {
       const int t = s / (L + 1), l = s - t * (L + 1);
       off = t * p.tstride + (l == 0 ? 0 : (D + 1) * H + (l - 1) * (H + 1) * H);
-      n = (l == 0) ? (D + 1) * H : (l < L ? (H + 1) * H : (H + 1) * No);      // weights [K][N] then bias [N]
+      K = (l == 0) ? D : H; N = (l < L) ? H : No; bias = 1;
     } else {
       const int q = s - fwd_img;
       const int tb = T - 1 - q / (L + 1), j = q % (L + 1);
       off = tb * p.tstride + bwd_base + (j == 0 ? 0 : No * H + (j - 1) * H * H);
-      n = (j == 0) ? No * H : (j < L ? H * H : H * Dp);
+      K = (j == 0) ? No : H; N = (j < L) ? H : Dp; bias = 0;
     }
   };
-  auto issue = [&](int s) {
-    int off, n;
-    img(s, off, n);
-    mbar_expect_tx(full + (s % NS), (uint32_t)n * 4u);
-    bulk_g2s(wring + (size_t)(s % NS) * wmax, p.packed + off, (uint32_t)n * 4u, full + (s % NS));
+  // an image larger than a ring slot streams in chunks of kc rows (the bias rides with the last chunk)
+  auto rows_per_chunk = [&](int K, int N, int bias) { return min(K, (wmax - (bias ? N : 0)) / N); };
+  int pi = 0, pk = 0, pcount = 0;                              // producer cursor (thread 0): image, first row, chunks issued
+  auto issue_next = [&]() {
+    if (pi >= n_img) return;
+    int off, K, N, bias;
+    img(pi, off, K, N, bias);
+    const int kc = rows_per_chunk(K, N, bias);
+    const int rows = min(kc, K - pk);
+    const bool last = pk + rows >= K;
+    const uint32_t bytes = (uint32_t)(rows * N + ((last && bias) ? N : 0)) * 4u;
+    const int slot = pcount % NS;
+    mbar_expect_tx(full + slot, bytes);
+    bulk_g2s(wring + (size_t)slot * wmax, p.packed + off + (size_t)pk * N, bytes, full + slot);
+    ++pcount;
+    if (last) { ++pi; pk = 0; } else pk += rows;
   };
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) mbar_init(full + i, 1);
     mbar_fence_init();
-    for (int i = 0; i < NS && i < n_img; ++i) issue(i);
+    for (int i = 0; i < NS; ++i) issue_next();
   }
+  int s = 0;                                                   // chunks consumed so far (ring position)
+  float acc[4][8];
+  // acc = in[32 rows x K] . image[K x 32 tn], the image arriving chunk by chunk; on return the LAST chunk is still in
+  // its slot (bias at wl[rows_last * N]) and must be released with release() after the epilogue has read it
+  const float* wl = nullptr;
+  int rows_last = 0;
+  auto release = [&]() {
+    __syncthreads();                                           // every thread has read the slot (and, for callers, more)
+    if (tid == 0) { fence_proxy_async(); issue_next(); }
+    ++s;
+  };
+  auto stream_gemm = [&](int tn, const float* in, int K, int N, int bias) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int kc = rows_per_chunk(K, N, bias);
+    for (int k0 = 0; k0 < K; k0 += kc) {
+      const int rows = min(kc, K - k0);
+      mbar_wait(full + (s % NS), (s / NS) & 1);
+      wl = wring + (size_t)(s % NS) * wmax;
+      gemm_any(tn, in + k0 * TR_LDA, rows, wl, ty, tx, acc);
+      rows_last = rows;
+      if (k0 + rows < K) release();
+    }
+  };
 
   // ---- batch rows, loss coefficients c_r (flow.py:305-310) ----
   const long long cur = p.cursor[0];
@@ -158,24 +194,19 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   __syncthreads();
 
   const int tnH = H / 32, tnO = No / 32, tnD = Dp / 32;
-  float acc[4][4];
   float ladj_p[4] = {0.f, 0.f, 0.f, 0.f};
   float znew[4][2];
-  int s = 0;
   // =========================== forward ===========================
   for (int t = 0; t < T; ++t) {
     float* in = xT;
     float* out = bufA;
     for (int l = 0; l < L; ++l) {
-      mbar_wait(full + (s % NS), (s / NS) & 1);
-      const int Kl = (l == 0) ? D : H;
-      const float* wimg = wring + (size_t)(s % NS) * wmax;
-      gemm_any(tnH, in, Kl, wimg, ty, tx, acc);
-      const float* bias = wimg + Kl * H;                      // bias rides behind the weights in the same bulk copy
+      stream_gemm(tnH, in, (l == 0) ? D : H, H, 1);
+      const float* bias = wl + rows_last * H;                 // bias rides behind the last weight rows in the same bulk copy
       float* hs = p.Hs + ((size_t)(t * L + l) * Bp + row0 + 4 * ty) * H;
       uint32_t bits = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         if (j >= tnH) continue;
         const int c = tx + 32 * j;
         const float b = bias[c];
@@ -185,23 +216,19 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
           float v = acc[i][j] + b;
           if (l > 0) v += in[c * TR_LDA + 4 * ty + i];        // residual block
           h[i] = fmaxf(v, 0.f);
-          bits |= (h[i] > 0.f ? 1u : 0u) << (4 * i + j);
+          bits |= (h[i] > 0.f ? 1u : 0u) << (8 * i + j);
           hs[(size_t)i * H + c] = h[i];
         }
         *reinterpret_cast<float4*>(out + c * TR_LDA + 4 * ty) = make_float4(h[0], h[1], h[2], h[3]);
       }
       relu_bits[(t * L + l) * 256 + tid] = bits;
-      __syncthreads();
-      if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
-      ++s;
+      release();
       in = out;
       out = (out == bufA) ? bufB : bufA;
     }
     // output layer + affine map
-    mbar_wait(full + (s % NS), (s / NS) & 1);
-    const float* wimg_o = wring + (size_t)(s % NS) * wmax;
-    gemm_any(tnO, in, H, wimg_o, ty, tx, acc);
-    const float* bo = wimg_o + H * No;
+    stream_gemm(tnO, in, H, No, 1);
+    const float* bo = wl + rows_last * No;
 #pragma unroll
   #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
@@ -221,9 +248,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
         znew[i][jj] = z;
       }
     }
-    __syncthreads();                                           // every thread has read xT and the weight slot
-    if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
-    ++s;
+    release();                                                 // every thread has read xT and the weight slot
 #pragma unroll
   #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
@@ -330,12 +355,11 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float* out = bufB;
     for (int j = 0; j < L; ++j) {                              // images B_o, B_{L-1}, ..., B_1
       const int lh = L - 1 - j;                                // hidden layer whose pre-activation gradient comes out
-      mbar_wait(full + (s % NS), (s / NS) & 1);
-      gemm_any(tnH, in, j == 0 ? No : H, wring + (size_t)(s % NS) * wmax, ty, tx, acc);
+      stream_gemm(tnH, in, j == 0 ? No : H, H, 0);
       const uint32_t bits = relu_bits[(t * L + lh) * 256 + tid];
       float* gh = p.Gh + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
 #pragma unroll
-      for (int jn = 0; jn < 4; ++jn) {
+      for (int jn = 0; jn < 8; ++jn) {
         if (jn >= tnH) continue;
         const int c = tx + 32 * jn;
         float g[4];
@@ -343,19 +367,16 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
         for (int i = 0; i < 4; ++i) {
           float v = acc[i][jn];
           if (j > 0) v += in[c * TR_LDA + 4 * ty + i];         // residual path
-          g[i] = ((bits >> (4 * i + jn)) & 1u) ? v : 0.f;       // ReLU
+          g[i] = ((bits >> (8 * i + jn)) & 1u) ? v : 0.f;       // ReLU
           gh[(size_t)i * H + c] = g[i];
         }
         *reinterpret_cast<float4*>(out + c * TR_LDA + 4 * ty) = make_float4(g[0], g[1], g[2], g[3]);
       }
-      __syncthreads();
-      if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
-      ++s;
+      release();
       float* tmp = in; in = out; out = tmp;
     }
     // image B_0: gradient w.r.t. the transform input through the hyper-network + the direct path
-    mbar_wait(full + (s % NS), (s / NS) & 1);
-    gemm_any(tnD, in, H, wring + (size_t)(s % NS) * wmax, ty, tx, acc);
+    stream_gemm(tnD, in, H, Dp, 0);
 #pragma unroll
   #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
@@ -364,9 +385,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       *reinterpret_cast<float4*>(gT + d * TR_LDA + 4 * ty) =
           make_float4(gxd[0][jj] + acc[0][jj], gxd[1][jj] + acc[1][jj], gxd[2][jj] + acc[2][jj], gxd[3][jj] + acc[3][jj]);
     }
-    __syncthreads();
-    if (tid == 0) { fence_proxy_async(); if (s + NS < n_img) issue(s + NS); }
-    ++s;
+    release();
   }
 }
 
@@ -433,13 +452,22 @@ __global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams
   }
 }
 
-static size_t train_smem(int D, int Dp, int H, int No, int T, int L, int& ns) {
+static size_t train_smem(int D, int Dp, int H, int No, int T, int L, int& ns, int& wslot) {
   const size_t wmax = (size_t)std::max(std::max((D + 1) * H, (H + 1) * H), std::max((H + 1) * No, H * Dp));
   const size_t brows = (size_t)std::max(H, No);
   const size_t act = (2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4 + (size_t)T * L * 256 * 4;
-  // small networks: a deeper ring lets the bulk copies run several layers ahead of the (latency-bound) chain
-  ns = (int)std::min<size_t>(8, std::max<size_t>(2, (200 * 1024 - act) / (wmax * 4)));
-  return (size_t)ns * wmax * 4 + act;
+  const size_t budget = 200 * 1024;
+  if (act + 2 * wmax * 4 <= budget) {
+    // small networks: whole images, and a deeper ring lets the bulk copies run several layers ahead of the chain
+    ns = (int)std::min<size_t>(8, (budget - act) / (wmax * 4));
+    wslot = (int)wmax;
+  } else {
+    // wide networks (H = 256): images stream through 3 slots in k-chunks of whole rows
+    ns = 3;
+    const size_t widest = (size_t)std::max(H, std::max(No, Dp));
+    wslot = (int)(((budget - act) / 3 / 4) / widest * widest);      // a multiple of every row length (H, No, Dp divide widest)
+  }
+  return (size_t)ns * wslot * 4 + act;
 }
 
 }  // namespace pmc
@@ -467,7 +495,7 @@ extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host
   p.Bp = (int)bp; p.D = m[TR_D]; p.Dp = m[TR_DP]; p.H = m[TR_H]; p.L = m[TR_L]; p.T = m[TR_T]; p.No = m[TR_NO];
   p.tstride = m[TR_TSTRIDE]; p.bias_off = m[TR_BIAS_OFF];
   p.weighted = wdata ? 1 : 0; p.backward = backward ? 1 : 0;
-  PMC_REQUIRE((p.H == 32 || p.H == 64 || p.H == 128) && p.Dp % 32 == 0 && p.Dp <= 64 && p.No == 2 * p.Dp && p.D >= 2 && p.D <= p.Dp && p.L >= 1,
+  PMC_REQUIRE((p.H == 32 || p.H == 64 || p.H == 128 || p.H == 256) && p.Dp % 32 == 0 && p.Dp <= 64 && p.No == 2 * p.Dp && p.D >= 2 && p.D <= p.Dp && p.L >= 1,
               "pmc_flow_train_step: unsupported flow shape");
   const size_t bpz = (size_t)bp;
   p.X = scratch;
@@ -476,8 +504,8 @@ extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host
   p.Gh = p.Hs + (size_t)p.T * p.L * bpz * p.H;
   p.Go = p.Gh + (size_t)p.T * p.L * bpz * p.H;
   p.loss_partials = loss_partials; p.logprob = logprob;
-  const size_t smem = train_smem(p.D, p.Dp, p.H, p.No, p.T, p.L, p.ns);
-  PMC_REQUIRE(smem <= 220 * 1024, "pmc_flow_train_step: shared memory budget exceeded");
+  const size_t smem = train_smem(p.D, p.Dp, p.H, p.No, p.T, p.L, p.ns, p.wslot);
+  PMC_REQUIRE(smem <= 220 * 1024 && p.wslot >= 2 * std::max(p.H, p.No), "pmc_flow_train_step: shared memory budget exceeded");
   cudaStream_t st = as_stream(stream);
   PMC_TRY(cudaFuncSetAttribute(flow_train_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   flow_train_fb_kernel<<<(unsigned)(bp / TR_ROWS), 256, smem, st>>>(p);

@@ -503,7 +503,7 @@ class TrainLayout:
 
 
 def train_supported(n_dim: int, n_hidden: int, kind: int) -> bool:
-    return kind == KIND_AFFINE and n_hidden in (32, 64, 128) and 2 <= n_dim <= 64
+    return kind == KIND_AFFINE and n_hidden in (32, 64, 128, 256) and 2 <= n_dim <= 64
 
 
 @lru_cache(maxsize=None)

@@ -27,10 +27,10 @@ elif which == "gauss32":
     truth = -0.5 * (D * np.log(2 * np.pi) + np.linalg.slogdet(cov + 9.0 * np.eye(D))[1])
 else:
     D = 50
-    c, s = 1.5, 0.5
+    c, sg = 1.5, 0.5
     def loglike(x):
-        a = -0.5 * np.sum(((x - c) / s) ** 2, axis=1); b = -0.5 * np.sum(((x + c) / s) ** 2, axis=1)
-        return np.logaddexp(a, b) - np.log(2.0) - D * (np.log(s) + 0.5 * np.log(2 * np.pi))
+        a = -0.5 * np.sum(((x - c) / sg) ** 2, axis=1); b = -0.5 * np.sum(((x + c) / sg) ** 2, axis=1)
+        return np.logaddexp(a, b) - np.log(2.0) - D * (np.log(sg) + 0.5 * np.log(2 * np.pi))
     prior = pc.Prior([uniform(-10.0, 20.0)] * D)
     truth = -D * np.log(20.0)
 

@@ -276,7 +276,8 @@ def test_graph_fit_matches_eager_fit(weighted, annealing):
 
 
 @pytest.mark.parametrize("preset,d,n,weighted", [("maf3", 4, 100, True), ("maf6", 10, 512, False), ("maf6", 32, 300, True),
-                                                 ("maf3", 42, 64, True), ("maf3", 21, 33, False)])
+                                                 ("maf3", 42, 64, True), ("maf3", 21, 33, False),
+                                                 ("maf6", 50, 512, True), ("maf3", 64, 96, False)])     # H = 256: images stream in k-chunks
 def test_fused_training_kernels_match_oracle_gradients(preset, d, n, weighted):
     """csrc/flow_train.cu (fused forward + input-gradient chain, grouped weight-gradient GEMM) against the
     oracle's autograd: loss to 1e-5 relative, every parameter gradient to 1e-4 of the gradient scale."""

@@ -7,7 +7,7 @@ from pocomc_b200 import config
 from pocomc_b200.flow import Flow, _FitEngine, epoch_batches
 
 profile_only = len(sys.argv) > 1 and sys.argv[1] == "profile"
-for d, preset in ((10, "maf6"), (32, "maf6")):
+for d, preset in ((10, "maf6"), (32, "maf6"), (50, "maf6")):
     torch.manual_seed(0)
     x = torch.randn(8192, d, device="cuda")
     w = torch.rand(8192, device="cuda") + 0.1
