@@ -197,6 +197,14 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", torch.cuda.current_device())
+    if world > 1:       # one process per GPU shares the box's host cores: keep each rank's BLAS / torch pools to its share
+        share = max(1, (os.cpu_count() or 1) // world)
+        torch.set_num_threads(share)
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=share)
+        except ImportError:
+            pass
     n_local = N_PER_GPU
     n_global = n_local * world
     wl = Workload(n_local, N_DIM, row_offset=rank * n_local)
@@ -314,7 +322,8 @@ def run_b200(args):
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     achieved_tf = flop / (sweep_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
-                    traffic=None, kernel="made_sweep_stream_kernel<Affine> (flow inverse, degree-ordered sweep)",
+                    traffic=2084608.0,      # bytes per launch: dram read 2.08 MB + write 0 (ncu --set full, profiles/r1c_sweep_v3_ncu.txt)
+                    kernel="made_sweep_stream_kernel<Affine> (flow inverse, degree-ordered sweep)",
                     peak_source="MEASURED_PEAKS.json bf16 burst" if peaks else "fallback 1.59 PFLOP/s",
                     flop_per_launch=flop, avg_launch_ms=sweep_ms,
                     note="fp32 FMA sweep on CUDA cores; 2*nnz(masks) useful FLOP per particle; share of step = "

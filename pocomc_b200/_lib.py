@@ -129,3 +129,17 @@ def call(name: str, *args):
     require_cuda()
     lib = load()
     check(getattr(lib, name)(*args, stream_ptr()), name)
+
+
+def bind(name: str, *args):
+    """Pre-bound call for per-step hot loops: the argument tuple (fixed device pointers, sizes) is converted once;
+    every invocation only looks up the current stream.  Same error behaviour as ``call``."""
+    require_cuda()
+    fn = getattr(load(), name)
+    get_stream, get_dev = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
+
+    def run():
+        code = fn(*args, C.c_void_p(get_stream(get_dev())))
+        if code != 0:
+            check(code, name)
+    return run

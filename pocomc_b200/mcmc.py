@@ -152,6 +152,8 @@ class McmcEngine:
         self.sigma = float(sigma)
         self.accept = 0.0
         self.stop = False
+        self._propose = self._scaler_inverse = self._finalize = None       # pre-bound libpmc_b200 calls (built on first use)
+        self._accept = {}
         self.sc, self._sc_keep, _ = self.scaler._params(True)
         if self.with_bc and self._sc_keep["bc"] is not None:
             self.sc.bc = _lib.ptr(self._sc_keep["bc"])
@@ -175,15 +177,19 @@ class McmcEngine:
                       (d + self.nu) / 2 if self.tp else 0.0, _lib.ptr(self.g), _lib.ptr(self.z), _lib.ptr(self.r), n, d)
 
     def propose(self):
-        n, d = self.n, self.d
-        pos = self.theta if self.use_flow else self.u
-        if self.tp:
-            _lib.call("pmc_tpcn_propose", 1 if self.use_flow else 0, _lib.ptr(pos), _lib.ptr(self.ctl),
-                      _lib.ptr(self.inv_t), _lib.ptr(self.chol_t), self.nu, _lib.ptr(self.g), _lib.ptr(self.z),
-                      _lib.ptr(self.prop64), _lib.ptr(self.prop32), _lib.ptr(self.m_cur), _lib.ptr(self.m_prop), n, d)
-        else:
-            _lib.call("pmc_rwm_propose", 1 if self.use_flow else 0, _lib.ptr(pos), _lib.ptr(self.ctl),
-                      _lib.ptr(self.chol_t), _lib.ptr(self.z), _lib.ptr(self.prop64), _lib.ptr(self.prop32), n, d)
+        if self._propose is None:          # every buffer of the engine is fixed: bind the argument list once
+            n, d = self.n, self.d
+            pos = self.theta if self.use_flow else self.u
+            if self.tp:
+                self._propose = _lib.bind("pmc_tpcn_propose", 1 if self.use_flow else 0, _lib.ptr(pos), _lib.ptr(self.ctl),
+                                          _lib.ptr(self.inv_t), _lib.ptr(self.chol_t), self.nu, _lib.ptr(self.g),
+                                          _lib.ptr(self.z), _lib.ptr(self.prop64), _lib.ptr(self.prop32),
+                                          _lib.ptr(self.m_cur), _lib.ptr(self.m_prop), n, d)
+            else:
+                self._propose = _lib.bind("pmc_rwm_propose", 1 if self.use_flow else 0, _lib.ptr(pos), _lib.ptr(self.ctl),
+                                          _lib.ptr(self.chol_t), _lib.ptr(self.z), _lib.ptr(self.prop64),
+                                          _lib.ptr(self.prop32), n, d)
+        self._propose()
 
     def pull_back(self):
         """theta' -> u' (flow.inverse, mcmc.py:88) -> x', logdetj' (+ boundary conditions, :91-97)."""
@@ -199,8 +205,10 @@ class McmcEngine:
             src, is32 = self.u_p32, 1
         else:
             src, is32 = self.prop64, 0
-        _lib.call("pmc_scaler_inverse", is32, _lib.ptr(src), C.byref(self.sc), _lib.ptr(self.u_p), _lib.ptr(self.x_p),
-                  _lib.ptr(self.ldj_p), _lib.ptr(self.finite), n, d)
+        if self._scaler_inverse is None:
+            self._scaler_inverse = _lib.bind("pmc_scaler_inverse", is32, _lib.ptr(src), C.byref(self.sc), _lib.ptr(self.u_p),
+                                             _lib.ptr(self.x_p), _lib.ptr(self.ldj_p), _lib.ptr(self.finite), n, d)
+        self._scaler_inverse()
 
     def evaluate_host(self):
         """Host black boxes on the finite rows only (mcmc.py:100-121).  When the prior is a
@@ -256,18 +264,25 @@ class McmcEngine:
             ng, lo = (self.n_global, self.row_offset) if self.sharded else (n, 0)
             hn[n + n * d:] = np.random.rand(ng)[lo:lo + n]                       # mcmc.py:137
             self.r.copy_(self.h_noise[n + n * d:], non_blocking=True)
-        _lib.call("pmc_mh_accept_update", self.kind, self.beta, self.nu, _lib.ptr(self.theta), _lib.ptr(self.u),
-                  _lib.ptr(self.x), _lib.ptr(self.logdetj), _lib.ptr(self.logl), _lib.ptr(self.logp), _lib.ptr(self.ldjf),
-                  _lib.ptr(self.prop64), _lib.ptr(self.u_p), _lib.ptr(self.x_p), _lib.ptr(self.ldj_p),
-                  _lib.ptr(self.logl_p), _lib.ptr(self.logp_p), _lib.ptr(self.ldjf_p), _lib.ptr(self.m_cur),
-                  _lib.ptr(self.m_prop), _lib.ptr(self.r), _lib.ptr(self.finite) if calls is None else None,
-                  _lib.ptr(self.alpha), _lib.ptr(self.partials), n, d)
-        parts, n_blocks, n_all = self.partials, 0, n
+        key = calls is None
+        if key not in self._accept:
+            self._accept[key] = _lib.bind(
+                "pmc_mh_accept_update", self.kind, self.beta, self.nu, _lib.ptr(self.theta), _lib.ptr(self.u),
+                _lib.ptr(self.x), _lib.ptr(self.logdetj), _lib.ptr(self.logl), _lib.ptr(self.logp), _lib.ptr(self.ldjf),
+                _lib.ptr(self.prop64), _lib.ptr(self.u_p), _lib.ptr(self.x_p), _lib.ptr(self.ldj_p),
+                _lib.ptr(self.logl_p), _lib.ptr(self.logp_p), _lib.ptr(self.ldjf_p), _lib.ptr(self.m_cur),
+                _lib.ptr(self.m_prop), _lib.ptr(self.r), _lib.ptr(self.finite) if calls is None else None,
+                _lib.ptr(self.alpha), _lib.ptr(self.partials), n, d)
+        self._accept[key]()
         if self.sharded:      # rank-ordered all-gather of the block partials, summed in fixed order by every rank
             parts = dist.gather_blocks(self.partials.view(-1, d + 4), self.shard_blocks)
-            n_blocks, n_all = parts.shape[0], self.n_global
-        _lib.call("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(parts), n_blocks, _lib.ptr(self.theta),
-                  self.mean_mode, self.n_steps, self.n_max, n_all, d)
+            _lib.call("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(parts), parts.shape[0], _lib.ptr(self.theta),
+                      self.mean_mode, self.n_steps, self.n_max, self.n_global, d)
+            return
+        if self._finalize is None:
+            self._finalize = _lib.bind("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(self.partials), 0,
+                                       _lib.ptr(self.theta), self.mean_mode, self.n_steps, self.n_max, n, d)
+        self._finalize()
 
     def read_controller(self):
         self.ctl_host.copy_(self.ctl, non_blocking=True)
