@@ -92,6 +92,15 @@ int pmc_flow_train_step(const float* packed, const int32_t* meta_host, int32_t m
                         const int64_t* cursor, int64_t bp, float* scratch, double* loss_partials,
                         float* logprob, const int32_t* tiles, const int32_t* wmap, float* grad,
                         int32_t backward, pmc_stream_t stream);
+/* Validation pass of one epoch (flow.py:326-342) in ONE launch: the weighted negative log-likelihood of the
+ * n_batches consecutive batches *cursor .. *cursor + n_batches - 1 of the same idx / mask tables, every batch
+ * normalised by its own weight sum like the reference's per-batch loss.  loss_partials receives
+ * n_batches * bp/32 partial sums (batch-major; sum of batch b = sum of its bp/32 entries); logprob (may be NULL)
+ * n_batches * bp per-row log-probabilities.  No scratch: nothing is kept for a backward pass.            */
+int pmc_flow_eval_batches(const float* packed, const int32_t* meta_host, int32_t meta_len,
+                          const float* xdata, const float* wdata, const int64_t* idx, const float* mask,
+                          const int64_t* cursor, int64_t bp, int64_t n_batches, double* loss_partials,
+                          float* logprob, pmc_stream_t stream);
 
 /* ---- MCMC controller state ------------------------------------------------------------------
  * Device-resident f64 block shared by the step kernels so a whole MCMC step is host-sync free:

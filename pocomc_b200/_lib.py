@@ -31,6 +31,7 @@ SIGNATURES = {
     "pmc_adamw_clip_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "pmc_flow_train_scratch_size": (_I64, [_P, _I64]),
     "pmc_flow_train_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "pmc_flow_eval_batches": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
     "pmc_tpcn_propose": (C.c_int, [_I32, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_rwm_propose": (C.c_int, [_I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_scaler_inverse": (C.c_int, [_I32, _P, C.POINTER(PmcScaler), _P, _P, _P, _P, _I64, _I32, _P]),

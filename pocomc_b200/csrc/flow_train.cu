@@ -48,6 +48,7 @@ struct TrainParams {
   float* logprob;            // [Bp] per-row log-probability (may be nullptr)
   int Bp, D, Dp, H, L, T, No, tstride, bias_off;
   int weighted, backward;
+  int cpb;                   // CTAs per batch (Bp / 32): a forward-only launch may cover several consecutive batches
   int ns;                    // weight ring depth (2..8 slots)
   int wslot;                 // floats per ring slot: the largest image, or less -- images then stream in k-chunks
 };
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   uint32_t* relu_bits = reinterpret_cast<uint32_t*>(gT + Dp * TR_LDA);   // [T*L][256]: (h > 0) of this thread's 4 x 8 outputs
 
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
-  const int row0 = blockIdx.x * TR_ROWS;
+  const int row0 = (blockIdx.x % p.cpb) * TR_ROWS;             // row inside the CTA's batch
   const int n_img = (p.backward ? 2 : 1) * T * (L + 1);
   const int fwd_img = T * (L + 1);
   const int bwd_base = (D + 1) * H + (L - 1) * (H + 1) * H + (H + 1) * No;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   };
 
   // ---- batch rows, loss coefficients c_r (flow.py:305-310) ----
-  const long long cur = p.cursor[0];
+  const long long cur = p.cursor[0] + blockIdx.x / p.cpb;
   const long long* bidx = p.idx + cur * Bp;
   const float* bmask = p.mask + cur * Bp;
   float sumw = 1.0f;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     const int r = i / Dp, d = i - r * Dp;
     const float v = (d < D) ? p.xdata[bidx[row0 + r] * D + d] : 0.f;
     xT[d * TR_LDA + r] = v;
-    p.X[((size_t)0 * Bp + row0 + r) * Dp + d] = v;
+    if (p.backward) p.X[((size_t)0 * Bp + row0 + r) * Dp + d] = v;
   }
   __syncthreads();
 
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
           if (l > 0) v += in[c * TR_LDA + 4 * ty + i];        // residual block
           h[i] = fmaxf(v, 0.f);
           bits |= (h[i] > 0.f ? 1u : 0u) << (8 * i + j);
-          hs[(size_t)i * H + c] = h[i];
+          if (p.backward) hs[(size_t)i * H + c] = h[i];
         }
         *reinterpret_cast<float4*>(out + c * TR_LDA + 4 * ty) = make_float4(h[0], h[1], h[2], h[3]);
       }
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
           const float ls = sraw / (1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS);
           z = fmaf(xT[d * TR_LDA + 4 * ty + i], expf(ls), shift);
           ladj_p[i] += ls;
-          p.S[((size_t)t * Bp + row0 + 4 * ty + i) * Dp + d] = sraw;
+          if (p.backward) p.S[((size_t)t * Bp + row0 + 4 * ty + i) * Dp + d] = sraw;
         }
         znew[i][jj] = z;
       }
@@ -256,7 +257,9 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       const int d = tx + 32 * jj;
       *reinterpret_cast<float4*>(xT + d * TR_LDA + 4 * ty) = make_float4(znew[0][jj], znew[1][jj], znew[2][jj], znew[3][jj]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) p.X[((size_t)(t + 1) * Bp + row0 + 4 * ty + i) * Dp + d] = znew[i][jj];
+      if (p.backward)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p.X[((size_t)(t + 1) * Bp + row0 + 4 * ty + i) * Dp + d] = znew[i][jj];
     }
     __syncthreads();
   }
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
         const float lp = -0.5f * ss - (float)D * TR_HALF_LOG_2PI + sl;
         const int r = 4 * ty + i;
         lossrow[r] = (crow[r] != 0.f) ? -(double)crow[r] * (double)lp : 0.0;
-        if (p.logprob) p.logprob[row0 + r] = lp;
+        if (p.logprob) p.logprob[(size_t)(blockIdx.x / p.cpb) * Bp + row0 + r] = lp;
       }
     }
     __syncthreads();
@@ -480,14 +483,10 @@ extern "C" int64_t pmc_flow_train_scratch_size(const int32_t* meta_host, int64_t
   return (T + 1) * bp * Dp + T * bp * Dp + 2 * T * L * bp * H + T * bp * No;
 }
 
-extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host, int32_t meta_len, const float* xdata,
-                                   const float* wdata, const int64_t* idx, const float* mask, const int64_t* cursor, int64_t bp,
-                                   float* scratch, double* loss_partials, float* logprob, const int32_t* tiles,
-                                   const int32_t* wmap, float* grad, int32_t backward, pmc_stream_t stream) {
-  PMC_REQUIRE(packed && meta_host && xdata && idx && mask && cursor && scratch && loss_partials, "pmc_flow_train_step: null pointer");
-  PMC_REQUIRE(meta_len >= TR_LEN && meta_host[TR_VERSION] == 200, "pmc_flow_train_step: not a training layout table");
-  PMC_REQUIRE(bp > 0 && bp % TR_ROWS == 0, "pmc_flow_train_step: padded batch must be a multiple of 32 rows");
-  PMC_REQUIRE(!backward || (tiles && wmap && grad), "pmc_flow_train_step: backward needs tiles, wmap and grad");
+static int train_launch(const float* packed, const int32_t* meta_host, int32_t meta_len, const float* xdata, const float* wdata,
+                        const int64_t* idx, const float* mask, const int64_t* cursor, int64_t bp, int64_t n_batches,
+                        float* scratch, double* loss_partials, float* logprob, const int32_t* tiles, const int32_t* wmap,
+                        float* grad, int32_t backward, pmc_stream_t stream) {
   const int* m = meta_host;
   TrainParams p;
   p.packed = packed; p.xdata = xdata; p.wdata = wdata;
@@ -495,10 +494,11 @@ extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host
   p.Bp = (int)bp; p.D = m[TR_D]; p.Dp = m[TR_DP]; p.H = m[TR_H]; p.L = m[TR_L]; p.T = m[TR_T]; p.No = m[TR_NO];
   p.tstride = m[TR_TSTRIDE]; p.bias_off = m[TR_BIAS_OFF];
   p.weighted = wdata ? 1 : 0; p.backward = backward ? 1 : 0;
+  p.cpb = (int)(bp / TR_ROWS);
   PMC_REQUIRE((p.H == 32 || p.H == 64 || p.H == 128 || p.H == 256) && p.Dp % 32 == 0 && p.Dp <= 64 && p.No == 2 * p.Dp && p.D >= 2 && p.D <= p.Dp && p.L >= 1,
               "pmc_flow_train_step: unsupported flow shape");
   const size_t bpz = (size_t)bp;
-  p.X = scratch;
+  p.X = scratch;                                               // forward-only launches never touch the scratch
   p.S = p.X + (size_t)(p.T + 1) * bpz * p.Dp;
   p.Hs = p.S + (size_t)p.T * bpz * p.Dp;
   p.Gh = p.Hs + (size_t)p.T * p.L * bpz * p.H;
@@ -508,11 +508,34 @@ extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host
   PMC_REQUIRE(smem <= 220 * 1024 && p.wslot >= 2 * std::max(p.H, p.No), "pmc_flow_train_step: shared memory budget exceeded");
   cudaStream_t st = as_stream(stream);
   PMC_TRY(cudaFuncSetAttribute(flow_train_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flow_train_fb_kernel<<<(unsigned)(bp / TR_ROWS), 256, smem, st>>>(p);
+  flow_train_fb_kernel<<<(unsigned)(n_batches * p.cpb), 256, smem, st>>>(p);
   PMC_LAUNCH_CHECK();
   if (backward) {
     flow_train_wgrad_kernel<<<(unsigned)m[TR_NTILES], 256, 0, st>>>(p, tiles, wmap, m[TR_MAP_TSTRIDE], grad);
     PMC_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host, int32_t meta_len, const float* xdata,
+                                   const float* wdata, const int64_t* idx, const float* mask, const int64_t* cursor, int64_t bp,
+                                   float* scratch, double* loss_partials, float* logprob, const int32_t* tiles,
+                                   const int32_t* wmap, float* grad, int32_t backward, pmc_stream_t stream) {
+  PMC_REQUIRE(packed && meta_host && xdata && idx && mask && cursor && scratch && loss_partials, "pmc_flow_train_step: null pointer");
+  PMC_REQUIRE(meta_len >= TR_LEN && meta_host[TR_VERSION] == 200, "pmc_flow_train_step: not a training layout table");
+  PMC_REQUIRE(bp > 0 && bp % TR_ROWS == 0, "pmc_flow_train_step: padded batch must be a multiple of 32 rows");
+  PMC_REQUIRE(!backward || (tiles && wmap && grad), "pmc_flow_train_step: backward needs tiles, wmap and grad");
+  return train_launch(packed, meta_host, meta_len, xdata, wdata, idx, mask, cursor, bp, 1, scratch, loss_partials, logprob, tiles,
+                      wmap, grad, backward, stream);
+}
+
+extern "C" int pmc_flow_eval_batches(const float* packed, const int32_t* meta_host, int32_t meta_len, const float* xdata,
+                                     const float* wdata, const int64_t* idx, const float* mask, const int64_t* cursor, int64_t bp,
+                                     int64_t n_batches, double* loss_partials, float* logprob, pmc_stream_t stream) {
+  PMC_REQUIRE(packed && meta_host && xdata && idx && mask && cursor && loss_partials, "pmc_flow_eval_batches: null pointer");
+  PMC_REQUIRE(meta_len >= TR_LEN && meta_host[TR_VERSION] == 200, "pmc_flow_eval_batches: not a training layout table");
+  PMC_REQUIRE(bp > 0 && bp % TR_ROWS == 0 && n_batches >= 0, "pmc_flow_eval_batches: padded batch must be a multiple of 32 rows");
+  if (n_batches == 0) return 0;
+  return train_launch(packed, meta_host, meta_len, xdata, wdata, idx, mask, cursor, bp, n_batches, nullptr, loss_partials, logprob,
+                      nullptr, nullptr, nullptr, 0, stream);
 }

@@ -417,6 +417,7 @@ class _FitEngine:
             self.tl_packed = torch.empty(tl.numel, dtype=torch.float32, device=dev)
             self.grad = torch.zeros(n, dtype=torch.float32, device=dev)      # masked entries stay 0
             self.fscratch = {}      # Bp -> (scratch floats, loss partials)
+            self.eval_partials = {} # Bp -> loss partials of a whole validation epoch
 
     def load(self, x: torch.Tensor, w):
         """copy the training matrix (already shuffled like flow.py:229-234) into the static buffers"""
@@ -557,13 +558,27 @@ class _FitEngine:
             hi[i, :len(b)] = b + offset
             hm[i, :len(b)] = 1.0
         assert all(len(b) <= nrows for b in batches)
-        g = self.graph(B, weighted, train)
+        g = None if (self.fused and not train) else self.graph(B, weighted, train)
         idx_all[:nb].copy_(hi, non_blocking=True)
         mask_all[:nb].copy_(hm, non_blocking=True)
         _FitEngine._staging_free = torch.cuda.Event()
         _FitEngine._staging_free.record()
         self.cursor.zero_()
         self.acc.zero_()
+        if g is None:
+            # validation pass: the batches are independent, so ONE launch covers the whole epoch (every batch keeps
+            # its own weight normalisation, flow.py:307-310)
+            mod = self.module
+            if B not in self.eval_partials:
+                self.eval_partials[B] = torch.zeros(self.MAX_BATCHES * (B // 32), dtype=torch.float64, device=mod.raw.device)
+            partials = self.eval_partials[B]
+            _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
+            _lib.call("pmc_flow_eval_batches", _lib.ptr(self.tl_packed), self.tl_meta.ctypes.data_as(_lib.C.c_void_p),
+                      int(self.tl_meta.size), _lib.ptr(self.x), _lib.ptr(self.w) if weighted else None, _lib.ptr(idx_all),
+                      _lib.ptr(mask_all), _lib.ptr(self.cursor), B, nb, _lib.ptr(partials), None)
+            self.acc += partials[:nb * (B // 32)].sum()
+            self.launches += 1
+            return self.acc
         for _ in range(nb):
             g.replay()
         self.launches += nb
