@@ -75,6 +75,15 @@ int64_t pmc_adamw_scratch_size(void);
 int pmc_adamw_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                         const double* hyper, int64_t* step, double* scratch, float* gnorm_out,
                         pmc_stream_t stream);
+/* Same update with the per-batch bookkeeping of the training loop (flow.py:301-322) folded in, so that one
+ * optimiser step is four launches: (i) *loss_acc += sum of loss_partials[0..n_loss) in index order and
+ * *cursor += 1 (either may be NULL); (ii) every updated parameter i is also written to image[pos_a[i]] and
+ * image[pos_b[i]] (negative = none) -- the forward and backward weight images of build_train -- which
+ * replaces the pmc_flow_pack pass between steps (image may be NULL).                                    */
+int pmc_adamw_clip_step_ex(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           const double* hyper, int64_t* step, double* scratch, float* gnorm_out,
+                           const double* loss_partials, int32_t n_loss, double* loss_acc, int64_t* cursor,
+                           const int32_t* pos_a, const int32_t* pos_b, float* image, pmc_stream_t stream);
 
 /* ---- fused training step of Flow.fit (flow.py:301-319) for MAF ---------------------------------
  * One mini-batch: weighted negative log-likelihood (flow.py:305-310) and, if `backward`, its gradient

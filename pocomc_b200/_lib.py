@@ -29,6 +29,7 @@ SIGNATURES = {
     "pmc_flow_forward_tc": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I64, _I32, _P]),
     "pmc_adamw_scratch_size": (_I64, []),
     "pmc_adamw_clip_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "pmc_adamw_clip_step_ex": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "pmc_flow_train_scratch_size": (_I64, [_P, _I64]),
     "pmc_flow_train_step": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "pmc_flow_eval_batches": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),

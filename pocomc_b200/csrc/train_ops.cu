@@ -12,8 +12,17 @@ namespace pmc {
 enum { HY_LR = 0, HY_BETA1, HY_BETA2, HY_EPS, HY_WD, HY_CLIP, HY_LEN };   // keep in sync with flow.py
 constexpr int NORM_BLOCKS = 296;                                           // 2 per SM; partials summed in fixed order
 
+// book: optional bookkeeping of the training loop folded into block 0 (saves three tiny launches per optimiser step):
+// loss_acc += sum(loss_partials[0..n_loss)) in index order, cursor += 1
+struct StepBook {
+  const double* loss_partials;
+  int n_loss;
+  double* loss_acc;
+  long long* cursor;
+};
+
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ partials,
-                                                          long long* __restrict__ step) {
+                                                          long long* __restrict__ step, StepBook book) {
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -28,14 +37,24 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restric
     double s = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += ws[i];
     partials[blockIdx.x] = s;
-    if (blockIdx.x == 0) step[0] += 1;        // the AdamW step counter t (read by the update kernel)
+    if (blockIdx.x == 0) {
+      step[0] += 1;                           // the AdamW step counter t (read by the update kernel)
+      if (book.loss_acc) {
+        double l = 0.0;
+        for (int i = 0; i < book.n_loss; ++i) l += book.loss_partials[i];
+        book.loss_acc[0] += l;
+      }
+      if (book.cursor) book.cursor[0] += 1;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, long long n, const double* __restrict__ partials,
                                                          int n_partials, const double* __restrict__ hyper,
-                                                         const long long* __restrict__ step, float* __restrict__ gnorm_out) {
+                                                         const long long* __restrict__ step, float* __restrict__ gnorm_out,
+                                                         const int* __restrict__ pos_a, const int* __restrict__ pos_b,
+                                                         float* __restrict__ image) {
   __shared__ float s_coef;
   if (threadIdx.x == 0) {
     double s = 0.0;
@@ -68,6 +87,11 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, 
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     pi -= step_size * (mi / denom);                              // param.addcdiv_(exp_avg, denom, value=-step_size)
     p[i] = pi; m[i] = mi; v[i] = vi;
+    if (image) {                                                 // keep the kernel-side weight image in step (no separate pack)
+      const int a = pos_a[i], b = pos_b[i];
+      if (a >= 0) image[a] = pi;
+      if (b >= 0) image[b] = pi;
+    }
   }
 }
 
@@ -77,17 +101,35 @@ using namespace pmc;
 
 extern "C" int64_t pmc_adamw_scratch_size(void) { return NORM_BLOCKS; }
 
+static int adamw_launch(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const double* hyper,
+                        int64_t* step, double* scratch, float* gnorm_out, StepBook book, const int* pos_a, const int* pos_b,
+                        float* image, pmc_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  int blocks = (int)std::min<long long>(NORM_BLOCKS, (n + 255) / 256);
+  grad_sqnorm_kernel<<<blocks, 256, 0, st>>>(grad, n, scratch, reinterpret_cast<long long*>(step), book);
+  PMC_LAUNCH_CHECK();
+  const int ublocks = grid_for(n, 256 * 4, 8);
+  adamw_clip_kernel<<<ublocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, scratch, blocks, hyper,
+                                              reinterpret_cast<const long long*>(step), gnorm_out, pos_a, pos_b, image);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int pmc_adamw_clip_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                    const double* hyper, int64_t* step, double* scratch, float* gnorm_out,
                                    pmc_stream_t stream) {
   PMC_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper && step && scratch && n > 0, "pmc_adamw_clip_step: bad arguments");
-  cudaStream_t st = as_stream(stream);
-  int blocks = (int)std::min<long long>(NORM_BLOCKS, (n + 255) / 256);
-  grad_sqnorm_kernel<<<blocks, 256, 0, st>>>(grad, n, scratch, reinterpret_cast<long long*>(step));
-  PMC_LAUNCH_CHECK();
-  const int ublocks = grid_for(n, 256 * 4, 8);
-  adamw_clip_kernel<<<ublocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, scratch, blocks, hyper,
-                                              reinterpret_cast<const long long*>(step), gnorm_out);
-  PMC_LAUNCH_CHECK();
-  return 0;
+  return adamw_launch(param, grad, exp_avg, exp_avg_sq, n, hyper, step, scratch, gnorm_out, StepBook{nullptr, 0, nullptr, nullptr},
+                      nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int pmc_adamw_clip_step_ex(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                      const double* hyper, int64_t* step, double* scratch, float* gnorm_out,
+                                      const double* loss_partials, int32_t n_loss, double* loss_acc, int64_t* cursor,
+                                      const int32_t* pos_a, const int32_t* pos_b, float* image, pmc_stream_t stream) {
+  PMC_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper && step && scratch && n > 0, "pmc_adamw_clip_step_ex: bad arguments");
+  PMC_REQUIRE(!loss_acc || (loss_partials && n_loss >= 0), "pmc_adamw_clip_step_ex: loss accumulation needs the partial sums");
+  PMC_REQUIRE(!image || (pos_a && pos_b), "pmc_adamw_clip_step_ex: the image update needs both position maps");
+  return adamw_launch(param, grad, exp_avg, exp_avg_sq, n, hyper, step, scratch, gnorm_out,
+                      StepBook{loss_partials, n_loss, loss_acc, reinterpret_cast<long long*>(cursor)}, pos_a, pos_b, image, stream);
 }

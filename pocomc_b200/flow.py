@@ -415,6 +415,20 @@ class _FitEngine:
             self.tl_wmap = torch.from_numpy(tl.wmap.copy()).to(dev)
             self.tl_tiles = torch.from_numpy(tl.tiles.copy()).to(dev)
             self.tl_packed = torch.empty(tl.numel, dtype=torch.float32, device=dev)
+            # inverse of the gather map: where parameter i sits in the forward / backward weight images
+            g = tl.gather.astype(np.int64)
+            pos = np.nonzero(g >= 0)[0]
+            order = np.argsort(g[pos], kind="stable")
+            raw_idx, where = g[pos][order], pos[order]
+            first = np.ones(len(raw_idx), bool)
+            first[1:] = raw_idx[1:] != raw_idx[:-1]
+            assert np.bincount(raw_idx, minlength=n).max() <= 2, "a parameter appears in more than two image slots"
+            pos_a = np.full(n, -1, np.int32)
+            pos_b = np.full(n, -1, np.int32)
+            pos_a[raw_idx[first]] = where[first]
+            pos_b[raw_idx[~first]] = where[~first]
+            self.tl_pos_a = torch.from_numpy(pos_a).to(dev)
+            self.tl_pos_b = torch.from_numpy(pos_b).to(dev)
             self.grad = torch.zeros(n, dtype=torch.float32, device=dev)      # masked entries stay 0
             self.fscratch = {}      # Bp -> (scratch floats, loss partials)
             self.eval_partials = {} # Bp -> loss partials of a whole validation epoch
@@ -446,7 +460,8 @@ class _FitEngine:
         return self.tables[B]
 
     def _body_fused(self, B, weighted, train):
-        """pack -> fused forward (+ backward + weight gradients) -> clip + AdamW: 5 launches (+3 bookkeeping)"""
+        """fused forward + backward + weight gradients -> clip + AdamW (+ loss / cursor bookkeeping + image update):
+        four launches per optimiser step"""
         mod = self.module
         idx_all, mask_all = self._tables(B)
         if B not in self.fscratch:
@@ -454,16 +469,22 @@ class _FitEngine:
             self.fscratch[B] = (torch.empty(nfl, dtype=torch.float32, device=mod.raw.device),
                                 torch.zeros(B // 32, dtype=torch.float64, device=mod.raw.device))
         scratch, partials = self.fscratch[B]
-        _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
+        if not train:
+            _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
         _lib.call("pmc_flow_train_step", _lib.ptr(self.tl_packed), self.tl_meta.ctypes.data_as(_lib.C.c_void_p),
                   int(self.tl_meta.size), _lib.ptr(self.x), _lib.ptr(self.w) if weighted else None, _lib.ptr(idx_all),
                   _lib.ptr(mask_all), _lib.ptr(self.cursor), B, _lib.ptr(scratch), _lib.ptr(partials), None,
                   _lib.ptr(self.tl_tiles), _lib.ptr(self.tl_wmap), _lib.ptr(self.grad), 1 if train else 0)
         if train:
-            _lib.call("pmc_adamw_clip_step", _lib.ptr(mod.raw), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
-                      mod.raw.numel(), _lib.ptr(self.hyper), _lib.ptr(self.step), _lib.ptr(self.scratch), _lib.ptr(self.gnorm))
-        self.acc += partials.sum()
-        self.cursor += 1
+            # clip + AdamW, and in the same two launches: loss accumulation, batch cursor, and the updated weights
+            # written straight into the training image (run_epoch packs it once per epoch; no pack between steps)
+            _lib.call("pmc_adamw_clip_step_ex", _lib.ptr(mod.raw), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
+                      mod.raw.numel(), _lib.ptr(self.hyper), _lib.ptr(self.step), _lib.ptr(self.scratch), _lib.ptr(self.gnorm),
+                      _lib.ptr(partials), B // 32, _lib.ptr(self.acc), _lib.ptr(self.cursor),
+                      _lib.ptr(self.tl_pos_a), _lib.ptr(self.tl_pos_b), _lib.ptr(self.tl_packed))
+        else:
+            self.acc += partials.sum()
+            self.cursor += 1
 
     def loss_and_grad(self, rows: torch.Tensor, weighted: bool):
         """(loss, gradient blob) of one batch on the fused kernels, no parameter update (tests / diagnostics)."""
@@ -579,6 +600,8 @@ class _FitEngine:
             self.acc += partials[:nb * (B // 32)].sum()
             self.launches += 1
             return self.acc
+        if self.fused and train:       # the training image follows raw inside the step; bring it up to date once per epoch
+            _lib.call("pmc_flow_pack", _lib.ptr(self.module.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
         for _ in range(nb):
             g.replay()
         self.launches += nb
