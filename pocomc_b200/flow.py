@@ -532,8 +532,10 @@ class _FitEngine:
             self.acc += loss.detach().double()
             self.cursor += 1
 
-    def graph(self, B, weighted, train=True):
-        key = (B, bool(weighted), bool(train))
+    STEPS_PER_GRAPH = 8     # consecutive optimiser steps captured in one graph (the batch cursor lives on the device)
+
+    def graph(self, B, weighted, train=True, steps=1):
+        key = (B, bool(weighted), bool(train), int(steps))
         if key not in self.graphs:
             self._tables(B)
             cur = torch.cuda.current_stream()
@@ -550,10 +552,11 @@ class _FitEngine:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                if self.fused:
-                    self._body_fused(B, weighted, train)
-                else:
-                    self._body(B, weighted, optimise=True)
+                for _ in range(int(steps)):
+                    if self.fused:
+                        self._body_fused(B, weighted, train)
+                    else:
+                        self._body(B, weighted, optimise=True)
             self.graphs[key] = g
         return self.graphs[key]
 
@@ -602,7 +605,14 @@ class _FitEngine:
             return self.acc
         if self.fused and train:       # the training image follows raw inside the step; bring it up to date once per epoch
             _lib.call("pmc_flow_pack", _lib.ptr(self.module.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
-        for _ in range(nb):
+        k = self.STEPS_PER_GRAPH if self.fused else 1
+        if nb >= k > 1:
+            gk = self.graph(B, weighted, train, steps=k)
+            for _ in range(nb // k):
+                gk.replay()
+        else:
+            k = nb + 1
+        for _ in range(nb % k):
             g.replay()
         self.launches += nb
         if train:
