@@ -93,7 +93,8 @@ int pmc_adamw_clip_step_ex(float* param, const float* grad, float* exp_avg, floa
  * table); `meta_host`, HOST table of the same layout; `tiles` / `wmap` device copies of its tile list and
  * gradient scatter maps.  Batch b = *cursor takes rows idx[b*bp .. b*bp+bp) of the training matrix
  * xdata [rows, D] (wdata [rows] sample weights or NULL), mask = 0 marks padding rows; bp % 32 == 0.
- * loss_partials receives bp/32 partial sums (loss = their sum, in index order); logprob (may be NULL)
+ * loss_partials receives bp/8 partial sums, one per 8 consecutive rows whatever tile the kernel picks
+ * (8, 16 or 32 rows per CTA); loss = their sum, in index order; logprob (may be NULL)
  * the per-row log-probability.  scratch: pmc_flow_train_scratch_size(meta_host, bp) floats.          */
 int64_t pmc_flow_train_scratch_size(const int32_t* meta_host, int64_t bp);
 int pmc_flow_train_step(const float* packed, const int32_t* meta_host, int32_t meta_len,
@@ -104,7 +105,7 @@ int pmc_flow_train_step(const float* packed, const int32_t* meta_host, int32_t m
 /* Validation pass of one epoch (flow.py:326-342) in ONE launch: the weighted negative log-likelihood of the
  * n_batches consecutive batches *cursor .. *cursor + n_batches - 1 of the same idx / mask tables, every batch
  * normalised by its own weight sum like the reference's per-batch loss.  loss_partials receives
- * n_batches * bp/32 partial sums (batch-major; sum of batch b = sum of its bp/32 entries); logprob (may be NULL)
+ * n_batches * bp/8 partial sums (batch-major; sum of batch b = sum of its bp/8 entries); logprob (may be NULL)
  * n_batches * bp per-row log-probabilities.  No scratch: nothing is kept for a backward pass.            */
 int pmc_flow_eval_batches(const float* packed, const int32_t* meta_host, int32_t meta_len,
                           const float* xdata, const float* wdata, const int64_t* idx, const float* mask,

@@ -27,8 +27,8 @@ using namespace tc;
 
 enum { TR_D = 0, TR_DP, TR_H, TR_L, TR_T, TR_NO, TR_TSTRIDE, TR_BIAS_OFF, TR_RAW_TSTRIDE, TR_MAP_TSTRIDE, TR_NTILES, TR_VERSION, TR_LEN };
 
-constexpr int TR_ROWS = 32;       // batch rows per CTA
-constexpr int TR_LDA = 36;        // row stride of the transposed activation buffers (floats)
+constexpr int TR_PAD = 32;        // the padded batch is a multiple of this many rows
+constexpr int TR_PART = 8;        // rows per loss partial (the finest CTA tile)
 constexpr float TR_LOG_SLOPE_ABS = 6.90775527898213705205f;   // |log(1e-3)|, zuko MonotonicAffineTransform
 constexpr float TR_HALF_LOG_2PI = 0.91893853320467274178f;
 
@@ -48,24 +48,23 @@ struct TrainParams {
   float* logprob;            // [Bp] per-row log-probability (may be nullptr)
   int Bp, D, Dp, H, L, T, No, tstride, bias_off;
   int weighted, backward;
-  int cpb;                   // CTAs per batch (Bp / 32): a forward-only launch may cover several consecutive batches
+  int cpb;                   // CTAs per batch (Bp / ROWS): a forward-only launch may cover several consecutive batches
   int ns;                    // weight ring depth (2..8 slots)
   int wslot;                 // floats per ring slot: the largest image, or less -- images then stream in k-chunks
 };
 
-// acc[i][j] += sum_k At[k][4 ty + i] * W[k][tx + 32 j]   (k over the rows of one streamed chunk of the image)
-template <int TN>
-__device__ __forceinline__ void gemm_tile(const float* __restrict__ At, int K, const float* __restrict__ W, int ty, int tx,
+// acc[i][j] += sum_k At[k][4 rg + i] * W[k][c0 + CSTR j]   (k over the rows of one streamed chunk of the image, N floats per row)
+template <int TN, int CSTR, int LDA>
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ At, int K, const float* __restrict__ W, int N, int rg, int c0,
                                           float (&acc)[4][8]) {
-  constexpr int N = 32 * TN;
-  const float* a = At + 4 * ty;
-  const float* w = W + tx;
+  const float* a = At + 4 * rg;
+  const float* w = W + c0;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    const float4 av = *reinterpret_cast<const float4*>(a + k * TR_LDA);
+    const float4 av = *reinterpret_cast<const float4*>(a);
     float wv[TN];
 #pragma unroll
-    for (int j = 0; j < TN; ++j) wv[j] = w[k * N + 32 * j];
+    for (int j = 0; j < TN; ++j) wv[j] = w[CSTR * j];
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       acc[0][j] = fmaf(av.x, wv[j], acc[0][j]);
@@ -73,16 +72,26 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ At, int K, c
       acc[2][j] = fmaf(av.z, wv[j], acc[2][j]);
       acc[3][j] = fmaf(av.w, wv[j], acc[3][j]);
     }
+    a += LDA;
+    w += N;
   }
 }
-__device__ __forceinline__ void gemm_any(int tn, const float* At, int K, const float* W, int ty, int tx, float (&acc)[4][8]) {
-  if (tn == 8) gemm_tile<8>(At, K, W, ty, tx, acc);
-  else if (tn == 4) gemm_tile<4>(At, K, W, ty, tx, acc);
-  else if (tn == 2) gemm_tile<2>(At, K, W, ty, tx, acc);
-  else gemm_tile<1>(At, K, W, ty, tx, acc);
+template <int CSTR, int LDA>
+__device__ __forceinline__ void gemm_any(int tn, const float* At, int K, const float* W, int N, int rg, int c0, float (&acc)[4][8]) {
+  if (tn == 8) gemm_tile<8, CSTR, LDA>(At, K, W, N, rg, c0, acc);
+  else if (tn == 4) gemm_tile<4, CSTR, LDA>(At, K, W, N, rg, c0, acc);
+  else if (tn == 2) gemm_tile<2, CSTR, LDA>(At, K, W, N, rg, c0, acc);
+  else gemm_tile<1, CSTR, LDA>(At, K, W, N, rg, c0, acc);
 }
 
+// ROWS batch rows per CTA.  The 8 warps form RG = ROWS/4 row groups (4 rows each, one broadcast LDS.128 per k) times
+// CG = 8/RG column groups: a hidden layer's H output columns are dealt to the column groups in 32-wide tiles (tile index
+// cg + CG j), so a smaller ROWS spreads one batch over more SMs at the same work per FFMA.  The two narrow GEMMs of a
+// transform (output layer, N = 2 Dp; input gradient, N = Dp) keep shift and scale of a feature in one thread and run on
+// the cg == 0 warps only.
+template <int ROWS>
 __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams p) {
+  constexpr int TR_ROWS = ROWS, TR_LDA = ROWS + 4, RG = ROWS / 4, CG = 8 / RG, CSW = 32 * CG;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full[8];
   __shared__ float crow[TR_ROWS];
@@ -99,7 +108,10 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   float* gT = xT + Dp * TR_LDA;
   uint32_t* relu_bits = reinterpret_cast<uint32_t*>(gT + Dp * TR_LDA);   // [T*L][256]: (h > 0) of this thread's 4 x 8 outputs
 
-  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, tx = tid & 31;
+  const int ty = warp % RG, cg = warp / RG;                     // row group (rows 4 ty .. 4 ty + 3), column group
+  const int cw0 = tx + 32 * cg;                                // first column of this thread in a hidden-width GEMM
+  const bool lead = (cg == 0);                                 // warps that run the narrow GEMMs and the affine maps
   const int row0 = (blockIdx.x % p.cpb) * TR_ROWS;             // row inside the CTA's batch
   const int n_img = (p.backward ? 2 : 1) * T * (L + 1);
   const int fwd_img = T * (L + 1);
@@ -151,17 +163,23 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     if (tid == 0) { fence_proxy_async(); issue_next(); }
     ++s;
   };
-  auto stream_gemm = [&](int tn, const float* in, int K, int N, int bias) {
+  // wide: N = H, every warp, columns cw0 + CSW j;  narrow: cg == 0 warps only, columns tx + 32 j.  Idle warps keep the
+  // ring position in step (same release() calls) without touching the slot.
+  auto stream_gemm = [&](bool wide, int tn, const float* in, int K, int N, int bias) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     const int kc = rows_per_chunk(K, N, bias);
+    const bool work = wide || lead;
     for (int k0 = 0; k0 < K; k0 += kc) {
       const int rows = min(kc, K - k0);
-      mbar_wait(full + (s % NS), (s / NS) & 1);
-      wl = wring + (size_t)(s % NS) * wmax;
-      gemm_any(tn, in + k0 * TR_LDA, rows, wl, ty, tx, acc);
+      if (work) {
+        mbar_wait(full + (s % NS), (s / NS) & 1);
+        wl = wring + (size_t)(s % NS) * wmax;
+        if (wide) gemm_any<CSW, TR_LDA>(tn, in + k0 * TR_LDA, rows, wl, N, ty, cw0, acc);
+        else gemm_any<32, TR_LDA>(tn, in + k0 * TR_LDA, rows, wl, N, ty, tx, acc);
+      }
       rows_last = rows;
       if (k0 + rows < K) release();
     }
@@ -176,7 +194,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float s = 0.f;
     for (int r = tid; r < Bp; r += 256) s += p.wdata[bidx[r]] * bmask[r];
     s = warp_sum(s);
-    if (tx == 0) red[ty] = s;
+    if (tx == 0) red[warp] = s;
     __syncthreads();
     sumw = 0.f;
     for (int i = 0; i < 8; ++i) sumw += red[i];
@@ -195,21 +213,22 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   __syncthreads();
 
   const int tnH = H / 32, tnO = No / 32, tnD = Dp / 32;
+  const int tnW = tnH / CG;                                    // 32-wide column tiles of a hidden layer per thread
   float ladj_p[4] = {0.f, 0.f, 0.f, 0.f};
-  float znew[4][2];
+  float znew[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   // =========================== forward ===========================
   for (int t = 0; t < T; ++t) {
     float* in = xT;
     float* out = bufA;
     for (int l = 0; l < L; ++l) {
-      stream_gemm(tnH, in, (l == 0) ? D : H, H, 1);
+      stream_gemm(true, tnW, in, (l == 0) ? D : H, H, 1);
       const float* bias = wl + rows_last * H;                 // bias rides behind the last weight rows in the same bulk copy
       float* hs = p.Hs + ((size_t)(t * L + l) * Bp + row0 + 4 * ty) * H;
       uint32_t bits = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (j >= tnH) continue;
-        const int c = tx + 32 * j;
+        if (j >= tnW) continue;
+        const int c = cw0 + CSW * j;
         const float b = bias[c];
         float h[4];
 #pragma unroll
@@ -227,49 +246,48 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       in = out;
       out = (out == bufA) ? bufB : bufA;
     }
-    // output layer + affine map
-    stream_gemm(tnO, in, H, No, 1);
-    const float* bo = wl + rows_last * No;
+    // output layer + affine map (lead warps)
+    stream_gemm(false, tnO, in, H, No, 1);
+    if (lead) {
+      const float* bo = wl + rows_last * No;
 #pragma unroll
-  #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-      if (jj >= tnD) continue;
-      const int d = tx + 32 * jj;
-      const float bs = bo[d], br = bo[Dp + d];
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj >= tnD) continue;
+        const int d = tx + 32 * jj;
+        const float bs = bo[d], br = bo[Dp + d];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float z = 0.f;
-        if (d < D) {
-          const float shift = acc[i][jj] + bs, sraw = ((tnD == 1) ? acc[i][jj + 1] : acc[i][(jj + 2) & 3]) + br;
-          const float ls = sraw / (1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS);
-          z = fmaf(xT[d * TR_LDA + 4 * ty + i], expf(ls), shift);
-          ladj_p[i] += ls;
-          if (p.backward) p.S[((size_t)t * Bp + row0 + 4 * ty + i) * Dp + d] = sraw;
+        for (int i = 0; i < 4; ++i) {
+          float z = 0.f;
+          if (d < D) {
+            const float shift = acc[i][jj] + bs, sraw = ((tnD == 1) ? acc[i][jj + 1] : acc[i][(jj + 2) & 3]) + br;
+            const float ls = sraw / (1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS);
+            z = fmaf(xT[d * TR_LDA + 4 * ty + i], expf(ls), shift);
+            ladj_p[i] += ls;
+            if (p.backward) p.S[((size_t)t * Bp + row0 + 4 * ty + i) * Dp + d] = sraw;
+          }
+          znew[i][jj] = z;
         }
-        znew[i][jj] = z;
       }
     }
     release();                                                 // every thread has read xT and the weight slot
+    if (lead) {
 #pragma unroll
-  #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-      if (jj >= tnD) continue;
-      const int d = tx + 32 * jj;
-      *reinterpret_cast<float4*>(xT + d * TR_LDA + 4 * ty) = make_float4(znew[0][jj], znew[1][jj], znew[2][jj], znew[3][jj]);
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj >= tnD) continue;
+        const int d = tx + 32 * jj;
+        *reinterpret_cast<float4*>(xT + d * TR_LDA + 4 * ty) = make_float4(znew[0][jj], znew[1][jj], znew[2][jj], znew[3][jj]);
+        if (p.backward)
 #pragma unroll
-      if (p.backward)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) p.X[((size_t)(t + 1) * Bp + row0 + 4 * ty + i) * Dp + d] = znew[i][jj];
+          for (int i = 0; i < 4; ++i) p.X[((size_t)(t + 1) * Bp + row0 + 4 * ty + i) * Dp + d] = znew[i][jj];
+      }
     }
     __syncthreads();
   }
-  // ---- log-probability and loss ----
-  {
+  // ---- log-probability and loss: one partial sum per TR_PART rows, in row order ----
+  if (lead) {
     float sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-#pragma unroll
-  #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
+    for (int jj = 0; jj < 2; ++jj) {
       if (jj >= tnD) continue;
 #pragma unroll
       for (int i = 0; i < 4; ++i) sq[i] = fmaf(znew[i][jj], znew[i][jj], sq[i]);
@@ -284,28 +302,31 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
         if (p.logprob) p.logprob[(size_t)(blockIdx.x / p.cpb) * Bp + row0 + r] = lp;
       }
     }
-    __syncthreads();
-    if (tid == 0) {
-      double sum = 0.0;
-      for (int r = 0; r < TR_ROWS; ++r) sum += lossrow[r];
-      p.loss_partials[blockIdx.x] = sum;
-    }
+  }
+  __syncthreads();
+  if (tid < TR_ROWS / TR_PART) {
+    double sum = 0.0;
+    for (int r = 0; r < TR_PART; ++r) sum += lossrow[tid * TR_PART + r];
+    p.loss_partials[(size_t)blockIdx.x * (TR_ROWS / TR_PART) + tid] = sum;
   }
   if (!p.backward) return;
   // =========================== backward ===========================
   // d loss / d z_T = c_r z ; d loss / d ladj = -c_r
+  if (lead) {
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
+    for (int jj = 0; jj < 2; ++jj) {
       if (jj >= tnD) continue;
-    const int d = tx + 32 * jj;
+      const int d = tx + 32 * jj;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) gT[d * TR_LDA + 4 * ty + i] = crow[4 * ty + i] * znew[i][jj];
+      for (int i = 0; i < 4; ++i) gT[d * TR_LDA + 4 * ty + i] = crow[4 * ty + i] * znew[i][jj];
+    }
   }
   __syncthreads();
   // transform inputs / raw log-scales of the affine backward are prefetched one transform ahead so the
   // global-memory latency never sits on the layer chain
   float xn[4][2], sn[4][2];
   auto prefetch_xs = [&](int t) {
+    if (!lead) return;
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       if (jj >= tnD) continue;
@@ -318,39 +339,44 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       }
     }
   };
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { xn[i][jj] = 0.f; sn[i][jj] = 0.f; }
   prefetch_xs(T - 1);
   for (int t = T - 1; t >= 0; --t) {
     float gxd[4][2], xc[4][2], sc[4][2];
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { xc[i][jj] = xn[i][jj]; sc[i][jj] = sn[i][jj]; }
+      for (int i = 0; i < 4; ++i) { xc[i][jj] = xn[i][jj]; sc[i][jj] = sn[i][jj]; gxd[i][jj] = 0.f; }
     if (t > 0) prefetch_xs(t - 1);
     // affine map backward -> gradient of the output layer (shift | scale_raw) as the next GEMM's input
+    if (lead) {
 #pragma unroll
-  #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-      if (jj >= tnD) continue;
-      const int d = tx + 32 * jj;
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj >= tnD) continue;
+        const int d = tx + 32 * jj;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = 4 * ty + i;
-        float gshift = 0.f, gsraw = 0.f, gx = 0.f;
-        if (d < D) {
-          const float gz = gT[d * TR_LDA + r];
-          const float x = xc[i][jj], sraw = sc[i][jj];
-          const float den = 1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS;
-          const float e = expf(sraw / den);
-          gshift = gz;
-          gsraw = (gz * x * e - crow[r]) / (den * den);
-          gx = gz * e;
+        for (int i = 0; i < 4; ++i) {
+          const int r = 4 * ty + i;
+          float gshift = 0.f, gsraw = 0.f, gx = 0.f;
+          if (d < D) {
+            const float gz = gT[d * TR_LDA + r];
+            const float x = xc[i][jj], sraw = sc[i][jj];
+            const float den = 1.0f + fabsf(sraw) / TR_LOG_SLOPE_ABS;
+            const float e = expf(sraw / den);
+            gshift = gz;
+            gsraw = (gz * x * e - crow[r]) / (den * den);
+            gx = gz * e;
+          }
+          gxd[i][jj] = gx;
+          bufA[d * TR_LDA + r] = gshift;
+          bufA[(Dp + d) * TR_LDA + r] = gsraw;
+          float* go = p.Go + ((size_t)t * Bp + row0 + r) * No;
+          go[d] = gshift;
+          go[Dp + d] = gsraw;
         }
-        gxd[i][jj] = gx;
-        bufA[d * TR_LDA + r] = gshift;
-        bufA[(Dp + d) * TR_LDA + r] = gsraw;
-        float* go = p.Go + ((size_t)t * Bp + row0 + r) * No;
-        go[d] = gshift;
-        go[Dp + d] = gsraw;
       }
     }
     __syncthreads();
@@ -358,13 +384,13 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float* out = bufB;
     for (int j = 0; j < L; ++j) {                              // images B_o, B_{L-1}, ..., B_1
       const int lh = L - 1 - j;                                // hidden layer whose pre-activation gradient comes out
-      stream_gemm(tnH, in, j == 0 ? No : H, H, 0);
+      stream_gemm(true, tnW, in, j == 0 ? No : H, H, 0);
       const uint32_t bits = relu_bits[(t * L + lh) * 256 + tid];
       float* gh = p.Gh + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
 #pragma unroll
       for (int jn = 0; jn < 8; ++jn) {
-        if (jn >= tnH) continue;
-        const int c = tx + 32 * jn;
+        if (jn >= tnW) continue;
+        const int c = cw0 + CSW * jn;
         float g[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -378,15 +404,16 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       release();
       float* tmp = in; in = out; out = tmp;
     }
-    // image B_0: gradient w.r.t. the transform input through the hyper-network + the direct path
-    stream_gemm(tnD, in, H, Dp, 0);
+    // image B_0: gradient w.r.t. the transform input through the hyper-network + the direct path (lead warps)
+    stream_gemm(false, tnD, in, H, Dp, 0);
+    if (lead) {
 #pragma unroll
-  #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-      if (jj >= tnD) continue;
-      const int d = tx + 32 * jj;
-      *reinterpret_cast<float4*>(gT + d * TR_LDA + 4 * ty) =
-          make_float4(gxd[0][jj] + acc[0][jj], gxd[1][jj] + acc[1][jj], gxd[2][jj] + acc[2][jj], gxd[3][jj] + acc[3][jj]);
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj >= tnD) continue;
+        const int d = tx + 32 * jj;
+        *reinterpret_cast<float4*>(gT + d * TR_LDA + 4 * ty) =
+            make_float4(gxd[0][jj] + acc[0][jj], gxd[1][jj] + acc[1][jj], gxd[2][jj] + acc[2][jj], gxd[3][jj] + acc[3][jj]);
+      }
     }
     release();
   }
@@ -455,7 +482,8 @@ __global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams
   }
 }
 
-static size_t train_smem(int D, int Dp, int H, int No, int T, int L, int& ns, int& wslot) {
+static size_t train_smem(int rows, int D, int Dp, int H, int No, int T, int L, int& ns, int& wslot) {
+  const size_t TR_LDA = (size_t)rows + 4;
   const size_t wmax = (size_t)std::max(std::max((D + 1) * H, (H + 1) * H), std::max((H + 1) * No, H * Dp));
   const size_t brows = (size_t)std::max(H, No);
   const size_t act = (2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4 + (size_t)T * L * 256 * 4;
@@ -494,9 +522,18 @@ static int train_launch(const float* packed, const int32_t* meta_host, int32_t m
   p.Bp = (int)bp; p.D = m[TR_D]; p.Dp = m[TR_DP]; p.H = m[TR_H]; p.L = m[TR_L]; p.T = m[TR_T]; p.No = m[TR_NO];
   p.tstride = m[TR_TSTRIDE]; p.bias_off = m[TR_BIAS_OFF];
   p.weighted = wdata ? 1 : 0; p.backward = backward ? 1 : 0;
-  p.cpb = (int)(bp / TR_ROWS);
   PMC_REQUIRE((p.H == 32 || p.H == 64 || p.H == 128 || p.H == 256) && p.Dp % 32 == 0 && p.Dp <= 64 && p.No == 2 * p.Dp && p.D >= 2 && p.D <= p.Dp && p.L >= 1,
               "pmc_flow_train_step: unsupported flow shape");
+  // Rows per CTA.  An optimiser step is ONE batch (<= 512 rows = 16 tiles of 32 rows on 148 SMs) and a chain of
+  // T (L+1) dependent layers, so the smallest tile the hidden width can be dealt over (H/32 >= column groups) wins;
+  // a validation pass over many batches already fills the machine and keeps 32-row tiles (4x less weight traffic).
+  int rows = (p.H >= 128) ? 8 : (p.H == 64) ? 16 : 32;
+  if (!backward && n_batches * (bp / 32) >= sm_count()) rows = 32;
+  if (const char* e = getenv("PMC_TRAIN_ROWS")) {              // tuning override
+    const int r = atoi(e);
+    if ((r == 8 || r == 16 || r == 32) && (p.H / 32) % (32 / r) == 0) rows = r;
+  }
+  p.cpb = (int)(bp / rows);
   const size_t bpz = (size_t)bp;
   p.X = scratch;                                               // forward-only launches never touch the scratch
   p.S = p.X + (size_t)(p.T + 1) * bpz * p.Dp;
@@ -504,11 +541,17 @@ static int train_launch(const float* packed, const int32_t* meta_host, int32_t m
   p.Gh = p.Hs + (size_t)p.T * p.L * bpz * p.H;
   p.Go = p.Gh + (size_t)p.T * p.L * bpz * p.H;
   p.loss_partials = loss_partials; p.logprob = logprob;
-  const size_t smem = train_smem(p.D, p.Dp, p.H, p.No, p.T, p.L, p.ns, p.wslot);
+  const size_t smem = train_smem(rows, p.D, p.Dp, p.H, p.No, p.T, p.L, p.ns, p.wslot);
   PMC_REQUIRE(smem <= 220 * 1024 && p.wslot >= 2 * std::max(p.H, p.No), "pmc_flow_train_step: shared memory budget exceeded");
   cudaStream_t st = as_stream(stream);
-  PMC_TRY(cudaFuncSetAttribute(flow_train_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flow_train_fb_kernel<<<(unsigned)(n_batches * p.cpb), 256, smem, st>>>(p);
+  const unsigned grid = (unsigned)(n_batches * p.cpb);
+#define PMC_TRAIN_CASE(R)                                                                                           \
+  if (rows == R) {                                                                                                  \
+    PMC_TRY(cudaFuncSetAttribute(flow_train_fb_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    flow_train_fb_kernel<R><<<grid, 256, smem, st>>>(p);                                                            \
+  }
+  PMC_TRAIN_CASE(8) PMC_TRAIN_CASE(16) PMC_TRAIN_CASE(32)
+#undef PMC_TRAIN_CASE
   PMC_LAUNCH_CHECK();
   if (backward) {
     flow_train_wgrad_kernel<<<(unsigned)m[TR_NTILES], 256, 0, st>>>(p, tiles, wmap, m[TR_MAP_TSTRIDE], grad);
@@ -523,7 +566,7 @@ extern "C" int pmc_flow_train_step(const float* packed, const int32_t* meta_host
                                    const int32_t* wmap, float* grad, int32_t backward, pmc_stream_t stream) {
   PMC_REQUIRE(packed && meta_host && xdata && idx && mask && cursor && scratch && loss_partials, "pmc_flow_train_step: null pointer");
   PMC_REQUIRE(meta_len >= TR_LEN && meta_host[TR_VERSION] == 200, "pmc_flow_train_step: not a training layout table");
-  PMC_REQUIRE(bp > 0 && bp % TR_ROWS == 0, "pmc_flow_train_step: padded batch must be a multiple of 32 rows");
+  PMC_REQUIRE(bp > 0 && bp % TR_PAD == 0, "pmc_flow_train_step: padded batch must be a multiple of 32 rows");
   PMC_REQUIRE(!backward || (tiles && wmap && grad), "pmc_flow_train_step: backward needs tiles, wmap and grad");
   return train_launch(packed, meta_host, meta_len, xdata, wdata, idx, mask, cursor, bp, 1, scratch, loss_partials, logprob, tiles,
                       wmap, grad, backward, stream);
@@ -534,7 +577,7 @@ extern "C" int pmc_flow_eval_batches(const float* packed, const int32_t* meta_ho
                                      int64_t n_batches, double* loss_partials, float* logprob, pmc_stream_t stream) {
   PMC_REQUIRE(packed && meta_host && xdata && idx && mask && cursor && loss_partials, "pmc_flow_eval_batches: null pointer");
   PMC_REQUIRE(meta_len >= TR_LEN && meta_host[TR_VERSION] == 200, "pmc_flow_eval_batches: not a training layout table");
-  PMC_REQUIRE(bp > 0 && bp % TR_ROWS == 0 && n_batches >= 0, "pmc_flow_eval_batches: padded batch must be a multiple of 32 rows");
+  PMC_REQUIRE(bp > 0 && bp % TR_PAD == 0 && n_batches >= 0, "pmc_flow_eval_batches: padded batch must be a multiple of 32 rows");
   if (n_batches == 0) return 0;
   return train_launch(packed, meta_host, meta_len, xdata, wdata, idx, mask, cursor, bp, n_batches, nullptr, loss_partials, logprob,
                       nullptr, nullptr, nullptr, 0, stream);

@@ -467,7 +467,7 @@ class _FitEngine:
         if B not in self.fscratch:
             nfl = int(_lib.load().pmc_flow_train_scratch_size(self.tl_meta.ctypes.data_as(_lib.C.c_void_p), B))
             self.fscratch[B] = (torch.empty(nfl, dtype=torch.float32, device=mod.raw.device),
-                                torch.zeros(B // 32, dtype=torch.float64, device=mod.raw.device))
+                                torch.zeros(B // 8, dtype=torch.float64, device=mod.raw.device))
         scratch, partials = self.fscratch[B]
         if not train:
             _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
@@ -480,7 +480,7 @@ class _FitEngine:
             # written straight into the training image (run_epoch packs it once per epoch; no pack between steps)
             _lib.call("pmc_adamw_clip_step_ex", _lib.ptr(mod.raw), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
                       mod.raw.numel(), _lib.ptr(self.hyper), _lib.ptr(self.step), _lib.ptr(self.scratch), _lib.ptr(self.gnorm),
-                      _lib.ptr(partials), B // 32, _lib.ptr(self.acc), _lib.ptr(self.cursor),
+                      _lib.ptr(partials), B // 8, _lib.ptr(self.acc), _lib.ptr(self.cursor),
                       _lib.ptr(self.tl_pos_a), _lib.ptr(self.tl_pos_b), _lib.ptr(self.tl_packed))
         else:
             self.acc += partials.sum()
@@ -500,7 +500,7 @@ class _FitEngine:
         if B not in self.fscratch:
             nfl = int(_lib.load().pmc_flow_train_scratch_size(self.tl_meta.ctypes.data_as(_lib.C.c_void_p), B))
             self.fscratch[B] = (torch.empty(nfl, dtype=torch.float32, device=mod.raw.device),
-                                torch.zeros(B // 32, dtype=torch.float64, device=mod.raw.device))
+                                torch.zeros(B // 8, dtype=torch.float64, device=mod.raw.device))
         scratch, partials = self.fscratch[B]
         _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
         _lib.call("pmc_flow_train_step", _lib.ptr(self.tl_packed), self.tl_meta.ctypes.data_as(_lib.C.c_void_p),
@@ -594,13 +594,13 @@ class _FitEngine:
             # its own weight normalisation, flow.py:307-310)
             mod = self.module
             if B not in self.eval_partials:
-                self.eval_partials[B] = torch.zeros(self.MAX_BATCHES * (B // 32), dtype=torch.float64, device=mod.raw.device)
+                self.eval_partials[B] = torch.zeros(self.MAX_BATCHES * (B // 8), dtype=torch.float64, device=mod.raw.device)
             partials = self.eval_partials[B]
             _lib.call("pmc_flow_pack", _lib.ptr(mod.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
             _lib.call("pmc_flow_eval_batches", _lib.ptr(self.tl_packed), self.tl_meta.ctypes.data_as(_lib.C.c_void_p),
                       int(self.tl_meta.size), _lib.ptr(self.x), _lib.ptr(self.w) if weighted else None, _lib.ptr(idx_all),
                       _lib.ptr(mask_all), _lib.ptr(self.cursor), B, nb, _lib.ptr(partials), None)
-            self.acc += partials[:nb * (B // 32)].sum()
+            self.acc += partials[:nb * (B // 8)].sum()
             self.launches += 1
             return self.acc
         if self.fused and train:       # the training image follows raw inside the step; bring it up to date once per epoch
