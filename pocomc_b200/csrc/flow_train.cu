@@ -419,11 +419,16 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   }
 }
 
-// dW_l[n][k] = sum_r dpre_l[r][n] * input_l[r][k], db_l[n] = sum_r dpre_l[r][n]; one 32 x 32 tile per CTA
+// dW_l[n][k] = sum_r dpre_l[r][n] * input_l[r][k], db_l[n] = sum_r dpre_l[r][n]; one 32 x 32 tile per CTA.
+// The batch is walked in chunks of CH rows whose loads are issued one chunk ahead: the kernel is bound by the L2
+// latency of those loads (the arithmetic of a chunk is ~0.5 us), so CH = 128 leaves 4 exposed round trips for a
+// 512-row batch where CH = 32 had 16.
+template <int CH>
 __global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams p, const int* __restrict__ tiles,
                                                                const int* __restrict__ wmap, int map_tstride,
                                                                float* __restrict__ grad) {
-  __shared__ float dp[32][33], in[32][33];
+  constexpr int Q = CH / 8;                                    // elements of each operand per thread per chunk
+  __shared__ float dp[CH][33], in[CH][33];
   const int t = tiles[4 * blockIdx.x], l = tiles[4 * blockIdx.x + 1], n0 = tiles[4 * blockIdx.x + 2], k0 = tiles[4 * blockIdx.x + 3];
   const int D = p.D, H = p.H, L = p.L, No = p.No, Bp = p.Bp, Dp = p.Dp;
   const int n_img = (l < L) ? H : No, k_true = (l == 0) ? D : H;
@@ -436,27 +441,29 @@ __global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams
   const int* bmap = map + n_img * k_true;
   const int tid = threadIdx.x, a = tid >> 4, b = tid & 15;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, bacc[2] = {0.f, 0.f};
-  float pd[4], pi[4];                                          // next chunk, fetched while the current one is reduced
+  float pd[Q], pi[Q];                                          // next chunk, fetched while the current one is reduced
   auto fetch = [&](int r0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < Q; ++q) {
       const int e = tid + 256 * q, rr = e >> 5, c = e & 31;
-      pd[q] = dpre[(size_t)(r0 + rr) * n_img + n0 + c];
-      pi[q] = (k0 + c < k_true) ? inp[(size_t)(r0 + rr) * ldk + k0 + c] : 0.f;
+      const bool ok = r0 + rr < Bp;
+      pd[q] = ok ? dpre[(size_t)(r0 + rr) * n_img + n0 + c] : 0.f;
+      pi[q] = (ok && k0 + c < k_true) ? inp[(size_t)(r0 + rr) * ldk + k0 + c] : 0.f;
     }
   };
   fetch(0);
-  for (int r0 = 0; r0 < Bp; r0 += 32) {
+  for (int r0 = 0; r0 < Bp; r0 += CH) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < Q; ++q) {
       const int e = tid + 256 * q, rr = e >> 5, c = e & 31;
       dp[rr][c] = pd[q];
       in[rr][c] = pi[q];
     }
     __syncthreads();
-    if (r0 + 32 < Bp) fetch(r0 + 32);
+    if (r0 + CH < Bp) fetch(r0 + CH);
+    const int nr = min(CH, Bp - r0);                           // a multiple of 32
 #pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
+    for (int rr = 0; rr < nr; ++rr) {
       const float d0 = dp[rr][2 * a], d1 = dp[rr][2 * a + 1], i0 = in[rr][2 * b], i1 = in[rr][2 * b + 1];
       acc[0][0] = fmaf(d0, i0, acc[0][0]); acc[0][1] = fmaf(d0, i1, acc[0][1]);
       acc[1][0] = fmaf(d1, i0, acc[1][0]); acc[1][1] = fmaf(d1, i1, acc[1][1]);
@@ -554,7 +561,11 @@ static int train_launch(const float* packed, const int32_t* meta_host, int32_t m
 #undef PMC_TRAIN_CASE
   PMC_LAUNCH_CHECK();
   if (backward) {
-    flow_train_wgrad_kernel<<<(unsigned)m[TR_NTILES], 256, 0, st>>>(p, tiles, wmap, m[TR_MAP_TSTRIDE], grad);
+    int ch = (bp >= 128) ? 128 : 32;
+    if (const char* e = getenv("PMC_WGRAD_CHUNK")) ch = atoi(e);     // tuning override
+    if (ch == 128) flow_train_wgrad_kernel<128><<<(unsigned)m[TR_NTILES], 256, 0, st>>>(p, tiles, wmap, m[TR_MAP_TSTRIDE], grad);
+    else if (ch == 64) flow_train_wgrad_kernel<64><<<(unsigned)m[TR_NTILES], 256, 0, st>>>(p, tiles, wmap, m[TR_MAP_TSTRIDE], grad);
+    else flow_train_wgrad_kernel<32><<<(unsigned)m[TR_NTILES], 256, 0, st>>>(p, tiles, wmap, m[TR_MAP_TSTRIDE], grad);
     PMC_LAUNCH_CHECK();
   }
   return 0;

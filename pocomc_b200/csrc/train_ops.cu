@@ -39,12 +39,22 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restric
     partials[blockIdx.x] = s;
     if (blockIdx.x == 0) {
       step[0] += 1;                           // the AdamW step counter t (read by the update kernel)
-      if (book.loss_acc) {
-        double l = 0.0;
-        for (int i = 0; i < book.n_loss; ++i) l += book.loss_partials[i];
-        book.loss_acc[0] += l;
-      }
       if (book.cursor) book.cursor[0] += 1;
+    }
+  }
+  // loss of the step: block 0 sums the partials with all its threads (fixed assignment and tree, so the result does not
+  // depend on timing); one thread walking them in index order cost ~3 us of dependent L2 round trips per step
+  if (blockIdx.x == 0 && book.loss_acc) {
+    double l = 0.0;
+    for (int i = threadIdx.x; i < book.n_loss; i += blockDim.x) l += book.loss_partials[i];
+    l = warp_sum(l);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += ws[i];
+      book.loss_acc[0] += s;
     }
   }
 }
@@ -55,10 +65,18 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, 
                                                          const long long* __restrict__ step, float* __restrict__ gnorm_out,
                                                          const int* __restrict__ pos_a, const int* __restrict__ pos_b,
                                                          float* __restrict__ image) {
-  __shared__ float s_coef;
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  __shared__ double ws[8];
+  {  // every block needs the total: all threads load (fixed assignment + tree: deterministic), not one thread x 296 loads
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) a += partials[i];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = a;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int i = 0; i < n_partials; ++i) s += partials[i];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += ws[i];
     const float total = (float)sqrt(s);                          // torch.linalg.vector_norm result is fp32
     float coef = 1.0f;
     if (hyper[HY_CLIP] > 0.0) {
@@ -67,14 +85,14 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, 
     }
     s_coef = coef;
     if (blockIdx.x == 0 && gnorm_out) gnorm_out[0] = total;
+    const double t = (double)step[0];                            // bias corrections: two double pow per block, not per thread
+    s_step_size = (float)(hyper[HY_LR] / (1.0 - pow(hyper[HY_BETA1], t)));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow(hyper[HY_BETA2], t));
   }
   __syncthreads();
   const float coef = s_coef;
   const double lr = hyper[HY_LR], b1 = hyper[HY_BETA1], b2 = hyper[HY_BETA2];
-  const double t = (double)step[0];
-  const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
-  const float step_size = (float)(lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float eps = (float)hyper[HY_EPS];
   const float decay = (float)(1.0 - lr * hyper[HY_WD]);
   const float w1 = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2);
