@@ -87,8 +87,8 @@ __device__ __forceinline__ void gemm_any(int tn, const float* At, int K, const f
 // ROWS batch rows per CTA.  The 8 warps form RG = ROWS/4 row groups (4 rows each, one broadcast LDS.128 per k) times
 // CG = 8/RG column groups: a hidden layer's H output columns are dealt to the column groups in 32-wide tiles (tile index
 // cg + CG j), so a smaller ROWS spreads one batch over more SMs at the same work per FFMA.  The two narrow GEMMs of a
-// transform (output layer, N = 2 Dp; input gradient, N = Dp) keep shift and scale of a feature in one thread and run on
-// the cg == 0 warps only.
+// transform (output layer, N = 2 Dp; input gradient, N = Dp) keep shift and scale of a feature in one thread: there the
+// column groups split K and the cg == 0 ("lead") warps sum the partials and run the affine maps.
 template <int ROWS>
 __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams p) {
   constexpr int TR_ROWS = ROWS, TR_LDA = ROWS + 4, RG = ROWS / 4, CG = 8 / RG, CSW = 32 * CG;
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   float* xT = bufB + brows * TR_LDA;
   float* gT = xT + Dp * TR_LDA;
   uint32_t* relu_bits = reinterpret_cast<uint32_t*>(gT + Dp * TR_LDA);   // [T*L][256]: (h > 0) of this thread's 4 x 8 outputs
+  float* redbuf = reinterpret_cast<float*>(relu_bits + (size_t)T * L * 256);   // [(CG-1) ROWS][No] split-K partial sums
 
   const int tid = threadIdx.x, warp = tid >> 5, tx = tid & 31;
   const int ty = warp % RG, cg = warp / RG;                     // row group (rows 4 ty .. 4 ty + 3), column group
@@ -163,25 +164,49 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     if (tid == 0) { fence_proxy_async(); issue_next(); }
     ++s;
   };
-  // wide: N = H, every warp, columns cw0 + CSW j;  narrow: cg == 0 warps only, columns tx + 32 j.  Idle warps keep the
-  // ring position in step (same release() calls) without touching the slot.
-  auto stream_gemm = [&](bool wide, int tn, const float* in, int K, int N, int bias) {
+  // wide (N = H): every warp owns the columns cw0 + CSW j of its 4 rows.
+  // narrow (output layer N = 2 Dp, input gradient N = Dp): shift and scale of a feature must meet in one thread, so
+  // the columns stay whole (tx + 32 j) and the K rows of every chunk are dealt over the column groups instead
+  // (split-K); the partial sums meet in `red` and the lead
+  // warps (cg == 0) add them in group order, so the result does not depend on timing.
+  auto stream_gemm = [&](bool wide, int tn, const float* in, int K, int N, int bias, float* red) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     const int kc = rows_per_chunk(K, N, bias);
-    const bool work = wide || lead;
     for (int k0 = 0; k0 < K; k0 += kc) {
       const int rows = min(kc, K - k0);
-      if (work) {
-        mbar_wait(full + (s % NS), (s / NS) & 1);
-        wl = wring + (size_t)(s % NS) * wmax;
-        if (wide) gemm_any<CSW, TR_LDA>(tn, in + k0 * TR_LDA, rows, wl, N, ty, cw0, acc);
-        else gemm_any<32, TR_LDA>(tn, in + k0 * TR_LDA, rows, wl, N, ty, tx, acc);
+      mbar_wait(full + (s % NS), (s / NS) & 1);
+      wl = wring + (size_t)(s % NS) * wmax;
+      if (wide) {
+        gemm_any<CSW, TR_LDA>(tn, in + k0 * TR_LDA, rows, wl, N, ty, cw0, acc);
+      } else {
+        const int lo = cg * rows / CG, hi = (cg + 1) * rows / CG;
+        gemm_any<32, TR_LDA>(tn, in + (k0 + lo) * TR_LDA, hi - lo, wl + lo * N, N, ty, tx, acc);
       }
       rows_last = rows;
       if (k0 + rows < K) release();
+    }
+    if (!wide && CG > 1) {
+      if (!lead) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j >= tn) continue;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) red[((cg - 1) * TR_ROWS + 4 * ty + i) * N + tx + 32 * j] = acc[i][j];
+        }
+      }
+      __syncthreads();
+      if (lead) {
+        for (int c = 1; c < CG; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j >= tn) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][j] += red[((c - 1) * TR_ROWS + 4 * ty + i) * N + tx + 32 * j];
+          }
+      }
     }
   };
 
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float* in = xT;
     float* out = bufA;
     for (int l = 0; l < L; ++l) {
-      stream_gemm(true, tnW, in, (l == 0) ? D : H, H, 1);
+      stream_gemm(true, tnW, in, (l == 0) ? D : H, H, 1, nullptr);
       const float* bias = wl + rows_last * H;                 // bias rides behind the last weight rows in the same bulk copy
       float* hs = p.Hs + ((size_t)(t * L + l) * Bp + row0 + 4 * ty) * H;
       uint32_t bits = 0;
@@ -247,7 +272,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       out = (out == bufA) ? bufB : bufA;
     }
     // output layer + affine map (lead warps)
-    stream_gemm(false, tnO, in, H, No, 1);
+    stream_gemm(false, tnO, in, H, No, 1, redbuf);
     if (lead) {
       const float* bo = wl + rows_last * No;
 #pragma unroll
@@ -384,7 +409,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float* out = bufB;
     for (int j = 0; j < L; ++j) {                              // images B_o, B_{L-1}, ..., B_1
       const int lh = L - 1 - j;                                // hidden layer whose pre-activation gradient comes out
-      stream_gemm(true, tnW, in, j == 0 ? No : H, H, 0);
+      stream_gemm(true, tnW, in, j == 0 ? No : H, H, 0, nullptr);
       const uint32_t bits = relu_bits[(t * L + lh) * 256 + tid];
       float* gh = p.Gh + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
 #pragma unroll
@@ -405,7 +430,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       float* tmp = in; in = out; out = tmp;
     }
     // image B_0: gradient w.r.t. the transform input through the hyper-network + the direct path (lead warps)
-    stream_gemm(false, tnD, in, H, Dp, 0);
+    stream_gemm(false, tnD, in, H, Dp, 0, redbuf);
     if (lead) {
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
@@ -493,7 +518,8 @@ static size_t train_smem(int rows, int D, int Dp, int H, int No, int T, int L, i
   const size_t TR_LDA = (size_t)rows + 4;
   const size_t wmax = (size_t)std::max(std::max((D + 1) * H, (H + 1) * H), std::max((H + 1) * No, H * Dp));
   const size_t brows = (size_t)std::max(H, No);
-  const size_t act = (2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4 + (size_t)T * L * 256 * 4;
+  const size_t act = (2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4 + (size_t)T * L * 256 * 4 +
+                     (size_t)(32 - rows) * No * 4;                  // + split-K partial sums of the narrow GEMMs
   const size_t budget = 200 * 1024;
   if (act + 2 * wmax * 4 <= budget) {
     // small networks: whole images, and a deeper ring lets the bulk copies run several layers ahead of the chain

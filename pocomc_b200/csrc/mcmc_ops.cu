@@ -34,18 +34,24 @@ tpcn_propose_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl
       zz[j] = z[row * d + j];
     }
     __syncwarp();
+    // both mat-vecs that only need the current state run in one j-loop (two independent fma chains, same
+    // left-to-right order per chain as before): Sigma^-1 (theta - mu) and L z
     double part = 0.0;
     for (int i = lane; i < d; i += 32) {
-      double v = 0.0;
-      for (int j = 0; j < d; ++j) v = fma(inv_t[(size_t)j * d + i], diff[j], v);
+      double v = 0.0, lz = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < d; ++j) {
+        v = fma(inv_t[(size_t)j * d + i], diff[j], v);
+        lz = fma(chol_t[(size_t)j * d + i], zz[j], lz);
+      }
       part = fma(diff[i], v, part);
+      dp[i] = lz;                                          // this lane's own slot: read back below by the same lane
     }
     const double m = warp_sum(part);
     const double s = 1.0 / (g[row] * (2.0 / (nu + m)));   // 1 / gamma(a, scale = 2/(nu+m))   mcmc.py:80
     const double amp = sigma * sqrt(s);
     for (int i = lane; i < d; i += 32) {
-      double lz = 0.0;
-      for (int j = 0; j < d; ++j) lz = fma(chol_t[(size_t)j * d + i], zz[j], lz);
+      const double lz = dp[i];
       const double pr = (mu[i] + keep * diff[i]) + amp * lz;
       prop64[row * d + i] = pr;
       if (prop32) prop32[row * d + i] = (float)pr;
@@ -55,6 +61,7 @@ tpcn_propose_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl
     part = 0.0;
     for (int i = lane; i < d; i += 32) {
       double v = 0.0;
+#pragma unroll 8
       for (int j = 0; j < d; ++j) v = fma(inv_t[(size_t)j * d + i], dp[j], v);
       part = fma(dp[i], v, part);
     }
@@ -212,7 +219,6 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
   const bool flow = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_RWM_FLOW);
   const bool tp = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_TPCN);
   const bool want_theta = (kind == PMC_KIND_TPCN_FLOW);
-  for (int j = lane; j < d; j += 32) th[j] = 0.0;
   const long long base = (long long)blockIdx.x * ROWS_PER_BLOCK + warp * 32;
   const long long row = base + lane;
   const bool valid = row < n;
@@ -243,19 +249,43 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
   const unsigned ballot = __ballot_sync(FULL, acc);
   const double s_alpha = warp_sum(alpha), s_track = warp_sum(track);
   const int s_fin = __popc(__ballot_sync(FULL, fin));
-  for (int rr = 0; rr < 32; ++rr) {
-    const long long rw = base + rr;
-    if (rw >= n) break;
-    const bool a = (ballot >> rr) & 1u;
-    for (int j = lane; j < d; j += 32) {
-      const long long o = rw * d + j;
-      if (a) {
-        u[o] = u_p[o];
-        x[o] = x_p[o];
-        if (pos32) pos32[o] = (float)prop64[o];   // theta[mask] = theta_prime[mask] rounds to f32, mcmc.py:141
+  // masked row copy + per-column theta sums.  A lane owns column j and walks the warp's 32 rows in ascending order
+  // (the order fixes the f64 sum bit for bit); rows go in batches of 8 whose loads are all issued before the first
+  // use -- one dependent round trip per batch instead of per row (the loop was 32 serial L2 latencies, 30 us at
+  // 10 000 particles).
+  for (int j = lane; j < d; j += 32) {
+    double tsum = 0.0;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      float pv[8];
+      double uu[8], xx[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long long rw = base + r0 + q;
+        const bool a = (ballot >> (r0 + q)) & 1u;         // accepted rows are valid rows
+        const long long o = rw * d + j;
+        pv[q] = 0.f; uu[q] = 0.0; xx[q] = 0.0;
+        if (a) {
+          uu[q] = u_p[o];
+          xx[q] = x_p[o];
+          if (pos32) pv[q] = (float)prop64[o];            // theta[mask] = theta_prime[mask] rounds to f32, mcmc.py:141
+        } else if (want_theta && rw < n) {
+          pv[q] = pos32[o];
+        }
       }
-      if (want_theta) th[j] += (double)pos32[o];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long long rw = base + r0 + q;
+        const long long o = rw * d + j;
+        if ((ballot >> (r0 + q)) & 1u) {
+          u[o] = uu[q];
+          x[o] = xx[q];
+          if (pos32) pos32[o] = pv[q];
+        }
+        if (want_theta && rw < n) tsum += (double)pv[q];
+      }
     }
+    th[j] = tsum;
   }
   if (lane == 0) { sc[0] = s_alpha; sc[1] = s_track; sc[2] = (double)__popc(ballot); sc[3] = (double)s_fin; }
   __syncthreads();
@@ -276,7 +306,13 @@ mcmc_finalize_kernel(int kind, double* __restrict__ ctl, const double* __restric
   for (int j = threadIdx.x; j < d + 4; j += blockDim.x) {
     double s = 0.0;
     if (j < 4 || (tpf && mean_mode == 0)) {
-      for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * (d + 4) + j];
+      for (int b0 = 0; b0 < n_blocks; b0 += 8) {              // 8 loads in flight, added in block order
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (b0 + q < n_blocks) ? partials[(size_t)(b0 + q) * (d + 4) + j] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (b0 + q < n_blocks) s += v[q];
+      }
       if (j >= 4) s /= (double)n;
     } else if (tpf) {
       // np.mean(theta, axis=0) on the f32 theta array: sequential f32 accumulation over rows, f32 divide
