@@ -234,6 +234,18 @@ class MaskedAutoregressiveFlow(nn.Module):
                   self._meta_host.ctypes.data_as(_lib.C.c_void_p), int(self._meta_host.size), _lib.ptr(src),
                   _lib.ptr(out), _lib.ptr(ladj), src.shape[0], 1 if inverse else 0)
 
+    def bind_sweep(self, src: torch.Tensor, out: torch.Tensor, ladj: torch.Tensor, inverse: bool):
+        """Pre-bound ``sweep_into`` for fixed buffers and fixed weights (the MCMC loop calls the flow with the same
+        tensors every step); the returned callable keeps the packed weight image alive."""
+        packed = self.packed()
+        if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
+            raise ValueError("bind_sweep needs a contiguous CUDA float32 input")
+        run = _lib.bind("pmc_flow_sweep", _lib.ptr(packed), _lib.ptr(self.meta),
+                        self._meta_host.ctypes.data_as(_lib.C.c_void_p), int(self._meta_host.size), _lib.ptr(src),
+                        _lib.ptr(out), _lib.ptr(ladj), src.shape[0], 1 if inverse else 0)
+        run.keep = (packed, self.meta, self._meta_host, src, out, ladj)
+        return run
+
     def mark_dirty(self):
         """``raw`` was updated in place by a kernel torch does not see (csrc/train_ops.cu): drop the packed copies."""
         self._packed_key, self._tc_key = None, None

@@ -153,6 +153,7 @@ class McmcEngine:
         self.accept = 0.0
         self.stop = False
         self._propose = self._scaler_inverse = self._finalize = None       # pre-bound libpmc_b200 calls (built on first use)
+        self._rng_fill = self._sweep = self._logprior = None
         self._stream = torch.cuda.current_stream()     # the engine lives for one kernel call on the caller's stream; looking it up costs ~20 us per step
         self._accept = {}
         self.sc, self._sc_keep, _ = self.scaler._params(True)
@@ -174,8 +175,13 @@ class McmcEngine:
             hn[n:n + n * d] = np.random.randn(ng, d)[lo:lo + n].reshape(-1)
             self.z.copy_(self.h_noise[n:n + n * d].view(n, d), non_blocking=True)
         else:
-            _lib.call("pmc_rng_fill", C.c_uint64(self.seed), C.c_uint64(self.step + 1), int(self.row_offset),
-                      (d + self.nu) / 2 if self.tp else 0.0, _lib.ptr(self.g), _lib.ptr(self.z), _lib.ptr(self.r), n, d)
+            if self._rng_fill is None:       # the step counter is the one argument that changes: a ctypes cell read at call time
+                self._rng_step = C.c_uint64(0)
+                self._rng_fill = _lib.bind("pmc_rng_fill", C.c_uint64(self.seed), self._rng_step, int(self.row_offset),
+                                           (d + self.nu) / 2 if self.tp else 0.0, _lib.ptr(self.g), _lib.ptr(self.z),
+                                           _lib.ptr(self.r), n, d)
+            self._rng_step.value = self.step + 1
+            self._rng_fill()
 
     def propose(self):
         if self._propose is None:          # every buffer of the engine is fixed: bind the argument list once
@@ -199,7 +205,9 @@ class McmcEngine:
             if self.sweep_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            self.module.sweep_into(self.prop32, self.u_p32, self.ldjf_p, inverse=True)
+            if self._sweep is None:
+                self._sweep = self.module.bind_sweep(self.prop32, self.u_p32, self.ldjf_p, inverse=True)
+            self._sweep()
             if self.sweep_events is not None:
                 e1.record()
                 self.sweep_events.append((e0, e1))
@@ -217,7 +225,11 @@ class McmcEngine:
         (config.device_prior) and only the likelihood crosses the PCIe bus."""
         n = self.n
         if self.logprior_device is not None:
-            self.logprior_device(self.x_p, self.finite, self.logp_p)       # also clears finite where logp' is not finite
+            if self._logprior is None:
+                bind = getattr(self.logprior_device, "bind", None)
+                self._logprior = bind(self.x_p, self.finite, self.logp_p) if bind is not None else \
+                    (lambda: self.logprior_device(self.x_p, self.finite, self.logp_p))
+            self._logprior()                                                # also clears finite where logp' is not finite
         self.h_x.copy_(self.x_p, non_blocking=True)
         self.h_fin.copy_(self.finite, non_blocking=True)
         self._stream.synchronize()

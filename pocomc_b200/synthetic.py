@@ -119,3 +119,10 @@ class DevicePrior:
         n, d = x.shape
         _lib.call("pmc_logprior", _lib.ptr(x), _lib.ptr(finite), _lib.ptr(kind), _lib.ptr(loc), _lib.ptr(scale),
                   _lib.ptr(out), n, d)
+
+    def bind(self, x: torch.Tensor, finite: torch.Tensor, out: torch.Tensor):
+        """Pre-bound variant of ``__call__`` for fixed buffers (the per-step loop of the MCMC engine)."""
+        kind, loc, scale = self._params(x.device)
+        n, d = x.shape
+        return _lib.bind("pmc_logprior", _lib.ptr(x), _lib.ptr(finite), _lib.ptr(kind), _lib.ptr(loc), _lib.ptr(scale),
+                         _lib.ptr(out), n, d)

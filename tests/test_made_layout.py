@@ -15,7 +15,7 @@ def _raw(flow):
 
 @pytest.mark.parametrize("preset,d", [("maf3", 2), ("maf3", 3), ("maf3", 4), ("maf6", 10), ("nsf3", 5),
                                       ("nsf6", 2), ("maf6", 32), ("nsf3", 13)])
-def test_sweep_matches_oracle(preset, d):
+def test_sweep_matches_oracle(preset, d, faithful_fp32_oracle):
     torch.manual_seed(d)
     flow = F.make_flow(d, preset)
     kind0 = F.PRESETS[preset][0]
