@@ -91,3 +91,23 @@ def test_weighted_geometry_matches_reference(golden):
     geo.fit(g["theta"], weights=g["w"])
     for k in KEYS:
         np.testing.assert_allclose(getattr(geo, k), g[k], err_msg=k, **F64)
+
+
+def test_fit_mvstud_matches_reference_vectors_and_takes_the_full_path_when_it_must(golden):
+    """student.py:5-85 on the recorded cloud (bit-for-bit: the shortcut past the unused Mahalanobis solve must not
+    change a single value), and the guard that sends degenerate clouds down the reference's own path."""
+    g = golden("geometry")
+    mu, sigma, nu = pc.geometry.fit_mvstud(g["theta"])
+    np.testing.assert_array_equal(mu, g["mvstud_mu"])
+    np.testing.assert_array_equal(sigma, g["mvstud_sigma"])
+    assert nu == g["mvstud_nu"] or (np.isinf(nu) and np.isinf(g["mvstud_nu"]))
+    from pocomc_b200.geometry import _delta_cannot_matter
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(200, 3))
+    diffs = (x - np.median(x, axis=0)).T
+    assert _delta_cannot_matter(diffs, np.cov(x.T))
+    dup = np.c_[x, x[:, 0]]                                         # singular covariance: no bound on delta
+    assert not _delta_cannot_matter((dup - np.median(dup, axis=0)).T, np.cov(dup.T) * 0.0)
+    bad = diffs.copy(); bad[0, 0] = np.inf
+    assert not _delta_cannot_matter(bad, np.cov(x.T))
+    assert not _delta_cannot_matter(diffs * 1e150, np.cov(x.T))       # |d|^2 / lambda_min overflows the bound
