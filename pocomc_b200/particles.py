@@ -69,6 +69,29 @@ class Particles:
             return np.asarray(self.past.get(key))
         return self.past.get(key)[index]
 
+    def take_flat(self, key, idx):
+        """``self.get(key, flat=True)[idx]`` without materialising the concatenated history: rows are copied
+        iteration by iteration, so the cost follows the number of selected rows instead of T x N (the trimmed
+        gather of ``Sampler._reweight`` runs once per temperature step and T grows with every step)."""
+        arrs = self.past.get(key)
+        idx = np.asarray(idx, dtype=np.int64)
+        if len(arrs) == 0 or idx.ndim != 1 or (idx.size > 1 and np.any(idx[1:] < idx[:-1])):
+            return self.get(key, flat=True)[idx]
+        first = np.asarray(arrs[0])
+        starts = np.concatenate([[0], np.cumsum([len(a) for a in arrs])])
+        if idx.size and (idx[0] < 0 or idx[-1] >= starts[-1]):
+            raise IndexError("index out of range of the flattened history")
+        dtypes = {np.asarray(a).dtype for a in arrs}
+        if len(dtypes) != 1 or any(np.asarray(a).shape[1:] != first.shape[1:] for a in arrs):
+            return self.get(key, flat=True)[idx]                      # mixed dtypes / shapes: let numpy decide
+        out = np.empty((idx.size,) + first.shape[1:], dtype=first.dtype)
+        cut = np.searchsorted(idx, starts)
+        for t, a in enumerate(arrs):
+            lo, hi = cut[t], cut[t + 1]
+            if hi > lo:
+                out[lo:hi] = np.asarray(a)[idx[lo:hi] - starts[t]]
+        return out
+
     # -- device mirror --------------------------------------------------------------------------
     def _sync_device(self):
         """Bring logl / den on the GPU up to date with the host history."""

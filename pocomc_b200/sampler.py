@@ -394,9 +394,9 @@ class Sampler:
         keep, w_trim = trim_weights_device(w_dev, ess=0.99, bins=1000)
         idx = torch.nonzero(keep).squeeze(1).cpu().numpy()
         for key in ("u", "x", "logdetj", "logl", "logp"):
-            current_particles[key] = self.particles.get(key, index=None, flat=True)[idx]
+            current_particles[key] = self.particles.take_flat(key, idx)
         if self.have_blobs:
-            current_particles["blobs"] = self.particles.get("blobs", index=None, flat=True)[idx]
+            current_particles["blobs"] = self.particles.take_flat("blobs", idx)
         current_particles["logz"] = logz
         current_particles["beta"] = beta
         current_particles["weights"] = w_trim.cpu().numpy()

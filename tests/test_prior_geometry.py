@@ -111,3 +111,21 @@ def test_fit_mvstud_matches_reference_vectors_and_takes_the_full_path_when_it_mu
     bad = diffs.copy(); bad[0, 0] = np.inf
     assert not _delta_cannot_matter(bad, np.cov(x.T))
     assert not _delta_cannot_matter(diffs * 1e150, np.cov(x.T))       # |d|^2 / lambda_min overflows the bound
+
+
+def test_particles_take_flat_equals_concatenate_then_index():
+    """Sampler._reweight's trimmed gather (sampler.py:792-800): same rows, same dtype, any index pattern."""
+    from pocomc_b200.particles import Particles
+    rng = np.random.default_rng(2)
+    p = Particles(7, 3)
+    for t in range(9):
+        p.update(dict(u=rng.normal(size=(7, 3)), logl=rng.normal(size=7), iter=t))
+    for idx in (np.array([0, 1, 6, 7, 20, 62]), np.arange(63), np.array([], dtype=np.int64), np.array([62]),
+                np.array([5, 5, 5, 40]), np.array([40, 3, 9])):                      # the last one is unsorted: fallback
+        for key in ("u", "logl"):
+            want = p.get(key, flat=True)[idx]
+            got = p.take_flat(key, idx)
+            assert got.dtype == want.dtype and got.shape == want.shape
+            np.testing.assert_array_equal(got, want)
+    with pytest.raises(IndexError):
+        p.take_flat("u", np.array([0, 63]))
