@@ -385,6 +385,154 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
 
 
 # ---------------------------------------------------------------------------------------------
+# "tip" stream: bulk / tip split of every hop (csrc/flow_tip.cu, experimental)
+# ---------------------------------------------------------------------------------------------
+TIP_MAXCH = 2             # the kernel keeps one group's fresh activations in 4 * TIP_MAXCH registers per lane
+
+
+def tip_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int) -> bool:
+    """Affine flows whose degree groups have at most 4 * TIP_MAXCH hidden units (H / (D - 1) <= 8: D >= 6 for
+    the reference's H = max(next_pow2(3 D), 32))."""
+    if kind != KIND_AFFINE or n_dim < 3 or n_layers < 1:
+        return False
+    return -(-n_hidden // (n_dim - 1)) <= 4 * TIP_MAXCH and stream_supported(n_dim, n_hidden, n_layers, kind)
+
+
+@lru_cache(maxsize=None)
+def build_stream_tip(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int = KIND_AFFINE,
+                     bins: int = 8) -> StreamLayout:
+    """Consumption-ordered weight stream for the bulk/tip sweep kernel.
+
+    Every dot product of the degree-ordered sweep is split into the part over inputs that were finished one
+    order position earlier (the BULK: no dependence on the value being computed right now, so its latency is
+    hidden) and the part over the inputs born in the current position (the TIP: one degree group, <= 8 units).
+    Stage k (order position k, feature iperm[k]; group g = k + 1 = sorted units [gstart[k], gstart[k+1])) holds,
+    all in float4 units:
+      out tip   : 4 nch(k-1) x (Wout[shift | scale][unit j of group k], 0, 0), then (b_shift, b_scale, 0, 0)
+      bulk of g : layer 0   nch slabs [pad16(k) rows][4]          rows = inputs of order < k
+                  layer l   nch slabs [pad16(gstart[k]) rows][4]   rows = sorted units of degree <= k
+      out bulk  : (k + 1 < D) one slab [pad16(gstart[k]) rows][4] = (Wout[shift], Wout[scale], 0, 0) of feature k + 1
+      tips of g : layer 0   per (chunk c, lane q): (bias, W0[unit, feature k], 0, 0)
+                  layer l   per (chunk c, lane q): (bias, 0, 0, 0) + nch float4 of W_l[unit, units of group g]
+    where unit = group unit 4 c + q (all zero for padding units).  meta: same header as build_stream, version 5."""
+    if not tip_supported(n_dim, n_hidden, n_layers, kind):
+        raise ValueError("flow shape not supported by the bulk/tip stream")
+    lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
+    D, H, L, T, total = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.total
+    ng = D - 1
+    hperm, degree = lay.hperm, lay.degree
+    gstart = np.searchsorted(degree, np.arange(1, ng + 2), side="left").astype(np.int64)    # gstart[i] = #units of degree <= i
+    gsize = np.diff(gstart)
+    nchunk = (gsize + 3) // 4
+    assert nchunk.max() <= TIP_MAXCH and gsize.min() > 0
+    raw_off = np.concatenate([[0], np.cumsum([int(np.prod(sh)) for sh in lay.raw_sizes])]).astype(np.int64)
+
+    def padded_units(g):
+        """raw unit ids of group g (1-based degree), padded with -1 to a multiple of 4"""
+        u = hperm[gstart[g - 1]:gstart[g]]
+        out = np.full(4 * int(nchunk[g - 1]), -1, np.int64)
+        out[:len(u)] = u
+        return out
+
+    def transform_gather(t):
+        base_r = t * lay.raw_tstride
+        iperm = np.arange(D) if t % 2 == 0 else D - 1 - np.arange(D)
+        wo, bo = base_r + raw_off[2 * L], base_r + raw_off[2 * L + 1]
+        stages = []
+        for k in range(D):
+            parts = []
+            feat = iperm[k]
+            # ---- out tip (units of group k = degree k) + bias
+            if k >= 1:
+                for u in padded_units(k):
+                    q = np.full(4, -1, np.int64)
+                    if u >= 0:
+                        q[:total] = wo + (feat * total + np.arange(total)) * H + u
+                    parts.append(q)
+            b = np.full(4, -1, np.int64)
+            b[:total] = bo + feat * total + np.arange(total)
+            parts.append(b)
+            g = k + 1
+            ek = int(gstart[k])                                   # sorted units of degree <= k
+            if g <= ng:
+                units = padded_units(g)
+                nch = int(nchunk[g - 1])
+                # ---- bulk of group g
+                for l in range(L):
+                    wl = base_r + raw_off[2 * l]
+                    rows = iperm[np.arange(k)] if l == 0 else hperm[:ek]
+                    width = D if l == 0 else H
+                    for c in range(nch):
+                        blk = np.full((_pad16(len(rows)), 4), -1, np.int64)
+                        for j in range(4):
+                            u = units[4 * c + j]
+                            if u >= 0 and len(rows):
+                                blk[:len(rows), j] = wl + u * width + rows
+                        parts.append(blk.reshape(-1))
+            if k + 1 < D:
+                # ---- out bulk of feature k + 1 over last-layer units of degree <= k
+                fnext = iperm[k + 1]
+                blk = np.full((_pad16(ek), 4), -1, np.int64)
+                for o in range(total):
+                    blk[:ek, o] = wo + (fnext * total + o) * H + hperm[:ek]
+                parts.append(blk.reshape(-1))
+            if g <= ng:
+                # ---- tips of group g
+                for l in range(L):
+                    wl, bl = base_r + raw_off[2 * l], base_r + raw_off[2 * l + 1]
+                    for c in range(nch):
+                        for q in range(4):
+                            u = units[4 * c + q]
+                            head = np.full(4, -1, np.int64)
+                            if u >= 0:
+                                head[0] = bl + u
+                                if l == 0:
+                                    head[1] = wl + u * D + feat
+                            parts.append(head)
+                            if l > 0:
+                                tipw = np.full(4 * nch, -1, np.int64)
+                                if u >= 0:
+                                    ok = units >= 0
+                                    tipw[ok] = wl + u * H + units[ok]
+                                parts.append(tipw)
+            stages.append(np.concatenate(parts))
+        return stages
+
+    stages0 = transform_gather(0)
+    sizes = np.array([len(a) for a in stages0], np.int64)
+    assert np.all(sizes % 4 == 0)
+    chunks, k0, acc, off = [], 0, 0, 0
+    for k in range(D):
+        if acc > 0 and acc + sizes[k] > STREAM_CHUNK_FLOATS:
+            chunks.append((k0, k, off, acc))
+            off += acc
+            k0, acc = k, 0
+        acc += int(sizes[k])
+    chunks.append((k0, D, off, acc))
+    chunks = np.asarray(chunks, np.int64)
+    tstride = int(sizes.sum())
+    slot_floats = int(chunks[:, 3].max())
+    gather = np.concatenate([np.concatenate(transform_gather(t)) for t in range(T)])
+    assert gather.size == T * tstride
+    tables = [gstart, nchunk, chunks.reshape(-1)]
+    meta = np.zeros(META_HEADER, np.int64)
+    meta[[M_D, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE]] = [D, H, L, T, kind, total, lay.tp, ng, tstride]
+    meta[M_MAXCH] = int(nchunk.max())
+    meta[M_RAW_TSTRIDE] = lay.raw_tstride
+    meta[M_BINS] = bins
+    meta[M_VERSION] = 5
+    meta[M_NCHUNKS] = len(chunks)
+    meta[M_SLOT_FLOATS] = slot_floats
+    pos = META_HEADER
+    for slot_id, tab in zip((M_OFF_GSTART, M_OFF_NCHUNK, M_OFF_CHUNKS), tables):
+        meta[slot_id] = pos
+        pos += len(tab)
+    meta = np.concatenate([meta] + [np.asarray(tb, np.int64) for tb in tables])
+    assert meta.max() < 2 ** 31 and gather.max() < 2 ** 31
+    return StreamLayout(tstride, slot_floats, chunks, meta.astype(np.int32), gather.astype(np.int32))
+
+
+# ---------------------------------------------------------------------------------------------
 # tensor-core (tcgen05) layout of the DENSE masked MLP: Flow.forward / log_prob / training forward
 # ---------------------------------------------------------------------------------------------
 TC_D, TC_H, TC_L, TC_T, TC_KIND, TC_KX, TC_NOUT, TC_TSTRIDE, TC_BIAS_OFF, TC_NCHUNKS, TC_SLOT_BYTES, TC_VERSION, TC_LEN = range(13)

@@ -370,3 +370,80 @@ def sweep_block(block, packed, x, inverse):
         out_all[row0:row0 + rows] = cur[:, :rows].T
         ladj_all[row0:row0 + rows] = ladj[:rows]
     return out_all, ladj_all
+
+
+def sweep_stream_tip(layout, stream, packed, x, inverse):
+    """Emulates the bulk/tip schedule of csrc/flow_tip.cu over made_layout.build_stream_tip's stream: every dot
+    product = bulk (inputs finished one order position earlier, computed ahead) + tip (the degree group born in
+    this position).  Walks the stream with a running float4 offset exactly like the kernel."""
+    m = stream.meta
+    assert int(m[ML.M_VERSION]) == 5
+    D, H, L, T, ng = (int(m[i]) for i in (ML.M_D, ML.M_H, ML.M_L, ML.M_T, ML.M_NG))
+    gstart = m[m[ML.M_OFF_GSTART]:m[ML.M_OFF_GSTART] + ng + 1].astype(np.int64)
+    nchunk = m[m[ML.M_OFF_NCHUNK]:m[ML.M_OFF_NCHUNK] + ng].astype(np.int64)
+    chunks = m[m[ML.M_OFF_CHUNKS]:m[ML.M_OFF_CHUNKS] + 4 * m[ML.M_NCHUNKS]].reshape(-1, 4)
+    p16 = lambda v: (int(v) + 15) // 16 * 16
+    cur = np.array(x, np.float32, copy=True)
+    n = len(cur)
+    ladj = np.zeros(n, np.float32)
+    for tt in range(T):
+        t = T - 1 - tt if inverse else tt
+        xs = np.zeros((n, D), np.float32)
+        act = np.zeros((L, n, H), np.float32)
+        bout = np.zeros((n, 4), np.float32)                     # bulk part of phi for the CURRENT position
+        fresh = np.zeros((n, 0), np.float32)                    # last-layer activations of the group born one position ago
+        for k0, k1, off, cnt in chunks:
+            w = packed[t * stream.tstride + off: t * stream.tstride + off + cnt].reshape(-1, 4)
+            pos = 0
+            for k in range(k0, k1):
+                feat = D - 1 - k if t % 2 else k
+                # ---- tip head: phi = bulk + out tip + bias -> univariate map
+                nchp = int(nchunk[k - 1]) if k >= 1 else 0
+                assert fresh.shape[1] == 4 * nchp
+                phi = bout + fresh @ w[pos:pos + 4 * nchp] + w[pos + 4 * nchp]
+                pos += 4 * nchp + 1
+                v = cur[:, feat].copy()
+                res, l = affine(phi, v, inverse)
+                ladj = ladj - l if inverse else ladj + l
+                xk = res if inverse else v
+                xs[:, k] = xk
+                cur[:, feat] = res
+                g = k + 1
+                ek = int(gstart[k])
+                bulk = None
+                if g <= ng:
+                    nch = int(nchunk[g - 1])
+                    gs, ge = int(gstart[g - 1]), int(gstart[g])
+                    bulk = np.zeros((L, n, 4 * nch), np.float32)
+                    for l_ in range(L):
+                        nrows = k if l_ == 0 else ek
+                        src = xs[:, :k] if l_ == 0 else act[l_ - 1][:, :ek]
+                        for c in range(nch):
+                            slab = w[pos:pos + p16(nrows)]; pos += p16(nrows)
+                            assert not slab[nrows:].any()
+                            bulk[l_][:, 4 * c:4 * c + 4] = src @ slab[:nrows]
+                if k + 1 < D:
+                    slab = w[pos:pos + p16(ek)]; pos += p16(ek)
+                    assert not slab[ek:].any()
+                    bout = act[L - 1][:, :ek] @ slab[:ek]
+                if g <= ng:
+                    prev = None                                     # fresh activations of the previous layer [n, 4 nch]
+                    for l_ in range(L):
+                        new = np.zeros((n, 4 * nch), np.float32)
+                        for c in range(nch):
+                            for q in range(4):
+                                j = 4 * c + q
+                                head = w[pos]; pos += 1
+                                if l_ == 0:
+                                    pre = bulk[0][:, j] + head[0] + head[1] * xk
+                                else:
+                                    tipw = w[pos:pos + nch].reshape(-1); pos += nch
+                                    pre = bulk[l_][:, j] + head[0] + prev @ tipw + prev[:, j]      # + residual
+                                new[:, j] = np.maximum(pre, 0)
+                        real = ge - gs
+                        assert not new[:, real:].any()              # padding units stay exactly zero
+                        act[l_][:, gs:ge] = new[:, :real]
+                        prev = new
+                    fresh = prev
+            assert pos == cnt // 4, (pos, cnt)
+    return cur, ladj

@@ -104,3 +104,34 @@ def test_block_program_matches_oracle(preset, d):
     xb, lb = sweep_block(blk, packed, z.numpy(), inverse=True)
     np.testing.assert_allclose(xb, xi.numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(lb, li.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("preset,d", [("maf3", 6), ("maf6", 10), ("maf3", 21), ("maf6", 32), ("maf3", 50)])
+def test_bulk_tip_stream_matches_oracle(preset, d, faithful_fp32_oracle):
+    """made_layout.build_stream_tip (experimental bulk/tip sweep, csrc/flow_tip.cu): the stream's gather map and the
+    bulk + tip decomposition of every dot product reproduce the oracle's forward and inverse."""
+    from sweep_emul import pack_stream, sweep_stream_tip
+    torch.manual_seed(100 + d)
+    flow = F.make_flow(d, preset)
+    kind, T = F.PRESETS[preset]
+    h = F.hidden_width(d)
+    assert ML.tip_supported(d, h, 3, ML.KIND_AFFINE)
+    lay = ML.build_layout(d, h, 3, T, ML.KIND_AFFINE)
+    st = ML.build_stream_tip(d, h, 3, T)
+    packed = pack_stream(st, _raw(flow))
+    x = (torch.randn(24, d) * 1.3).float()
+    with torch.no_grad():
+        z, ladj = flow().transform.call_and_ladj(x)
+        xi, li = flow().transform.inv.call_and_ladj(z)
+    zs, ls = sweep_stream_tip(lay, st, packed, x.numpy(), inverse=False)
+    np.testing.assert_allclose(zs, z.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(ls, ladj.numpy(), rtol=1e-4, atol=2e-5)
+    xs, lis = sweep_stream_tip(lay, st, packed, z.numpy(), inverse=True)
+    np.testing.assert_allclose(xs, xi.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(lis, li.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_bulk_tip_stream_support_matrix():
+    assert not ML.tip_supported(2, 32, 3, ML.KIND_AFFINE)        # one degree group of 32 units
+    assert not ML.tip_supported(32, 128, 3, ML.KIND_RQS)
+    assert ML.tip_supported(100, 512, 3, ML.KIND_AFFINE) == ML.stream_supported(100, 512, 3, ML.KIND_AFFINE)
