@@ -25,7 +25,11 @@ sweep_variant
     sweep (csrc/flow_block.cu) for affine flows: the dense part of every degree block on mma.sync
     (3xTF32), the triangular part hop by hop with register/shuffle hand-over; half the instructions of
     ``"ffma"`` but 359 us vs 331 us per 10 000-particle inverse (2.25 serial warps per scheduler at
-    68 particles per SM).  Read when a flow is constructed.
+    68 particles per SM).  ``"tip"``: experimental bulk/tip sweep (csrc/flow_tip.cu) for
+    affine flows with degree groups of <= 8 units: every dot product split into the part finished one order
+    position earlier (issued ahead, off the dependent chain) and the group born in this position (exchanged by
+    shuffles); parity green, 388 us vs 331 us per 10 000-particle inverse in its first form.
+    Read when a flow is constructed.
 forward_path
     ``"tc"`` (default): ``Flow.forward`` / ``log_prob`` without a graph run on the tcgen05 dense kernel
     (csrc/flow_tc.cu, 3xTF32 split = fp32 fidelity) when the flow is affine with H <= 128 and the batch

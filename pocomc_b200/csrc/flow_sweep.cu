@@ -878,6 +878,9 @@ namespace pmc {
 // csrc/flow_block.cu: blocked sweep (dense part on mma.sync, triangular part as short fp32 dots)
 int launch_block(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in, float* out,
                  float* ladj, long long n, int inverse, cudaStream_t st);
+// csrc/flow_tip.cu: bulk/tip sweep (experimental)
+int launch_tip(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in, float* out,
+               float* ladj, long long n, int inverse, cudaStream_t st);
 }
 
 using namespace pmc;
@@ -898,6 +901,8 @@ extern "C" int pmc_flow_sweep(const float* packed, const int32_t* meta, const in
   if (n == 0) return 0;
   const int* hm = meta_host;
   PMC_REQUIRE(hm[M_D] >= 2 && hm[M_H] >= 1 && hm[M_L] >= 1 && hm[M_T] >= 1, "pmc_flow_sweep: bad meta header");
+  if (hm[M_VERSION] == 5)
+    return launch_tip(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
   if (hm[M_VERSION] == 4)
     return launch_block(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
   if (hm[M_VERSION] == 3) {

@@ -111,6 +111,11 @@ class MaskedAutoregressiveFlow(nn.Module):
             klay = ML.build_block(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
             self.packed_numel = klay.numel
             self._pack_entry = "pmc_flow_tc_pack"                  # TF32 hi / lo images of the dense weights
+        elif config.sweep_variant == "tip" and ML.tip_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind):
+            # bulk/tip sweep (csrc/flow_tip.cu, experimental): every hop's dot product split into the part finished
+            # one order position earlier and the degree group born in this position
+            klay = ML.build_stream_tip(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+            self.packed_numel = klay.numel
         elif ML.stream_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind, lay.bins):
             klay = ML.build_stream(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins,
                                    variant="mma" if config.sweep_variant == "mma" else "ffma")
