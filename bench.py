@@ -326,7 +326,8 @@ def run_b200(args):
                     kernel="made_sweep_stream_kernel<Affine> (flow inverse, degree-ordered sweep)",
                     peak_source="MEASURED_PEAKS.json bf16 burst" if peaks else "fallback 1.59 PFLOP/s",
                     flop_per_launch=flop, avg_launch_ms=sweep_ms,
-                    note="fp32 FMA sweep on CUDA cores; 2*nnz(masks) useful FLOP per particle; share of step = "
+                    note="fp32 FMA sweep on CUDA cores, bound by shared-memory wavefronts (128 FMA per 5 wavefronts caps the FMA pipe at 20 %, "
+                         "DESIGN.md section 7); 2*nnz(masks) useful FLOP per particle; share of step = "
                          f"{sweep_ms * MCMC_STEPS * args.steps / (t_dev * 1e3):.2f}")
 
     value = n_global * MCMC_STEPS * args.steps / t_dev

@@ -304,6 +304,318 @@ made_sweep_tip_kernel(const float* __restrict__ stream, const int* __restrict__ 
   if (q == 0 && p < rows) ladj_out[row0 + p] = ladj;
 }
 
+// ---- v2: the same schedule with PPL particles per lane (register blocking) -----------------------------------
+// Arithmetic of the shared-memory pipe for the 4-lanes-per-particle mapping: one lane-row of a dot product costs an
+// LDS.128 of weights -- 4 wavefronts, each delivering only 16 distinct bytes because the 8 lanes of a slice read the
+// same float4 -- plus one wavefront of activations, for 4 FFMA warp instructions: 128 FMA per 5 wavefronts.  At one
+// wavefront per cycle per SM that caps the FMA pipe at 20 %; the stream kernel sits at 11 % with ~75 % of the
+// wavefront slots busy (58 M wavefronts in 387 us, profiles/r1c).  The sweep is shared-memory-bandwidth bound, not
+// latency bound -- which is why halving its instruction count (flow_block.cu) or cutting its dependency chain (v1
+// above) bought nothing.  With PPL particles per lane the same weight load feeds PPL x 4 FFMAs: 8 wavefronts per
+// 512 FMA at PPL = 2, 8 per 1024 at PPL = 4.  That blocking was tried in the stream kernel and lost to latency
+// (half / a quarter of the warps, each a serial chain of full dot products); with the bulk/tip split the chain is
+// short, so here it can pay.  NOT yet run on a GPU: selected only by PMC_TIP_PPL = 2 | 4.
+template <int PPL>
+__device__ __forceinline__ void dot4_partial_ppl(const float4* __restrict__ wp, const float* __restrict__ ap, int rows,
+                                                 float (&acc)[PPL][4]) {
+#pragma unroll
+  for (int e = 0; e < PPL; ++e) { acc[e][0] = 0.f; acc[e][1] = 0.f; acc[e][2] = 0.f; acc[e][3] = 0.f; }
+#pragma unroll 2
+  for (int s = 0; s < rows; s += 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = wp[4 * j];
+      float x[PPL];
+      if (PPL == 1) {
+        x[0] = ap[32 * j];
+      } else if (PPL == 2) {
+        const float2 t2 = *reinterpret_cast<const float2*>(ap + 64 * j);
+        x[0] = t2.x; x[PPL - 1] = t2.y;
+      } else {
+        const float4 t4 = *reinterpret_cast<const float4*>(ap + 128 * j);
+        x[0] = t4.x; x[1 % PPL] = t4.y; x[2 % PPL] = t4.z; x[3 % PPL] = t4.w;
+      }
+#pragma unroll
+      for (int e = 0; e < PPL; ++e) {
+        acc[e][0] = fmaf(w.x, x[e], acc[e][0]); acc[e][1] = fmaf(w.y, x[e], acc[e][1]);
+        acc[e][2] = fmaf(w.z, x[e], acc[e][2]); acc[e][3] = fmaf(w.w, x[e], acc[e][3]);
+      }
+    }
+    wp += 16; ap += 128 * PPL;
+  }
+}
+
+// consumer warps per CTA for PPL particles per lane: fewer, fatter warps leave room for the blocked accumulators
+__host__ __device__ constexpr int ppl_threads(int ppl) { return ppl == 1 ? MAX_THREADS : ppl == 2 ? 352 : 192; }
+
+template <int MAXCH, int PPL>
+__global__ void __launch_bounds__(ppl_threads(PPL), 1)
+made_sweep_tip_ppl_kernel(const float* __restrict__ stream, const int* __restrict__ meta, int meta_len,
+                          const float* __restrict__ in, float* __restrict__ out, float* __restrict__ ladj_out,
+                          long long n, int inverse, int ppc) {
+  static_assert(PPL == 1 || PPL == 2 || PPL == 4, "particles per lane");
+  constexpr int PWV = PW * PPL;                // particles per warp
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  int* sm = reinterpret_cast<int*>(smem_raw);
+  for (int i = threadIdx.x; i < meta_len; i += blockDim.x) sm[i] = meta[i];
+  __syncthreads();
+  const int D = sm[M_D], H = sm[M_H], L = sm[M_L], T = sm[M_T], ng = sm[M_NG];
+  const int Dp = (D + 15) & ~15, Hp = (H + 15) & ~15;
+  const int tstride = sm[M_TSTRIDE], nchunks = sm[M_NCHUNKS], slot_floats = sm[M_SLOT_FLOATS];
+  const int* gstart = sm + sm[M_OFF_GSTART];
+  const int* nchunk = sm + sm[M_OFF_NCHUNK];
+  const int* chunks = sm + sm[M_OFF_CHUNKS];
+  size_t off = ((size_t)meta_len * 4 + 15) & ~(size_t)15;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + off);
+  uint64_t* empty = full + NS;
+  off = (off + 2 * NS * 8 + 127) & ~(size_t)127;
+  float* ring = reinterpret_cast<float*>(smem_raw + off);
+  off += (size_t)NS * slot_floats * 4;
+  float* acts = reinterpret_cast<float*>(smem_raw + off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long cta_row0 = (long long)blockIdx.x * ppc;
+  const int cta_rows = (int)min((long long)ppc, n - cta_row0);
+  const int active = (cta_rows + PWV - 1) / PWV;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, active); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {  // ---- producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tt = 0; tt < T; ++tt) {
+        const int t = inverse ? (T - 1 - tt) : tt;
+        const float* src = stream + (size_t)t * tstride;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int slot = it % NS;
+          if (it >= NS) mbar_wait_backoff(empty + slot, ((it / NS) - 1) & 1);
+          const uint32_t bytes = (uint32_t)chunks[4 * c + 3] * 4u;
+          mbar_expect_tx(full + slot, bytes);
+          bulk_g2s(ring + (size_t)slot * slot_floats, src + chunks[4 * c + 2], bytes, full + slot);
+        }
+      }
+    }
+    return;
+  }
+  const int cw = warp - 1;
+  if (cw >= active) return;
+
+  // ---- consumers: lane = q * 8 + p carries particles p * PPL + e, e < PPL, of the warp's PWV
+  const int p = lane & 7, q = lane >> 3;
+  const int pe = p * PPL;
+  const int per_warp = (D + Dp + L * Hp) * PWV;
+  float* cur = acts + (size_t)cw * per_warp;   // [D][PWV]
+  float* xs = cur + D * PWV;                   // [Dp][PWV]
+  float* act = xs + Dp * PWV;                  // [L][Hp][PWV]
+  const long long row0 = cta_row0 + (long long)cw * PWV;
+  const int rows = (int)min((long long)PWV, n - row0);
+  for (int i = lane; i < (Dp + L * Hp) * PWV; i += 32) xs[i] = 0.0f;
+  for (int i = lane; i < PWV * D; i += 32) {
+    const int r = i / D, c = i - r * D;
+    cur[c * PWV + r] = (r < rows) ? in[row0 * D + i] : 0.0f;
+  }
+  __syncwarp();
+  const int lane_off = PPL * lane;             // row s = q + 4 j of particle pe + e sits at s * PWV + pe + e = lane_off + 32 PPL j + e
+  const float* act_last = act + (size_t)(L - 1) * Hp * PWV + lane_off;
+  float ladj[PPL];
+#pragma unroll
+  for (int e = 0; e < PPL; ++e) ladj[e] = 0.f;
+  int it = 0;
+  for (int tt = 0; tt < T; ++tt) {
+    const int t = inverse ? (T - 1 - tt) : tt;
+    const bool rev = (t & 1);
+    float bout0[PPL], bout1[PPL], fresh[4 * MAXCH][PPL];
+#pragma unroll
+    for (int e = 0; e < PPL; ++e) {
+      bout0[e] = 0.f; bout1[e] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4 * MAXCH; ++j) fresh[j][e] = 0.f;
+    }
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const int slot = it % NS;
+      mbar_wait(full + slot, (it / NS) & 1);
+      const float4* w = reinterpret_cast<const float4*>(ring + (size_t)slot * slot_floats);
+      const int k0 = chunks[4 * c], k1 = chunks[4 * c + 1];
+      for (int k = k0; k < k1; ++k) {
+        const int feat = rev ? (D - 1 - k) : k;
+        // ---- tip head
+        const int nchp = (k >= 1) ? nchunk[k - 1] : 0;
+        float phi0[PPL], phi1[PPL];
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) { phi0[e] = bout0[e]; phi1[e] = bout1[e]; }
+#pragma unroll
+        for (int cc = 0; cc < MAXCH; ++cc) {
+          if (cc < nchp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t4 = w[4 * cc + j];
+#pragma unroll
+              for (int e = 0; e < PPL; ++e) {
+                phi0[e] = fmaf(fresh[4 * cc + j][e], t4.x, phi0[e]);
+                phi1[e] = fmaf(fresh[4 * cc + j][e], t4.y, phi1[e]);
+              }
+            }
+          }
+        }
+        const float4 b4 = w[4 * nchp];
+        w += 4 * nchp + 1;
+        float xk[PPL], res[PPL];
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+          const float s0 = phi0[e] + b4.x, s1 = phi1[e] + b4.y;
+          const float v = cur[feat * PWV + pe + e];
+          const float ls = s1 / (1.0f + fabsf(s1 / LOG_SLOPE));
+          const float sc = expf(ls);
+          res[e] = inverse ? (v - s0) / sc : fmaf(v, sc, s0);
+          ladj[e] = inverse ? (ladj[e] - ls) : (ladj[e] + ls);
+          xk[e] = inverse ? res[e] : v;
+        }
+        const int g = k + 1;
+        const bool has_group = g <= ng;
+        // ---- bulk phase
+        const int nch = has_group ? nchunk[k] : 0;
+        const int ek16 = (gstart[k] + 15) & ~15;
+        const int k16 = (k + 15) & ~15;
+        float bulk[MAXL][MAXCH][PPL];
+#pragma unroll
+        for (int l_ = 0; l_ < MAXL; ++l_)
+#pragma unroll
+          for (int cc = 0; cc < MAXCH; ++cc)
+#pragma unroll
+            for (int e = 0; e < PPL; ++e) bulk[l_][cc][e] = 0.f;
+        if (has_group) {
+#pragma unroll
+          for (int l_ = 0; l_ < MAXL; ++l_) {
+            if (l_ < L) {
+              const int nrows = (l_ == 0) ? k16 : ek16;
+              const float* src = (l_ == 0) ? (xs + lane_off) : (act + (size_t)(l_ - 1) * Hp * PWV + lane_off);
+#pragma unroll
+              for (int cc = 0; cc < MAXCH; ++cc) {
+                if (cc < nch) {
+                  float acc[PPL][4];
+                  dot4_partial_ppl<PPL>(w + q, src, nrows, acc);
+                  w += nrows;
+#pragma unroll
+                  for (int e = 0; e < PPL; ++e) bulk[l_][cc][e] = reduce_scatter4(acc[e], lane);
+                }
+              }
+            }
+          }
+        }
+        float nb0[PPL], nb1[PPL];
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) { nb0[e] = 0.f; nb1[e] = 0.f; }
+        if (k + 1 < D) {
+          float acc[PPL][4];
+          dot4_partial_ppl<PPL>(w + q, act_last, ek16, acc);
+          w += ek16;
+#pragma unroll
+          for (int e = 0; e < PPL; ++e) {
+            float a0 = acc[e][0] + __shfl_xor_sync(FULL, acc[e][0], 8);
+            float a1 = acc[e][1] + __shfl_xor_sync(FULL, acc[e][1], 8);
+            a0 += __shfl_xor_sync(FULL, a0, 16);
+            a1 += __shfl_xor_sync(FULL, a1, 16);
+            nb0[e] = a0; nb1[e] = a1;
+          }
+        }
+        __syncwarp();
+        if (q == 0) {
+#pragma unroll
+          for (int e = 0; e < PPL; ++e) {
+            xs[k * PWV + pe + e] = xk[e];
+            cur[feat * PWV + pe + e] = res[e];
+          }
+        }
+        // ---- tips
+        if (has_group) {
+          const int gs = gstart[k], gsz = gstart[k + 1] - gs;
+          float mine[MAXCH][PPL], prev[4 * MAXCH][PPL];
+#pragma unroll
+          for (int e = 0; e < PPL; ++e) {
+#pragma unroll
+            for (int j = 0; j < 4 * MAXCH; ++j) prev[j][e] = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < MAXCH; ++cc) mine[cc][e] = 0.f;
+          }
+#pragma unroll
+          for (int l_ = 0; l_ < MAXL; ++l_) {
+            if (l_ < L) {
+              float* dst = act + (size_t)l_ * Hp * PWV;
+              const int stride = (l_ == 0) ? 1 : (1 + nch);
+              float nw[MAXCH][PPL];
+#pragma unroll
+              for (int cc = 0; cc < MAXCH; ++cc) {
+#pragma unroll
+                for (int e = 0; e < PPL; ++e) nw[cc][e] = 0.f;
+                if (cc < nch) {
+                  const float4* base = w + (size_t)(4 * cc + q) * stride;
+                  const float4 head = base[0];
+                  float pre[PPL];
+#pragma unroll
+                  for (int e = 0; e < PPL; ++e) pre[e] = bulk[l_][cc][e] + head.x;
+                  if (l_ == 0) {
+#pragma unroll
+                    for (int e = 0; e < PPL; ++e) pre[e] = fmaf(head.y, xk[e], pre[e]);
+                  } else {
+#pragma unroll
+                    for (int c2 = 0; c2 < MAXCH; ++c2) {
+                      if (c2 < nch) {
+                        const float4 t4 = base[1 + c2];
+#pragma unroll
+                        for (int e = 0; e < PPL; ++e) {
+                          pre[e] = fmaf(t4.x, prev[4 * c2 + 0][e], pre[e]); pre[e] = fmaf(t4.y, prev[4 * c2 + 1][e], pre[e]);
+                          pre[e] = fmaf(t4.z, prev[4 * c2 + 2][e], pre[e]); pre[e] = fmaf(t4.w, prev[4 * c2 + 3][e], pre[e]);
+                        }
+                      }
+                    }
+#pragma unroll
+                    for (int e = 0; e < PPL; ++e) pre[e] += mine[cc][e];
+                  }
+#pragma unroll
+                  for (int e = 0; e < PPL; ++e) {
+                    nw[cc][e] = fmaxf(pre[e], 0.f);
+                    if (4 * cc + q < gsz) dst[(gs + 4 * cc + q) * PWV + pe + e] = nw[cc][e];
+                  }
+                }
+              }
+              w += (size_t)4 * nch * stride;
+#pragma unroll
+              for (int cc = 0; cc < MAXCH; ++cc)
+#pragma unroll
+                for (int e = 0; e < PPL; ++e) {
+                  mine[cc][e] = nw[cc][e];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) prev[4 * cc + j][e] = __shfl_sync(FULL, nw[cc][e], 8 * j + p);
+                }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4 * MAXCH; ++j)
+#pragma unroll
+            for (int e = 0; e < PPL; ++e) fresh[j][e] = prev[j][e];
+        }
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) { bout0[e] = nb0[e]; bout1[e] = nb1[e]; }
+        __syncwarp();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+    }
+  }
+  for (int i = lane; i < PWV * D; i += 32) {
+    const int r = i / D, c = i - r * D;
+    if (r < rows) out[row0 * D + i] = cur[c * PWV + r];
+  }
+  if (q == 0) {
+#pragma unroll
+    for (int e = 0; e < PPL; ++e)
+      if (pe + e < rows) ladj_out[row0 + pe + e] = ladj[e];
+  }
+}
+
 }  // namespace tip
 
 int launch_tip(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in, float* out,
@@ -319,20 +631,35 @@ int launch_tip(const float* stream, const int* meta, int meta_len, const int* hm
   const int sms = sm_count();
   const long long max_smem = (long long)((budget - fixed) / per_particle);
   const long long per_sm = (n + sms - 1) / sms;
-  long long cap = std::min<long long>(max_smem, (long long)(MAX_THREADS / 32 - 1) * PW) / PW * PW;
+  int ppl = 1;                                                    // particles per lane: 1 = the validated kernel
+  if (const char* e = getenv("PMC_TIP_PPL")) ppl = atoi(e);
+  PMC_REQUIRE(ppl == 1 || ppl == 2 || ppl == 4, "pmc_flow_sweep: PMC_TIP_PPL must be 1, 2 or 4");
+  const int pw = PW * ppl;
+  PMC_REQUIRE(max_smem >= pw, "pmc_flow_sweep: flow too large for this many particles per lane");
+  long long cap = std::min<long long>(max_smem, (long long)(ppl_threads(ppl) / 32 - 1) * pw) / pw * pw;
   const long long waves = (per_sm + cap - 1) / cap;
   long long ppc = (n + waves * sms - 1) / (waves * sms);
-  ppc = std::min(cap, (ppc + PW - 1) / PW * PW);
+  ppc = std::min(cap, (ppc + pw - 1) / pw * pw);
   const long long grid = (n + ppc - 1) / ppc;
-  const int threads = 32 * (1 + (int)(ppc / PW));
+  const int threads = 32 * (1 + (int)(ppc / pw));
   const size_t smem = fixed + (size_t)ppc * per_particle;
-  if (hmeta[M_MAXCH] == 1) {
-    PMC_TRY(cudaFuncSetAttribute(made_sweep_tip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    made_sweep_tip_kernel<1><<<(unsigned)grid, threads, smem, st>>>(stream, meta, meta_len, in, out, ladj, n, inverse, (int)ppc);
+  const int mc = hmeta[M_MAXCH];
+#define PMC_TIP_LAUNCH(KERN)                                                                          \
+  do {                                                                                                 \
+    PMC_TRY(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    KERN<<<(unsigned)grid, threads, smem, st>>>(stream, meta, meta_len, in, out, ladj, n, inverse, (int)ppc); \
+  } while (0)
+  if (ppl == 1) {
+    if (mc == 1) PMC_TIP_LAUNCH(made_sweep_tip_kernel<1>);
+    else PMC_TIP_LAUNCH(made_sweep_tip_kernel<2>);
+  } else if (ppl == 2) {
+    if (mc == 1) PMC_TIP_LAUNCH((made_sweep_tip_ppl_kernel<1, 2>));
+    else PMC_TIP_LAUNCH((made_sweep_tip_ppl_kernel<2, 2>));
   } else {
-    PMC_TRY(cudaFuncSetAttribute(made_sweep_tip_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    made_sweep_tip_kernel<2><<<(unsigned)grid, threads, smem, st>>>(stream, meta, meta_len, in, out, ladj, n, inverse, (int)ppc);
+    if (mc == 1) PMC_TIP_LAUNCH((made_sweep_tip_ppl_kernel<1, 4>));
+    else PMC_TIP_LAUNCH((made_sweep_tip_ppl_kernel<2, 4>));
   }
+#undef PMC_TIP_LAUNCH
   PMC_LAUNCH_CHECK();
   return 0;
 }
