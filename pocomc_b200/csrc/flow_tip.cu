@@ -19,7 +19,7 @@
 // (lane = q * 8 + p), same TMA-fed ring, same activation arrays [unit][8 particles] for the bulk reads.
 //
 // Status (round 1): layout and decomposition pinned against the oracle on the CPU (tests/sweep_emul.py:
-// sweep_stream_tip), kernel parity-green on B200 (tests/test_gpu_flow.py::test_bulk_tip_sweep_matches_oracle), but
+// sweep_stream_tip), kernel parity-green on B200 (tests/test_zz_gpu_experimental.py::test_bulk_tip_sweep_matches_oracle), but
 // SLOWER than the stream kernel in its first form: 388 us vs 331 us per 10 000-particle maf6 / 32-D inverse.  The
 // dependent chain is shorter, the instruction stream is not (bulk dots + a reduce-scatter per chunk + shuffle
 // exchanges), and no ncu capture exists yet -- the default stays the stream kernel.
