@@ -9,13 +9,15 @@ contributes its fixed-size per-256-row block partials, they are all-gathered in 
 particle) order and summed in that fixed order by every rank."""
 from __future__ import annotations
 
+import math
 import os
 
+import numpy as np
 import torch
 import torch.distributed as td
 
 __all__ = ["init_from_env", "is_active", "world", "shard_range", "shard_counts", "gather_blocks", "allreduce_sum_det",
-           "allreduce_sum_int"]
+           "allreduce_sum_int", "merge_weight_stats", "combine_weight_stats"]
 
 
 def init_from_env(backend: str = None):
@@ -108,3 +110,39 @@ def allreduce_sum_int(value: int) -> int:
     t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
     td.all_reduce(t)
     return int(t.item())
+
+
+def merge_weight_stats(parts: np.ndarray) -> np.ndarray:
+    """Merge per-shard (max logw, sum e, sum e^2) triples -- e = exp(logw - max) over the shard, what
+    ``pmc_ps_reduce`` returns in out4[0:3] -- into the triple of the whole history, shard by shard in the
+    given order with the rule of csrc/smc_ops.cu ``Lse3::merge`` (rescale the sums of the smaller maximum).
+    Shards without finite weights (max = -inf) are skipped.  float64 throughout; pure host arithmetic."""
+    parts = np.asarray(parts, dtype=np.float64).reshape(-1, 3)
+    m, s1, s2 = -np.inf, 0.0, 0.0
+    for om, o1, o2 in parts:
+        if om == -np.inf:
+            continue
+        if m == -np.inf:
+            m, s1, s2 = float(om), float(o1), float(o2)
+        elif om <= m:
+            c = math.exp(om - m)
+            s1 += o1 * c
+            s2 += o2 * c * c
+        else:
+            c = math.exp(m - om)
+            s1 = s1 * c + o1
+            s2 = s2 * c * c + o2
+            m = float(om)
+    return np.array([m, s1, s2], dtype=np.float64)
+
+
+def combine_weight_stats(local3: torch.Tensor) -> torch.Tensor:
+    """Sharded history ("every bisection probe"): every rank reduces its own slice of the
+    history to (max, sum e, sum e^2); the triples are all-gathered and merged in rank order, so every rank
+    holds the same global triple (hence the same ESS = s1^2 / s2 and log Z = max + log s1 - log(T N)) and
+    takes the same branch of the bisection.  One 24-byte all-gather per probe."""
+    if not is_active():
+        return local3
+    g = gather_blocks(local3.reshape(1, 3).to(torch.float64))
+    merged = merge_weight_stats(g.detach().cpu().numpy())
+    return torch.from_numpy(merged).to(local3.device)

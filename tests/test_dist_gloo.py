@@ -45,6 +45,19 @@ def _worker(rank, world, port, out):
     back = dist.gather_blocks(torch.from_numpy(rows_all[a:b].copy()), cnt)
     ok &= np.array_equal(back.numpy(), rows_all)
     ok &= dist.allreduce_sum_int(10 ** 12 + rank) == 2 * 10 ** 12 + 1
+    # persistent-sampling probe over a history sharded by particle: local (max, sum e, sum e^2) -> global triple,
+    # identical on every rank and equal to the single-process reduction of the whole history
+    logw = np.random.default_rng(5).normal(size=(6, n)) * 30.0            # [T, N] with a huge dynamic range
+    mine_lw = logw[:, a:b].reshape(-1)
+    mx = mine_lw.max()
+    e = np.exp(mine_lw - mx)
+    got = dist.combine_weight_stats(torch.tensor([mx, e.sum(), (e * e).sum()], dtype=torch.float64)).numpy()
+    allw = logw.reshape(-1)
+    eg = np.exp(allw - allw.max())
+    want = np.array([allw.max(), eg.sum(), (eg * eg).sum()])
+    ok &= got[0] == want[0] and bool(np.allclose(got[1:], want[1:], rtol=1e-13, atol=0.0))
+    both = dist.gather_blocks(torch.from_numpy(got.reshape(1, 3).copy()))
+    ok &= bool(torch.equal(both[0], both[1]))                              # bit-identical on the two ranks
     out[rank] = bool(ok)
     td.destroy_process_group()
 
@@ -66,3 +79,27 @@ def test_gather_and_deterministic_sum_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)), dict(out)
+
+
+def test_merge_weight_stats_rule():
+    """the host mirror of csrc/smc_ops.cu Lse3::merge: order of the maxima, empty shards, associativity to rounding"""
+    from pocomc_b200 import dist
+    rng = np.random.default_rng(1)
+    lw = rng.normal(size=5000) * 50.0
+    cuts = [0, 17, 17, 2000, 4999, 5000]                                     # includes an empty shard
+    parts = []
+    for lo, hi in zip(cuts, cuts[1:]):
+        seg = lw[lo:hi]
+        if seg.size == 0:
+            parts.append([-np.inf, 0.0, 0.0])
+            continue
+        e = np.exp(seg - seg.max())
+        parts.append([seg.max(), e.sum(), (e * e).sum()])
+    got = dist.merge_weight_stats(np.array(parts))
+    e = np.exp(lw - lw.max())
+    np.testing.assert_equal(got[0], lw.max())
+    np.testing.assert_allclose(got[1:], [e.sum(), (e * e).sum()], rtol=1e-13)
+    np.testing.assert_array_equal(dist.merge_weight_stats(np.array([[-np.inf, 0.0, 0.0]])), [-np.inf, 0.0, 0.0])
+    # without a process group the combine is the identity
+    t = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    assert dist.combine_weight_stats(t) is t
