@@ -17,7 +17,8 @@ import torch
 import torch.distributed as td
 
 __all__ = ["init_from_env", "is_active", "world", "shard_range", "shard_counts", "gather_blocks", "allreduce_sum_det",
-           "allreduce_sum_int", "merge_weight_stats", "combine_weight_stats"]
+           "allreduce_sum_int", "merge_weight_stats", "combine_weight_stats",
+           "gather_history_scalars", "split_history_index"]
 
 
 def init_from_env(backend: str = None):
@@ -146,3 +147,30 @@ def combine_weight_stats(local3: torch.Tensor) -> torch.Tensor:
     g = gather_blocks(local3.reshape(1, 3).to(torch.float64))
     merged = merge_weight_stats(g.detach().cpu().numpy())
     return torch.from_numpy(merged).to(local3.device)
+
+
+def gather_history_scalars(local: torch.Tensor, counts) -> torch.Tensor:
+    """History sharded by particle: every rank holds ``local [T, n_r]`` (one scalar per stored particle of its
+    block, e.g. the persistent-sampling log-weights); returns the full ``[T, N]`` array in global particle
+    order on every rank.  The bit-exact weight trimming (tools.trim_weights: global percentiles with numpy's
+    linear interpolation) runs redundantly on this array -- 8 bytes per history element instead of the
+    (2 D + 3) x 8 of the particle rows, which stay sharded."""
+    if not is_active():
+        return local
+    rows = gather_blocks(local.t().contiguous(), list(counts))        # [N, T], rank blocks = particle blocks
+    return rows.t().contiguous()
+
+
+def split_history_index(idx: np.ndarray, n_total: int, counts) -> tuple:
+    """Global flat history indices ``i = t * N + j`` (iteration t, particle j; what the trim / resampling
+    kernels return) -> (owner rank of every index, flat index ``t * n_r + (j - lo_r)`` into that rank's
+    ``[T, n_r]`` shard).  Pure index arithmetic, identical on every rank."""
+    idx = np.asarray(idx, dtype=np.int64)
+    counts = np.asarray(list(counts), dtype=np.int64)
+    if counts.sum() != n_total:
+        raise ValueError("shard counts do not add up to the number of particles")
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    t, j = np.divmod(idx, n_total)
+    owner = np.searchsorted(starts, j, side="right") - 1
+    local = t * counts[owner] + (j - starts[owner])
+    return owner, local

@@ -58,6 +58,18 @@ def _worker(rank, world, port, out):
     ok &= got[0] == want[0] and bool(np.allclose(got[1:], want[1:], rtol=1e-13, atol=0.0))
     both = dist.gather_blocks(torch.from_numpy(got.reshape(1, 3).copy()))
     ok &= bool(torch.equal(both[0], both[1]))                              # bit-identical on the two ranks
+    # scalars of the sharded history come back as [T, N] in global particle order; global trim / resampling
+    # indices map to (owner, local flat index) and every selected row is found exactly once
+    full = dist.gather_history_scalars(torch.from_numpy(logw[:, a:b].copy()), cnt)
+    ok &= np.array_equal(full.numpy(), logw)
+    pick = np.sort(np.random.default_rng(6).choice(logw.size, size=500, replace=False))
+    owner, local = dist.split_history_index(pick, n, cnt)
+    mine_sel = local[owner == rank]
+    vals = torch.from_numpy(logw[:, a:b].reshape(-1)[mine_sel].copy()).reshape(-1, 1)
+    sel_counts = [int((owner == r).sum()) for r in range(world)]
+    back_vals = dist.gather_blocks(vals, sel_counts).numpy().reshape(-1)
+    want_vals = np.concatenate([logw.reshape(-1)[pick[owner == r]] for r in range(world)])
+    ok &= np.array_equal(back_vals, want_vals) and sum(sel_counts) == 500
     out[rank] = bool(ok)
     td.destroy_process_group()
 
@@ -103,3 +115,19 @@ def test_merge_weight_stats_rule():
     # without a process group the combine is the identity
     t = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
     assert dist.combine_weight_stats(t) is t
+
+
+def test_split_history_index_arithmetic():
+    from pocomc_b200 import dist
+    n, T, counts = 10, 4, [3, 0, 5, 2]
+    idx = np.arange(n * T)
+    owner, local = dist.split_history_index(idx, n, counts)
+    hist = np.arange(n * T).reshape(T, n)                                    # value = global flat index
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    for r, c in enumerate(counts):
+        shard = hist[:, starts[r]:starts[r] + c].reshape(-1)
+        np.testing.assert_array_equal(shard[local[owner == r]], idx[owner == r])
+    assert not np.any(owner == 1)                                            # the empty shard owns nothing
+    import pytest
+    with pytest.raises(ValueError):
+        dist.split_history_index(idx, n, [3, 3])
