@@ -447,3 +447,163 @@ def sweep_stream_tip(layout, stream, packed, x, inverse):
                     fresh = prev
             assert pos == cnt // 4, (pos, cnt)
     return cur, ladj
+
+
+def sweep_tip_lanes(stream, packed, x, inverse, ppl=1):
+    """Lane-level transliteration of csrc/flow_tip.cu (made_sweep_tip_kernel for ppl = 1, made_sweep_tip_ppl_kernel
+    for ppl = 2 | 4): one warp = 32 lanes, lane = q * 8 + p carrying particles p * ppl + e; shared memory as flat
+    float arrays with the kernel's index expressions, shuffles as lane permutations.  Pins the lane mapping
+    (activation addressing of the blocked dot products, reduce-scatter, shuffle exchange, guarded writes, stream
+    pointer arithmetic) on the CPU; x may hold any number of rows (processed warp tile by warp tile)."""
+    m = stream.meta
+    assert int(m[ML.M_VERSION]) == 5
+    D, H, L, T, ng = (int(m[i]) for i in (ML.M_D, ML.M_H, ML.M_L, ML.M_T, ML.M_NG))
+    Dp, Hp = (D + 15) // 16 * 16, (H + 15) // 16 * 16
+    gstart = m[m[ML.M_OFF_GSTART]:m[ML.M_OFF_GSTART] + ng + 1].astype(np.int64)
+    nchunk = m[m[ML.M_OFF_NCHUNK]:m[ML.M_OFF_NCHUNK] + ng].astype(np.int64)
+    chunks = m[m[ML.M_OFF_CHUNKS]:m[ML.M_OFF_CHUNKS] + 4 * m[ML.M_NCHUNKS]].reshape(-1, 4)
+    maxch = int(m[ML.M_MAXCH])
+    PWV = 8 * ppl
+    lane = np.arange(32)
+    p_, q_ = lane & 7, lane >> 3
+    pe = p_ * ppl
+    lane_off = ppl * lane
+    f32 = np.float32
+    LS = f32(math.log(1e-3))
+    x = np.asarray(x, f32)
+    n = len(x)
+    out = np.zeros_like(x)
+    ladj_out = np.zeros(n, f32)
+
+    def shfl(v, src):                      # __shfl_sync(FULL, v, src): v [32] per-lane values
+        return v[src]
+
+    def dot4(w4, wpos, src, base, rows):
+        """dot4_partial(_ppl): acc[lane, e, 4]"""
+        acc = np.zeros((32, ppl, 4), f32)
+        wp, ap = wpos + q_, base + lane_off
+        for _ in range(0, rows, 16):
+            for j in range(4):
+                w = w4[wp + 4 * j]                                        # [32, 4]
+                for e in range(ppl):
+                    xv = src[ap + 32 * ppl * j + e]
+                    acc[:, e, :] += w * xv[:, None]
+            wp = wp + 16
+            ap = ap + 128 * ppl
+        return acc
+
+    def reduce_scatter4(a):                # a [32, 4] -> [32]: lane q ends with unit q's total
+        hi = (lane & 16) != 0
+        k0 = np.where(hi, a[:, 2], a[:, 0]) + shfl(np.where(hi, a[:, 0], a[:, 2]), lane ^ 16)
+        k1 = np.where(hi, a[:, 3], a[:, 1]) + shfl(np.where(hi, a[:, 1], a[:, 3]), lane ^ 16)
+        mid = (lane & 8) != 0
+        return np.where(mid, k1, k0) + shfl(np.where(mid, k0, k1), lane ^ 8)
+
+    for row0 in range(0, n, PWV):
+        rows = min(PWV, n - row0)
+        cur = np.zeros(D * PWV, f32)
+        xs = np.zeros(Dp * PWV, f32)
+        act = np.zeros(L * Hp * PWV, f32)
+        for r in range(rows):
+            for c in range(D):
+                cur[c * PWV + r] = x[row0 + r, c]
+        ladj = np.zeros((32, ppl), f32)
+        for tt in range(T):
+            t = T - 1 - tt if inverse else tt
+            rev = bool(t & 1)
+            bout = np.zeros((32, ppl, 2), f32)
+            fresh = np.zeros((32, 4 * maxch, ppl), f32)
+            for k0, k1, off, cnt in chunks:
+                w4 = packed[t * stream.tstride + off: t * stream.tstride + off + cnt].reshape(-1, 4)
+                w = 0
+                for k in range(k0, k1):
+                    feat = D - 1 - k if rev else k
+                    nchp = int(nchunk[k - 1]) if k >= 1 else 0
+                    phi = bout.copy()
+                    for cc in range(nchp):
+                        for j in range(4):
+                            t4 = w4[w + 4 * cc + j]
+                            for e in range(ppl):
+                                phi[:, e, 0] += fresh[:, 4 * cc + j, e] * t4[0]
+                                phi[:, e, 1] += fresh[:, 4 * cc + j, e] * t4[1]
+                    b4 = w4[w + 4 * nchp]
+                    w += 4 * nchp + 1
+                    xk = np.zeros((32, ppl), f32)
+                    res = np.zeros((32, ppl), f32)
+                    for e in range(ppl):
+                        s0, s1 = phi[:, e, 0] + b4[0], phi[:, e, 1] + b4[1]
+                        v = cur[feat * PWV + pe + e]
+                        ls = (s1 / (f32(1) + np.abs(s1 / LS))).astype(f32)
+                        sc = np.exp(ls).astype(f32)
+                        res[:, e] = (v - s0) / sc if inverse else v * sc + s0
+                        ladj[:, e] = ladj[:, e] - ls if inverse else ladj[:, e] + ls
+                        xk[:, e] = res[:, e] if inverse else v
+                    g = k + 1
+                    has_group = g <= ng
+                    nch = int(nchunk[k]) if has_group else 0
+                    ek16 = (int(gstart[k]) + 15) // 16 * 16
+                    k16 = (k + 15) // 16 * 16
+                    bulk = np.zeros((L, maxch, 32, ppl), f32)
+                    if has_group:
+                        for l_ in range(L):
+                            nrows = k16 if l_ == 0 else ek16
+                            src, base = (xs, 0) if l_ == 0 else (act, (l_ - 1) * Hp * PWV)
+                            for cc in range(nch):
+                                acc = dot4(w4, w, src, base, nrows)
+                                w += nrows
+                                for e in range(ppl):
+                                    bulk[l_, cc, :, e] = reduce_scatter4(acc[:, e, :])
+                    nb = np.zeros((32, ppl, 2), f32)
+                    if k + 1 < D:
+                        acc = dot4(w4, w, act, (L - 1) * Hp * PWV, ek16)
+                        w += ek16
+                        for e in range(ppl):
+                            for o in range(2):
+                                a = acc[:, e, o] + shfl(acc[:, e, o], lane ^ 8)
+                                nb[:, e, o] = a + shfl(a, lane ^ 16)
+                    for ln in np.nonzero(q_ == 0)[0]:
+                        for e in range(ppl):
+                            xs[k * PWV + pe[ln] + e] = xk[ln, e]
+                            cur[feat * PWV + pe[ln] + e] = res[ln, e]
+                    if has_group:
+                        gs, gsz = int(gstart[k]), int(gstart[k + 1] - gstart[k])
+                        mine = np.zeros((maxch, 32, ppl), f32)
+                        prev = np.zeros((4 * maxch, 32, ppl), f32)
+                        for l_ in range(L):
+                            stride = 1 if l_ == 0 else 1 + nch
+                            nw = np.zeros((maxch, 32, ppl), f32)
+                            for cc in range(nch):
+                                base = w + (4 * cc + q_) * stride                   # per lane
+                                head = w4[base]
+                                for e in range(ppl):
+                                    pre = bulk[l_, cc, :, e] + head[:, 0]
+                                    if l_ == 0:
+                                        pre = pre + head[:, 1] * xk[:, e]
+                                    else:
+                                        for c2 in range(nch):
+                                            t4 = w4[base + 1 + c2]
+                                            for jj in range(4):
+                                                pre = pre + t4[:, jj] * prev[4 * c2 + jj, :, e]
+                                        pre = pre + mine[cc, :, e]
+                                    nw[cc, :, e] = np.maximum(pre, 0)
+                                    for ln in range(32):
+                                        if 4 * cc + q_[ln] < gsz:
+                                            act[l_ * Hp * PWV + (gs + 4 * cc + q_[ln]) * PWV + pe[ln] + e] = nw[cc, ln, e]
+                            w += 4 * nch * stride
+                            for cc in range(maxch):
+                                for e in range(ppl):
+                                    mine[cc, :, e] = nw[cc, :, e]
+                                    for j in range(4):
+                                        prev[4 * cc + j, :, e] = shfl(nw[cc, :, e], 8 * j + p_)
+                        for j in range(4 * maxch):
+                            fresh[:, j, :] = prev[j]
+                    bout = nb
+                assert w == cnt // 4
+        for r in range(rows):
+            for c in range(D):
+                out[row0 + r, c] = cur[c * PWV + r]
+        for ln in np.nonzero(q_ == 0)[0]:
+            for e in range(ppl):
+                if pe[ln] + e < rows:
+                    ladj_out[row0 + pe[ln] + e] = ladj[ln, e]
+    return out, ladj_out

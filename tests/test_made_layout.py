@@ -135,3 +135,26 @@ def test_bulk_tip_stream_support_matrix():
     assert not ML.tip_supported(2, 32, 3, ML.KIND_AFFINE)        # one degree group of 32 units
     assert not ML.tip_supported(32, 128, 3, ML.KIND_RQS)
     assert ML.tip_supported(100, 512, 3, ML.KIND_AFFINE) == ML.stream_supported(100, 512, 3, ML.KIND_AFFINE)
+
+
+@pytest.mark.parametrize("ppl", [1, 2, 4])
+@pytest.mark.parametrize("preset,d,n", [("maf3", 6, 11), ("maf3", 21, 37)])
+def test_bulk_tip_lane_mapping(preset, d, n, ppl, faithful_fp32_oracle):
+    """Lane-level transliteration of csrc/flow_tip.cu (32 lanes, shuffles, the kernel's shared-memory index
+    expressions) for 1, 2 and 4 particles per lane against the oracle, ragged last warp tile included."""
+    from sweep_emul import pack_stream, sweep_tip_lanes
+    torch.manual_seed(7 * d + ppl)
+    flow = F.make_flow(d, preset)
+    kind, T = F.PRESETS[preset]
+    st = ML.build_stream_tip(d, F.hidden_width(d), 3, T)
+    packed = pack_stream(st, _raw(flow))
+    x = (torch.randn(n, d) * 1.2).float()
+    with torch.no_grad():
+        z, ladj = flow().transform.call_and_ladj(x)
+        xi, li = flow().transform.inv.call_and_ladj(z)
+    zs, ls = sweep_tip_lanes(st, packed, x.numpy(), False, ppl)
+    np.testing.assert_allclose(zs, z.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(ls, ladj.numpy(), rtol=1e-4, atol=2e-5)
+    xs, lis = sweep_tip_lanes(st, packed, z.numpy(), True, ppl)
+    np.testing.assert_allclose(xs, xi.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(lis, li.numpy(), rtol=1e-4, atol=1e-4)
