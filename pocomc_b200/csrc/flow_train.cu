@@ -4,7 +4,7 @@
 // The reference builds this with torch autograd over ~70 small ops per transform; the batch is at most
 // 512 rows (sampler.py:289), so the step is launch- and latency-bound, not throughput-bound.  Here:
 //
-//   flow_train_fb_kernel : one CTA per 32 batch rows runs the WHOLE forward chain (T transforms x (L+1)
+//   flow_train_fb_kernel<ROWS> : one CTA per ROWS = 8 / 16 / 32 batch rows runs the WHOLE forward chain (T transforms x (L+1)
 //       masked linear layers + affine map) and the WHOLE input-gradient chain back, fp32 FMA.  Weight
 //       images (mask folded in, transposed as each GEMM wants them; built by pmc_flow_pack from the
 //       flat blob) stream through a double-buffered shared-memory slot with 1-D bulk copies
@@ -12,8 +12,9 @@
 //       shared memory transposed ([feature][row]) so the inner product loop is one broadcast LDS.128
 //       plus conflict-free LDS.32s per k.  Activations / pre-activation gradients are also written to a
 //       global scratch for the weight-gradient pass.
-//   flow_train_wgrad_kernel : grouped GEMM dW = dpre^T . input over the whole batch, one 32x32 tile of
-//       one layer per CTA, scattered straight into the flat gradient blob (no atomics, deterministic).
+//   flow_train_wgrad_kernel<CH> : grouped GEMM dW = dpre^T . input over the whole batch (CH-row chunks fetched one
+//       ahead), one 32x32 tile of one layer per CTA, scattered straight into the flat gradient blob (no atomics,
+//       deterministic).
 //
 // Arithmetic matches the autograd path operation for operation (fp32, same association up to the
 // order of the k-loop); parity is tested against the oracle's gradients.
