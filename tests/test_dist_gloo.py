@@ -87,7 +87,7 @@ def test_shard_range_covers_everything():
 def test_gather_and_deterministic_sum_world2():
     world = 2
     port = _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # never fork a multi-threaded (CUDA) parent
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)), dict(out)

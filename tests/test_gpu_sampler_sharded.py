@@ -69,7 +69,7 @@ def test_sharded_run_equals_single_process(kwargs):
         config.mean_mode = None
         os.environ.pop("PMC_SWEEP_LPP", None)
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # never fork a multi-threaded (CUDA) parent
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), kwargs, out), nprocs=world, join=True)
     for r in range(world):
