@@ -52,6 +52,7 @@ struct TrainParams {
   int cpb;                   // CTAs per batch (Bp / ROWS): a forward-only launch may cover several consecutive batches
   int ns;                    // weight ring depth (2..8 slots)
   int wslot;                 // floats per ring slot: the largest image, or less -- images then stream in k-chunks
+  int splitk;                // experimental (PMC_TRAIN_SPLITK=1): hidden-width GEMMs split K over the column groups too
 };
 
 // acc[i][j] += sum_k At[k][4 rg + i] * W[k][c0 + CSTR j]   (k over the rows of one streamed chunk of the image, N floats per row)
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
   // the columns stay whole (tx + 32 j) and the K rows of every chunk are dealt over the column groups instead
   // (split-K); the partial sums meet in `red` and the lead
   // warps (cg == 0) add them in group order, so the result does not depend on timing.
+  const bool wide_splitk = (CG > 1) && p.splitk;
   auto stream_gemm = [&](bool wide, int tn, const float* in, int K, int N, int bias, float* red) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -180,14 +182,41 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
       const int rows = min(kc, K - k0);
       mbar_wait(full + (s % NS), (s / NS) & 1);
       wl = wring + (size_t)(s % NS) * wmax;
-      if (wide) {
+      if (wide && !wide_splitk) {
         gemm_any<CSW, TR_LDA>(tn, in + k0 * TR_LDA, rows, wl, N, ty, cw0, acc);
+      } else if (wide) {
+        // every warp: ALL column tiles of its 4 rows (a 4 x 4 register tile per lane and k: one broadcast LDS.128 of
+        // activations per 16 FFMA instead of per 4) over its quarter of the k rows
+        const int lo = cg * rows / CG, hi = (cg + 1) * rows / CG;
+        gemm_any<32, TR_LDA>(tn * CG, in + (k0 + lo) * TR_LDA, hi - lo, wl + lo * N, N, ty, tx, acc);
       } else {
         const int lo = cg * rows / CG, hi = (cg + 1) * rows / CG;
         gemm_any<32, TR_LDA>(tn, in + (k0 + lo) * TR_LDA, hi - lo, wl + lo * N, N, ty, tx, acc);
       }
       rows_last = rows;
       if (k0 + rows < K) release();
+    }
+    if (wide && wide_splitk) {
+      // partial sums of every warp -> red[cg][column][row]; then warp (rg, cg) sums ITS column tiles cg + CG j over the
+      // CG partials in group order (deterministic) and carries on as the owner of those columns, like the plain path
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j >= tn * CG) continue;
+        *reinterpret_cast<float4*>(red + ((size_t)(cg * N + tx + 32 * j) * TR_ROWS + 4 * ty)) =
+            make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j >= tn) continue;
+        const int c = cw0 + CSW * j;
+        float4 sum = *reinterpret_cast<const float4*>(red + ((size_t)c * TR_ROWS + 4 * ty));
+        for (int c2 = 1; c2 < CG; ++c2) {
+          const float4 v = *reinterpret_cast<const float4*>(red + ((size_t)(c2 * N + c) * TR_ROWS + 4 * ty));
+          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        acc[0][j] = sum.x; acc[1][j] = sum.y; acc[2][j] = sum.z; acc[3][j] = sum.w;
+      }
     }
     if (!wide && CG > 1) {
       if (!lead) {
@@ -247,7 +276,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float* in = xT;
     float* out = bufA;
     for (int l = 0; l < L; ++l) {
-      stream_gemm(true, tnW, in, (l == 0) ? D : H, H, 1, nullptr);
+      stream_gemm(true, tnW, in, (l == 0) ? D : H, H, 1, redbuf);
       const float* bias = wl + rows_last * H;                 // bias rides behind the last weight rows in the same bulk copy
       float* hs = p.Hs + ((size_t)(t * L + l) * Bp + row0 + 4 * ty) * H;
       uint32_t bits = 0;
@@ -410,7 +439,7 @@ __global__ void __launch_bounds__(256, 1) flow_train_fb_kernel(const TrainParams
     float* out = bufB;
     for (int j = 0; j < L; ++j) {                              // images B_o, B_{L-1}, ..., B_1
       const int lh = L - 1 - j;                                // hidden layer whose pre-activation gradient comes out
-      stream_gemm(true, tnW, in, j == 0 ? No : H, H, 0, nullptr);
+      stream_gemm(true, tnW, in, j == 0 ? No : H, H, 0, redbuf);
       const uint32_t bits = relu_bits[(t * L + lh) * 256 + tid];
       float* gh = p.Gh + ((size_t)(t * L + lh) * Bp + row0 + 4 * ty) * H;
 #pragma unroll
@@ -515,12 +544,13 @@ __global__ void __launch_bounds__(256) flow_train_wgrad_kernel(const TrainParams
   }
 }
 
-static size_t train_smem(int rows, int D, int Dp, int H, int No, int T, int L, int& ns, int& wslot) {
+static size_t train_smem(int rows, int splitk, int D, int Dp, int H, int No, int T, int L, int& ns, int& wslot) {
   const size_t TR_LDA = (size_t)rows + 4;
   const size_t wmax = (size_t)std::max(std::max((D + 1) * H, (H + 1) * H), std::max((H + 1) * No, H * Dp));
   const size_t brows = (size_t)std::max(H, No);
   const size_t act = (2 * brows * TR_LDA + 2 * (size_t)Dp * TR_LDA) * 4 + (size_t)T * L * 256 * 4 +
-                     (size_t)(32 - rows) * No * 4;                  // + split-K partial sums of the narrow GEMMs
+                     (splitk && rows < 32 ? (size_t)32 * brows * 4      // split-K partial sums: [CG][max(H, No)][rows]
+                                          : (size_t)(32 - rows) * No * 4);   // narrow GEMMs only: [CG - 1][rows][No]
   const size_t budget = 200 * 1024;
   if (act + 2 * wmax * 4 <= budget) {
     // small networks: whole images, and a deeper ring lets the bulk copies run several layers ahead of the chain
@@ -575,7 +605,9 @@ static int train_launch(const float* packed, const int32_t* meta_host, int32_t m
   p.Gh = p.Hs + (size_t)p.T * p.L * bpz * p.H;
   p.Go = p.Gh + (size_t)p.T * p.L * bpz * p.H;
   p.loss_partials = loss_partials; p.logprob = logprob;
-  const size_t smem = train_smem(rows, p.D, p.Dp, p.H, p.No, p.T, p.L, p.ns, p.wslot);
+  p.splitk = 0;
+  if (const char* e = getenv("PMC_TRAIN_SPLITK")) p.splitk = atoi(e) ? 1 : 0;   // experimental, not yet run on a GPU
+  const size_t smem = train_smem(rows, p.splitk, p.D, p.Dp, p.H, p.No, p.T, p.L, p.ns, p.wslot);
   PMC_REQUIRE(smem <= 220 * 1024 && p.wslot >= 2 * std::max(p.H, p.No), "pmc_flow_train_step: shared memory budget exceeded");
   cudaStream_t st = as_stream(stream);
   const unsigned grid = (unsigned)(n_batches * p.cpb);

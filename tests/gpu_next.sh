@@ -13,6 +13,8 @@ PMC_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_gpu_experimen
     done
   done
 } | tee gpurun_out/next_sweep_times.log
+# training step: default tiling vs split-K hidden GEMMs
+{ timeout 100 python tests/train_bench.py 2>&1 | grep fused | sed 's/^/default  /'; PMC_TRAIN_SPLITK=1 timeout 100 python tests/train_bench.py 2>&1 | grep fused | sed 's/^/split-K  /'; } | tee gpurun_out/next_train_times.log
 # one full capture each: default stream kernel, bulk/tip at 2 particles per lane
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:made_sweep_stream -c 1 -f -o gpurun_out/next_sweep_stream python tests/sweep_bench.py > /dev/null 2>&1
 PMC_B200_SWEEP=tip PMC_TIP_PPL=2 timeout 120 ncu --set full --clock-control none --import-source on -k regex:made_sweep_tip -c 1 -f -o gpurun_out/next_sweep_tip2 python tests/sweep_bench.py > /dev/null 2>&1
