@@ -94,6 +94,12 @@ def require_cuda():
     _cuda_ok = True
 
 
+def device() -> torch.device:
+    """the CUDA device this process computes on (one process per GPU)"""
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def ptr(t):
     """device/host pointer of a torch tensor (None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())

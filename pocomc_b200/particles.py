@@ -95,8 +95,7 @@ class Particles:
     # -- device mirror --------------------------------------------------------------------------
     def _sync_device(self):
         """Bring logl / den on the GPU up to date with the host history."""
-        _lib.require_cuda()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = _lib.device()
         T = len(self.past["logl"])
         if T == 0:
             raise ValueError("no particles stored yet")

@@ -1,0 +1,109 @@
+"""CPU, world_size 2 (gloo): pocomc_b200.sharded.ShardedParticles -- a history sharded by particle answers the
+beta probe, the weights and the trimmed-row gather of Sampler._reweight exactly like the unsharded history
+(SURVEY section 8e).  The device kernels are replaced by the numpy stand-ins of tests/fake_lib.py; what is under test
+is the exchange: rank-ordered merge of the probe statistics, [T, N] reassembly of the weights, ownership of rows."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+T_ITERS, N, D = 7, 1000, 3
+
+
+def _history(seed=4):
+    rng = np.random.default_rng(seed)
+    logl = rng.normal(size=(T_ITERS, N)) * 8.0 - 20.0
+    u = rng.normal(size=(T_ITERS, N, D))
+    beta = np.sort(np.concatenate([[0.0], rng.random(T_ITERS - 1)]))
+    logz = np.cumsum(rng.normal(size=T_ITERS)) * 0.3
+    logz[0] = 0.0
+    return logl, u, beta, logz
+
+
+def _fill(p, logl, u, beta, logz, cols=slice(None)):
+    for t in range(T_ITERS):
+        p.update(dict(logl=logl[t, cols].copy(), u=u[t, cols].copy(), beta=float(beta[t]), logz=float(logz[t]), iter=t))
+
+
+class _Patch:
+    """minimal stand-in for pytest's monkeypatch inside spawned workers"""
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import fake_lib
+    from pocomc_b200 import dist
+    from pocomc_b200.particles import Particles
+    from pocomc_b200.sharded import ShardedParticles
+    fake_lib.install(_Patch())
+    dist.init_from_env("gloo")
+    logl, u, beta, logz = _history()
+    counts = dist.shard_counts(N, world, 256)
+    lo, hi = dist.shard_range(N, rank, world, 256)
+    full = Particles(N, D)
+    _fill(full, logl, u, beta, logz)
+    mine = ShardedParticles(N, D, counts, rank)
+    _fill(mine, logl, u, beta, logz, slice(lo, hi))
+    ok = True
+    for b in (0.0, 0.37, 1.0):
+        pf, ps = full.probe(b), mine.probe(b)
+        ok &= ps["m"] == pf["m"] == T_ITERS * N and ps["max"] == pf["max"]
+        ok &= bool(np.isclose(ps["ess"], pf["ess"], rtol=1e-12)) and bool(np.isclose(ps["logz"], pf["logz"], rtol=1e-12, atol=1e-12))
+        w_full = full.weights_device(b, stats=pf["stats"]).numpy()
+        w_glob = mine.global_scalars(mine.weights_device(b, stats=ps["stats"])).numpy()
+        ok &= w_glob.shape == w_full.shape and bool(np.allclose(w_glob, w_full, rtol=1e-12, atol=0.0))
+        ok &= bool(np.isclose(w_glob.sum(), 1.0, rtol=1e-12))
+    # the statistics are bit-identical on the two ranks (same branch of the bisection everywhere)
+    both = dist.gather_blocks(mine.probe(0.5)["stats"].reshape(1, 4))
+    ok &= bool(torch.equal(both[0], both[1]))
+    # trimmed rows by global flat index, in global order, on every rank
+    idx = np.sort(np.random.default_rng(8).choice(T_ITERS * N, size=900, replace=False))
+    ok &= np.array_equal(mine.take_flat_global("u", idx), full.take_flat("u", idx))
+    ok &= np.array_equal(mine.take_flat_global("logl", idx), full.take_flat("logl", idx))
+    ok &= mine.take_flat_global("u", np.array([], dtype=np.int64)).shape == (0, D)
+    out[rank] = bool(ok)
+    td.destroy_process_group()
+
+
+def test_sharded_particles_world2():
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)), dict(out)
+
+
+def test_sharded_particles_single_process_is_the_plain_history(monkeypatch):
+    import fake_lib
+    from pocomc_b200.particles import Particles
+    from pocomc_b200.sharded import ShardedParticles
+    fake_lib.install(monkeypatch)
+    logl, u, beta, logz = _history(9)
+    full, one = Particles(N, D), ShardedParticles(N, D, [N], 0)
+    _fill(full, logl, u, beta, logz)
+    _fill(one, logl, u, beta, logz)
+    pf, ps = full.probe(0.6), one.probe(0.6)
+    assert ps["ess"] == pytest.approx(pf["ess"], rel=1e-14) and ps["logz"] == pytest.approx(pf["logz"], rel=1e-14)
+    # the fake denominators follow particles.py:222: logw = beta logl - (LSE_i(beta_i logl - logz_i) - log T)
+    lw = logl * 0.6 - (np.logaddexp.reduce(beta[:, None, None] * logl[None] - logz[:, None, None], axis=0) - np.log(T_ITERS))
+    assert pf["logz"] == pytest.approx(np.logaddexp.reduce(lw.reshape(-1)) - np.log(lw.size), rel=1e-12)
+    with pytest.raises(NotImplementedError):
+        one.probe(1.0, uss_k=10)
+    with pytest.raises(ValueError):
+        ShardedParticles(N, D, [N - 1], 0)
