@@ -150,6 +150,16 @@ class Particles:
                   _lib.ptr(stats), _lib.ptr(w), _lib.ptr(lw))
         return (w, lw) if want_logw else w
 
+    # -- the two questions Sampler._reweight asks beyond the probe; a sharded store (pocomc_b200.sharded) answers
+    #    them with an exchange, this one directly
+    def weights_global(self, beta_final, stats=None):
+        """normalised weights of the WHOLE flattened history ``[T * N]`` on the device"""
+        return self.weights_device(beta_final, stats=stats)
+
+    def take_rows(self, key, idx):
+        """rows ``idx`` (ascending flat indices into the whole history) of ``key``"""
+        return self.take_flat(key, idx)
+
     def compute_logw_and_logz(self, beta_final=1.0, normalize=True):
         """Persistent-sampling log-weights of every stored particle and the evidence estimate for
         ``beta_final`` (particles.py:215-231):

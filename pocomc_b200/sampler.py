@@ -384,7 +384,7 @@ class Sampler:
                     beta_min = beta
         self.pbar.update_stats(dict(beta=beta, ESS=int(ess_est), logZ=logz))
 
-        w_dev = self.particles.weights_device(beta, stats=p_sel["stats"])
+        w_dev = self.particles.weights_global(beta, stats=p_sel["stats"])
         if self.dynamic:                                                   # sampler.py:783-790
             n_unique = float(weight_stats_device(w_dev, int(self.n_active)).cpu().numpy()[2])
             if n_unique < self.n_active * (0.95 * self.dynamic_ratio):
@@ -394,9 +394,9 @@ class Sampler:
         keep, w_trim = trim_weights_device(w_dev, ess=0.99, bins=1000)
         idx = torch.nonzero(keep).squeeze(1).cpu().numpy()
         for key in ("u", "x", "logdetj", "logl", "logp"):
-            current_particles[key] = self.particles.take_flat(key, idx)
+            current_particles[key] = self.particles.take_rows(key, idx)
         if self.have_blobs:
-            current_particles["blobs"] = self.particles.take_flat("blobs", idx)
+            current_particles["blobs"] = self.particles.take_rows("blobs", idx)
         current_particles["logz"] = logz
         current_particles["beta"] = beta
         current_particles["weights"] = w_trim.cpu().numpy()

@@ -92,3 +92,11 @@ class ShardedParticles(Particles):
         out = np.empty((idx.size, got.shape[1]), dtype=got.dtype)
         out[where] = got
         return out.reshape((idx.size,) + tail)
+
+    # -- the store interface of Sampler._reweight ------------------------------------------------------
+    def weights_global(self, beta_final, stats=None):
+        return self.global_scalars(self.weights_device(beta_final, stats=stats))
+
+    def take_rows(self, key, idx):
+        return self.take_flat_global(key, idx)
+

@@ -55,7 +55,34 @@ def ps_weights(logl, den, beta_f, t_total, n, stats, w, logw):
         _arr(logw, t_total * n)[:] = lw - (st[0] + math.log(st[1]))
 
 
-TABLE = {"pmc_ps_append": ps_append, "pmc_ps_reduce": ps_reduce, "pmc_ps_weights": ps_weights}
+def weight_stats(w, m, uss_k, scratch, out3):
+    """tools.py:56-93 on an (unnormalised) weight vector: [sum w, sum w^2, sum 1 - (1 - w / sum)^k]"""
+    x = _arr(w, m)
+    o = _arr(out3, 3)
+    o[0], o[1] = x.sum(), (x * x).sum()
+    o[2] = np.sum(1.0 - (1.0 - x / x.sum()) ** uss_k) if uss_k > 0 else 0.0
+
+
+def trim_threshold(ws, m, ess_frac, bins, scratch, out3):
+    """tools.py:10-53 on the ascending-sorted weights: walk the percentile grid linspace(0, 99, bins) from the top
+    until ESS(w[w >= thr]) / ESS(w) >= ess_frac; out3 = [threshold, kept sum, grid index]"""
+    x = _arr(ws, m)
+    total = x.sum()
+    ess_total = total * total / (x * x).sum()
+    grid = np.linspace(0.0, 99.0, int(bins))
+    i = int(bins) - 1
+    while True:
+        thr = np.percentile(x, grid[i])
+        kept = x[x >= thr]
+        if kept.sum() ** 2 / (kept * kept).sum() / ess_total >= ess_frac or i == 0:
+            break
+        i -= 1
+    o = _arr(out3, 3)
+    o[0], o[1], o[2] = thr, kept.sum(), float(i)
+
+
+TABLE = {"pmc_ps_append": ps_append, "pmc_ps_reduce": ps_reduce, "pmc_ps_weights": ps_weights,
+         "pmc_weight_stats": weight_stats, "pmc_trim_threshold": trim_threshold}
 
 
 def install(monkeypatch):

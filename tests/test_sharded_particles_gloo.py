@@ -26,7 +26,26 @@ def _history(seed=4):
 
 def _fill(p, logl, u, beta, logz, cols=slice(None)):
     for t in range(T_ITERS):
-        p.update(dict(logl=logl[t, cols].copy(), u=u[t, cols].copy(), beta=float(beta[t]), logz=float(logz[t]), iter=t))
+        p.update(dict(logl=logl[t, cols].copy(), u=u[t, cols].copy(), x=2.0 * u[t, cols], logdetj=u[t, cols, 0] - 1.0,
+                      logp=-0.5 * np.sum(u[t, cols] ** 2, axis=1), beta=float(beta[t]), logz=float(logz[t]), iter=t))
+
+
+def _reweight_with(store):
+    """pocomc_b200.sampler.Sampler._reweight on a bare namespace carrying only what the method reads"""
+    import types
+    from pocomc_b200.sampler import Sampler
+
+    class _Bar:
+        def update_stats(self, info): pass
+        def update_iter(self): pass
+
+    ns = types.SimpleNamespace(particles=store, t=T_ITERS, pbar=_Bar(), n_effective=400, n_active=N, dynamic=True,
+                               dynamic_ratio=0.8, metric="ess", have_blobs=False)
+    ns._probe = lambda beta: Sampler._probe(ns, beta)
+    ns._ess_of_probe = lambda p: Sampler._ess_of_probe(ns, p)
+    cur = Sampler._reweight(ns, {})
+    cur["n_effective"] = ns.n_effective
+    return cur
 
 
 class _Patch:
@@ -77,6 +96,15 @@ def _worker(rank, world, port, out):
     ok &= np.array_equal(mine.take_flat_global("u", idx), full.take_flat("u", idx))
     ok &= np.array_equal(mine.take_flat_global("logl", idx), full.take_flat("logl", idx))
     ok &= mine.take_flat_global("u", np.array([], dtype=np.int64)).shape == (0, D)
+    # the whole of Sampler._reweight (bisection on beta, dynamic n_effective, trimming, gather of the survivors)
+    # run on the sharded store must reproduce the run on the unsharded one, on every rank
+    ra, rb = _reweight_with(full), _reweight_with(mine)
+    ok &= ra["beta"] == rb["beta"] and ra["n_effective"] == rb["n_effective"]
+    ok &= bool(np.isclose(ra["logz"], rb["logz"], rtol=1e-12, atol=1e-12)) and bool(np.isclose(ra["ess"], rb["ess"], rtol=1e-12))
+    ok &= ra["weights"].shape == rb["weights"].shape and bool(np.allclose(ra["weights"], rb["weights"], rtol=1e-11, atol=0.0))
+    for key in ("u", "x", "logdetj", "logl", "logp"):
+        ok &= np.array_equal(ra[key], rb[key])
+    ok &= 0.0 < ra["beta"] < 1.0 and 0 < len(ra["weights"]) < T_ITERS * N
     out[rank] = bool(ok)
     td.destroy_process_group()
 
