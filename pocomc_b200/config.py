@@ -55,6 +55,8 @@ forward_path = os.environ.get("PMC_B200_FORWARD", "tc")
 tc_min_rows = int(os.environ.get("PMC_B200_TC_MIN_ROWS", "1"))
 device_prior = os.environ.get("PMC_B200_DEVICE_PRIOR", "1") == "1"
 device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
+# experimental: under torch.distributed every rank stores only its block of the particle history (pocomc_b200.sharded)
+shard_history = os.environ.get("PMC_B200_SHARD_HISTORY", "0") == "1"
 
 
 def set_rng_mode(mode: str):

@@ -86,6 +86,13 @@ class Sampler:
         self.n_total = None
         self.n_evidence = None
         self.particles = Particles(n_active, n_dim)
+        if config.shard_history and dist.is_active() and self.n_active >= dist.world()[1]:
+            # experimental: every rank keeps only its block of every stored iteration; same
+            # block boundaries as _mutate_sharded
+            from .sharded import ShardedParticles
+            rank, ws = dist.world()
+            align = 256 if self.n_active // 256 >= ws else 1
+            self.particles = ShardedParticles(self.n_active, self.n_dim, dist.shard_counts(self.n_active, ws, align), rank)
         self.t = 0
 
         self.pool = pool

@@ -50,6 +50,54 @@ class ShardedParticles(Particles):
         if sum(self.counts) != int(n_particles):
             raise ValueError("shard counts do not add up to n_particles")
 
+    PER_PARTICLE = ("u", "x", "logdetj", "logl", "logp", "logw", "blobs")
+
+    def _block(self):
+        lo = sum(self.counts[:self.rank])
+        return lo, lo + self.counts[self.rank]
+
+    # -- storing and reading back ------------------------------------------------------------------
+    def update(self, data):
+        """Append one iteration.  Per-particle arrays may arrive whole (N rows: what ``Sampler`` hands over after
+        the per-temperature all-gather of the mutated rows) or already cut to this rank's block."""
+        lo, hi = self._block()
+        cut = {}
+        for key, val in data.items():
+            if key in self.PER_PARTICLE and val is not None and np.ndim(val) >= 1 and len(val) == self.n_particles \
+                    and self.n_particles != hi - lo:
+                val = np.asarray(val)[lo:hi]
+            cut[key] = val
+        super().update(cut)
+
+    def _gather_history(self, key):
+        """this rank's ``[T, n_r, ...]`` of ``key`` -> the whole ``[T, N, ...]`` on every rank"""
+        local = np.asarray(self.past.get(key))
+        if not dist.is_active() or local.ndim < 2:
+            return local
+        T, n_local = local.shape[:2]
+        tail = local.shape[2:]
+        rows = np.ascontiguousarray(np.moveaxis(local, 1, 0).reshape(n_local, -1))      # [n_r, T * prod(tail)]
+        full = dist.gather_blocks(torch.from_numpy(rows), self.counts).numpy()
+        return np.moveaxis(full.reshape((self.n_particles, T) + tail), 0, 1)
+
+    def get(self, key, index=None, flat=False):
+        """Like ``Particles.get``; reading the WHOLE history of a per-particle key (``index=None``) is a collective
+        that reassembles it in global particle order (posterior(), results)."""
+        if index is None and key in self.PER_PARTICLE and len(self.past.get(key)) and self.past.get(key)[0] is not None:
+            full = self._gather_history(key)
+            return full.reshape((-1,) + full.shape[2:]) if flat else full
+        return super().get(key, index=index, flat=flat)
+
+    def compute_logw_and_logz(self, beta_final=1.0, normalize=True):
+        p = self.probe(beta_final)
+        T, n_local = self._t_done, self._d_logl.shape[1]
+        dev = self._d_logl.device
+        stats = p["stats"] if normalize else torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float64, device=dev)
+        lw = torch.empty(T * n_local, dtype=torch.float64, device=dev)
+        _lib.call("pmc_ps_weights", _lib.ptr(self._d_logl), _lib.ptr(self._d_den), float(beta_final), int(T), n_local,
+                  _lib.ptr(stats), None, _lib.ptr(lw))
+        return self.global_scalars(lw).cpu().numpy(), p["logz"]
+
     # -- beta probe ------------------------------------------------------------------------------
     def probe(self, beta_final, uss_k=0):
         if uss_k:

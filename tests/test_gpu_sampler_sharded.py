@@ -80,3 +80,33 @@ def test_sharded_run_equals_single_process(kwargs):
         np.testing.assert_array_equal(got["logl"], single["logl"])
         assert got["calls"] == single["calls"]
         assert got["logz"] == single["logz"]
+
+
+@pytest.mark.skipif(os.environ.get("PMC_B200_EXPERIMENTAL") != "1",
+                    reason="particle-sharded HISTORY (config.shard_history, pocomc_b200.sharded) is pinned on the CPU over "
+                           "gloo with numpy stand-ins for the kernels but has not run on GPUs yet: set PMC_B200_EXPERIMENTAL=1")
+def test_sharded_history_run_equals_single_process(monkeypatch):
+    """Same bar as above with every rank storing only its block of the history (probe statistics merged in rank
+    order, weights gathered as scalars, trimmed rows gathered by owner)."""
+    import torch.multiprocessing as mp
+    kwargs = dict(sample="tpcn", precondition=True)
+    os.environ["PMC_SWEEP_LPP"] = "4"
+    try:
+        single = _run(**kwargs)
+    finally:
+        from pocomc_b200 import config
+        config.mean_mode = None
+        os.environ.pop("PMC_SWEEP_LPP", None)
+    monkeypatch.setenv("PMC_B200_SHARD_HISTORY", "1")             # read by pocomc_b200.config in the spawned workers
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), kwargs, out), nprocs=world, join=True)
+    for r in range(world):
+        got = out[r]
+        np.testing.assert_array_equal(got["beta"], single["beta"])
+        np.testing.assert_array_equal(got["steps"], single["steps"])
+        np.testing.assert_array_equal(got["x"], single["x"])
+        assert got["calls"] == single["calls"]
+        np.testing.assert_allclose(got["logz"], single["logz"], rtol=1e-12)
+

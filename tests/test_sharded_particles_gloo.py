@@ -96,6 +96,18 @@ def _worker(rank, world, port, out):
     ok &= np.array_equal(mine.take_flat_global("u", idx), full.take_flat("u", idx))
     ok &= np.array_equal(mine.take_flat_global("logl", idx), full.take_flat("logl", idx))
     ok &= mine.take_flat_global("u", np.array([], dtype=np.int64)).shape == (0, D)
+    # update() cuts whole-population arrays to this rank's block; reading the whole history back is a collective
+    cut = ShardedParticles(N, D, counts, rank)
+    _fill(cut, logl, u, beta, logz)                                   # N rows per iteration, like Sampler hands them over
+    ok &= len(cut.past["logl"][0]) == hi - lo and np.array_equal(cut.past["u"][3], u[3, lo:hi])
+    ok &= np.array_equal(cut.get("u"), full.get("u")) and np.array_equal(cut.get("u", flat=True), full.get("u", flat=True))
+    ok &= np.array_equal(cut.get("logl", flat=True), full.get("logl", flat=True))
+    ok &= cut.get("beta", index=-1) == full.get("beta", index=-1) and np.array_equal(cut.get("beta"), full.get("beta"))
+    lw_s, z_s = cut.compute_logw_and_logz(1.0)
+    lw_f, z_f = full.compute_logw_and_logz(1.0)
+    ok &= lw_s.shape == lw_f.shape and bool(np.allclose(lw_s, lw_f, rtol=1e-12, atol=1e-12)) and bool(np.isclose(z_s, z_f, rtol=1e-12))
+    res_s, res_f = cut.compute_results(), full.compute_results()
+    ok &= set(res_s) == set(res_f) and np.array_equal(res_s["x"], res_f["x"]) and res_s["logw"].shape == res_f["logw"].shape
     # the whole of Sampler._reweight (bisection on beta, dynamic n_effective, trimming, gather of the survivors)
     # run on the sharded store must reproduce the run on the unsharded one, on every rank
     ra, rb = _reweight_with(full), _reweight_with(mine)
