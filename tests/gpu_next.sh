@@ -5,6 +5,7 @@
 # Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 PMC_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_gpu_experimental.py -x -q --timeout 60 2>&1 | tail -4 | tee gpurun_out/next_experimental_tests.log
+PMC_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_sampler_sharded.py -x -q --timeout 120 -k history 2>&1 | tail -4 | tee gpurun_out/next_sharded_history.log
 {
   for n in 10000 5120 2560; do
     N=$n timeout 60 python tests/sweep_bench.py 2>&1 | grep "inverse=True" | sed "s/^/stream        /"
