@@ -8,7 +8,6 @@ from ._version import version
 from .flow import *          # noqa: F401,F403
 from .prior import *         # noqa: F401,F403
 from .sampler import *       # noqa: F401,F403
-from .parallel import *      # noqa: F401,F403
 from . import config, mcmc, particles, scaler, tools, geometry  # noqa: F401
 
 __version__ = version

@@ -17,19 +17,6 @@ device_prior
     True (default): when the prior handed to the MCMC kernels is ``pocomc_b200.Prior.logpdf`` of
     frozen scipy ``norm`` / ``uniform`` factors, log-prior values are computed on the GPU
     (identical formula, f64); any other prior object is called on the host like the reference does.
-sweep_variant
-    ``"ffma"`` (default): the fp32-FMA TMA-stream sweep kernel.  ``"mma"``: experimental warp-MMA
-    sweep (mma.sync TF32 with a 3xTF32 split, passes the same parity tests) -- slower on B200 at the
-    benchmark sizes (505 us vs 344 us per 10 000-particle inverse) because 16 particles per warp and
-    1.8 KB of activations per particle leave ~1 warp per scheduler.  ``"block"``: experimental blocked
-    sweep (csrc/flow_block.cu) for affine flows: the dense part of every degree block on mma.sync
-    (3xTF32), the triangular part hop by hop with register/shuffle hand-over; half the instructions of
-    ``"ffma"`` but 359 us vs 331 us per 10 000-particle inverse (2.25 serial warps per scheduler at
-    68 particles per SM).  ``"tip"``: experimental bulk/tip sweep (csrc/flow_tip.cu) for
-    affine flows with degree groups of <= 8 units: every dot product split into the part finished one order
-    position earlier (issued ahead, off the dependent chain) and the group born in this position (exchanged by
-    shuffles); parity green, 388 us vs 331 us per 10 000-particle inverse in its first form.
-    Read when a flow is constructed.
 forward_path
     ``"tc"`` (default): ``Flow.forward`` / ``log_prob`` without a graph run on the tcgen05 dense kernel
     (csrc/flow_tc.cu, 3xTF32 split = fp32 fidelity) when the flow is affine with H <= 128 and the batch
@@ -48,7 +35,6 @@ import os
 
 rng_mode = os.environ.get("PMC_B200_RNG", "host")
 mean_mode = None  # None -> 1 for "host", 0 for "device"
-sweep_variant = os.environ.get("PMC_B200_SWEEP", "ffma")
 fit_kernels = os.environ.get("PMC_B200_FIT_KERNELS", "fused")
 fit_path = os.environ.get("PMC_B200_FIT", "graph")
 forward_path = os.environ.get("PMC_B200_FORWARD", "tc")

@@ -523,222 +523,6 @@ made_sweep_stream_kernel(const float* __restrict__ stream, const int* __restrict
   }
 }
 
-// ---- v4: warp-MMA sweep ---------------------------------------------------------------------------
-// ncu on the FFMA stream kernel (profiles/r1c): 314 M warp instructions for 1.39 G useful MACs and 58 M
-// shared-memory wavefronts -- issue- and LDS-bound, with 24 shuffle/select instructions per hop just to
-// sum the K-slices.  Here a warp owns 16 particles and every hop is a [16 x K] x [K x 8] product on the
-// warp-level tensor path (mma.sync.m16n8k8 TF32): the K reduction happens inside the MMA, the hop
-// output lands in registers in a layout that is written straight back as the next hop's A operand.
-// fp32 fidelity (the reference flow is fp32, parity bar 2e-5) comes from the 3xTF32 split
-// a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with round-to-nearest splits (error ~1e-6 relative).
-// tcgen05 is deliberately not used here: its minimum tile is M = 64/128 particles per CTA and each of
-// the T*D*(L+1) dependent hops would pay a smem->fence->MMA->commit->mbarrier->TMEM-load round trip
-// (~0.5-1 us) where the register-resident warp MMA pays ~0.1 us; see DESIGN.md section 7.
-__device__ __forceinline__ unsigned tf32_rna(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-// x = hi + lo exactly, hi = x with the 13 low mantissa bits cleared (a valid TF32 value); the tensor
-// core ignores the low 13 bits of lo itself.  (cvt.rna.tf32 would halve the residual but ptxas expands
-// it to a ~6-instruction sequence on sm_100a; 18 of them per k-step dominated the first version.)
-__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-// activation arrays: row r (unit / order position), particle m in 0..15, XOR-swizzled so that the
-// four rows t, t+4 a lane group touches per A fragment fall into disjoint banks (no padding)
-__device__ __forceinline__ int act_idx(int r, int m) { return r * 16 + (m ^ (((r >> 1) & 1) << 3)); }
-
-// c[0..3] = (16 x 8) tile of A[16 x 8*ksteps] * B: A from `a` (lane-offset pointer into a swizzled
-// activation array, advanced 128 floats per k-step), B fragments from `wf` ([ks][32 lanes] float2).
-__device__ __forceinline__ void hop_mma(const float2* __restrict__ wf, int ksteps, const float* __restrict__ a, int off0,
-                                        int off1, float (&c)[4]) {
-  float hh[4] = {0.f, 0.f, 0.f, 0.f}, hl[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const float2 b = wf[ks * 32];
-    const float a0 = a[off0], a1 = a[off1], a2 = a[off0 + 64], a3 = a[off1 + 64];
-    a += 128;
-    unsigned ah[4], al[4], bh[2], bl[2];
-    split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]); split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
-    split_tf32(b.x, bh[0], bl[0]); split_tf32(b.y, bh[1], bl[1]);
-    mma_tf32(hh, ah, bh);
-    mma_tf32(hl, ah, bl);
-    mma_tf32(lh, al, bh);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) c[i] = hh[i] + (hl[i] + lh[i]);
-}
-
-template <class UNI>
-__global__ void __launch_bounds__(STREAM_MAX_THREADS, 1)
-made_sweep_mma_kernel(const float* __restrict__ stream, const int* __restrict__ meta, int meta_len,
-                      const float* __restrict__ in, float* __restrict__ out, float* __restrict__ ladj_out,
-                      long long n, int inverse, int ppc) {
-  constexpr int PW = 16;                                // particles per consumer warp (MMA M)
-  constexpr int TP = UNI::TP;
-  constexpr int NTO = (UNI::TOTAL + 7) / 8;             // n-tiles of the output hop
-  constexpr int PST = NTO * 8 + 1;                      // phi staging row stride (odd: conflict-free reads)
-  constexpr int NS = STREAM_STAGES;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  int* sm = reinterpret_cast<int*>(smem_raw);
-  for (int i = threadIdx.x; i < meta_len; i += blockDim.x) sm[i] = meta[i];
-  __syncthreads();
-  const int D = sm[M_D], H = sm[M_H], L = sm[M_L], T = sm[M_T], ng = sm[M_NG];
-  const int Dp = (D + 7) & ~7, Hp = (H + 7) & ~7;
-  const int tstride = sm[M_TSTRIDE], nchunks = sm[M_NCHUNKS], slot_floats = sm[M_SLOT_FLOATS];
-  const int* gstart = sm + sm[M_OFF_GSTART];
-  const int* chunks = sm + sm[M_OFF_CHUNKS];
-  size_t off = ((size_t)meta_len * 4 + 15) & ~(size_t)15;
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + off);
-  int* done = reinterpret_cast<int*>(full + NS);          // per-slot count of warps that finished reading it
-  off = (off + 2 * NS * 8 + 127) & ~(size_t)127;
-  float* ring = reinterpret_cast<float*>(smem_raw + off);
-  off += (size_t)NS * slot_floats * 4;
-  float* acts = reinterpret_cast<float*>(smem_raw + off);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long cta_row0 = (long long)blockIdx.x * ppc;
-  const int cta_rows = (int)min((long long)ppc, n - cta_row0);
-  const int active = (cta_rows + PW - 1) / PW;
-  // Weight ring without a producer warp: thread 0 launches the first NS bulk copies; afterwards the
-  // LAST warp to finish reading a slot (shared-memory counter) refills it with chunk it+NS.  Warps only
-  // ever block in the hardware-suspended mbarrier wait on `full` -- nothing spins on an issue port.
-  const int total_chunks = T * nchunks;
-  auto issue = [&](int ci) {     // chunk index in consumption order -> TMA bulk copy into its slot
-    const int tt = ci / nchunks, c = ci - tt * nchunks;
-    const int tsel = inverse ? (T - 1 - tt) : tt;
-    const int slot = ci % NS;
-    const unsigned bytes = (unsigned)chunks[4 * c + 3] * 4u;
-    mbar_expect_tx(full + slot, bytes);
-    bulk_g2s(ring + (size_t)slot * slot_floats, stream + (size_t)tsel * tstride + chunks[4 * c + 2], bytes, full + slot);
-  };
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); done[i] = 0; }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < NS && i < total_chunks; ++i) issue(i);
-  }
-  __syncthreads();
-  const int cw = warp;
-  if (cw >= active) return;
-
-  // ---- consumer warp: 16 particles
-  const int g = lane >> 2, t = lane & 3;
-  const int per_warp = (D + Dp + L * Hp + PST) * PW;
-  float* cur = acts + (size_t)cw * per_warp;  // [D][16] running vector (feature order), not swizzled
-  float* xs = cur + D * PW;                   // [Dp][16] swizzled: data-side values by ORDER position
-  float* act = xs + Dp * PW;                  // [L][Hp][16] swizzled
-  float* phis = act + (size_t)L * Hp * PW;    // [16][PST] output-hop staging
-  const long long row0 = cta_row0 + (long long)cw * PW;
-  const int rows = (int)min((long long)PW, n - row0);
-  for (int i = lane; i < (Dp + L * Hp) * PW; i += 32) xs[i] = 0.0f;
-  for (int i = lane; i < PW * D; i += 32) {
-    const int r = i / D, c = i - r * D;
-    cur[c * PW + r] = (r < rows) ? in[row0 * D + i] : 0.0f;
-  }
-  __syncwarp();
-  const int sw = ((t >> 1) & 1) << 3;
-  const int off0 = t * 16 + (g ^ sw), off1 = off0 ^ 8;   // A-fragment offsets of rows t (+64: rows t+4), particles g / g+8
-  const float* act_last = act + (size_t)(L - 1) * Hp * PW;
-  float ladj = 0.0f;
-  int it = 0;
-  for (int tt = 0; tt < T; ++tt) {
-    const int tr = inverse ? (T - 1 - tt) : tt;
-    const bool rev = (tr & 1);
-    for (int c = 0; c < nchunks; ++c, ++it) {
-      const int slot = it % NS;
-      mbar_wait(full + slot, (it / NS) & 1);
-      const float* w = ring + (size_t)slot * slot_floats;
-      const int k0 = chunks[4 * c], k1 = chunks[4 * c + 1];
-      for (int k = k0; k < k1; ++k) {
-        const int feat = rev ? (D - 1 - k) : k;
-        // ---- output hop: phi[16][TOTAL] = act_{L-1}[:, 0:E_k] Wo_k + b
-        const int ks_out = (gstart[k] + 7) >> 3;
-        {
-          const float* bias = w + (size_t)NTO * ks_out * 64;
-#pragma unroll
-          for (int nt = 0; nt < NTO; ++nt) {
-            float cfr[4];
-            hop_mma(reinterpret_cast<const float2*>(w) + lane, ks_out, act_last, off0, off1, cfr);
-            w += ks_out * 64;
-            const float2 b = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * t);
-            float* pr = phis + 8 * nt + 2 * t;
-            pr[g * PST] = cfr[0] + b.x; pr[g * PST + 1] = cfr[1] + b.y;
-            pr[(g + 8) * PST] = cfr[2] + b.x; pr[(g + 8) * PST + 1] = cfr[3] + b.y;
-          }
-          w += NTO * 8;
-        }
-        __syncwarp();
-        if (lane < PW) {   // one lane per particle applies the univariate transform
-          float phi[TP];
-#pragma unroll
-          for (int j = 0; j < TP; ++j) phi[j] = (j < UNI::TOTAL) ? phis[lane * PST + j] : 0.0f;
-          const float v = cur[feat * PW + lane];
-          float l;
-          const float res = UNI::apply(phi, v, inverse != 0, l);
-          ladj = inverse ? (ladj - l) : (ladj + l);
-          xs[act_idx(k, lane)] = inverse ? res : v;
-          cur[feat * PW + lane] = res;
-        }
-        __syncwarp();
-        const int gg = k + 1;
-        if (gg > ng) continue;
-        const int gs = gstart[gg - 1], ge = gstart[gg];
-        if (ge == gs) continue;
-        const int nt_h = (ge - gs + 7) >> 3;
-        const float* src = xs;
-        float* dst = act;
-        for (int l_ = 0; l_ < L; ++l_) {
-          const int ksteps = (((l_ == 0) ? gg : ge) + 7) >> 3;
-          const float* bias = w + (size_t)nt_h * ksteps * 64;
-          for (int nt = 0; nt < nt_h; ++nt) {
-            float cfr[4];
-            hop_mma(reinterpret_cast<const float2*>(w) + lane, ksteps, src, off0, off1, cfr);
-            w += ksteps * 64;
-            const float2 b = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * t);
-            const int u0 = gs + 8 * nt + 2 * t;
-            float v00 = cfr[0] + b.x, v01 = cfr[1] + b.y, v10 = cfr[2] + b.x, v11 = cfr[3] + b.y;
-            const int i00 = act_idx(u0, g), i01 = act_idx(u0 + 1, g), i10 = act_idx(u0, g + 8), i11 = act_idx(u0 + 1, g + 8);
-            if (u0 < ge) {
-              if (l_ > 0) { v00 += src[i00]; v10 += src[i10]; }     // residual hidden layers
-              dst[i00] = fmaxf(v00, 0.0f); dst[i10] = fmaxf(v10, 0.0f);
-            }
-            if (u0 + 1 < ge) {
-              if (l_ > 0) { v01 += src[i01]; v11 += src[i11]; }
-              dst[i01] = fmaxf(v01, 0.0f); dst[i11] = fmaxf(v11, 0.0f);
-            }
-          }
-          w += nt_h * 8;
-          src = dst;
-          dst += Hp * PW;
-          __syncwarp();
-        }
-      }
-      __syncwarp();
-      if (lane == 0 && it + NS < total_chunks) {
-        __threadfence_block();                                    // this warp's reads of the slot happen-before the refill
-        if (atomicAdd(done + slot, 1) == active - 1) {            // last reader of the slot
-          done[slot] = 0;
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads -> async-proxy write
-          issue(it + NS);
-        }
-      }
-    }
-  }
-  for (int i = lane; i < PW * D; i += 32) {
-    const int r = i / D, c = i - r * D;
-    if (r < rows) out[row0 * D + i] = cur[c * PW + r];
-  }
-  if (lane < rows) ladj_out[row0 + lane] = ladj;
-}
-
 __global__ void pack_kernel(const float* __restrict__ raw, const int* __restrict__ gather,
                             float* __restrict__ packed, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -845,43 +629,7 @@ static int launch_stream(const float* stream, const int* meta, int meta_len, con
   return 2;
 }
 
-template <class UNI>
-static int launch_mma(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in,
-                      float* out, float* ladj, long long n, int inverse, cudaStream_t st) {
-  const int D = hmeta[M_D], H = hmeta[M_H], L = hmeta[M_L];
-  const size_t fixed = (((size_t)meta_len * 4 + 15) & ~(size_t)15) + 2 * STREAM_STAGES * 8 + 256 +
-                       (size_t)STREAM_STAGES * hmeta[M_SLOT_FLOATS] * 4;
-  const int pst = (UNI::TOTAL + 7) / 8 * 8 + 1;
-  const size_t per_particle = (size_t)(D + ((D + 7) & ~7) + L * ((H + 7) & ~7) + pst) * 4;
-  const size_t budget = 227 * 1024;
-  PMC_REQUIRE(fixed + 16 * per_particle <= budget, "pmc_flow_sweep: flow too large for the warp-MMA kernel");
-  const int sms = sm_count(), pw = 16;
-  const long long max_smem = (long long)((budget - fixed) / per_particle);
-  const long long per_sm = (n + sms - 1) / sms;
-  long long cap = std::min<long long>(max_smem, (long long)(STREAM_MAX_THREADS / 32) * pw) / pw * pw;
-  long long waves = (per_sm + cap - 1) / cap;
-  long long ppc = (n + waves * sms - 1) / (waves * sms);
-  ppc = std::min(cap, (ppc + pw - 1) / pw * pw);
-  const long long grid = (n + ppc - 1) / ppc;
-  const int threads = 32 * (int)(ppc / pw);
-  const size_t smem = fixed + (size_t)ppc * per_particle;
-  auto kern = made_sweep_mma_kernel<UNI>;
-  PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)grid, threads, smem, st>>>(stream, meta, meta_len, in, out, ladj, n, inverse, (int)ppc);
-  PMC_LAUNCH_CHECK();
-  return 0;
-}
-
 }  // namespace pmc
-
-namespace pmc {
-// csrc/flow_block.cu: blocked sweep (dense part on mma.sync, triangular part as short fp32 dots)
-int launch_block(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in, float* out,
-                 float* ladj, long long n, int inverse, cudaStream_t st);
-// csrc/flow_tip.cu: bulk/tip sweep (experimental)
-int launch_tip(const float* stream, const int* meta, int meta_len, const int* hmeta, const float* in, float* out,
-               float* ladj, long long n, int inverse, cudaStream_t st);
-}
 
 using namespace pmc;
 
@@ -901,15 +649,6 @@ extern "C" int pmc_flow_sweep(const float* packed, const int32_t* meta, const in
   if (n == 0) return 0;
   const int* hm = meta_host;
   PMC_REQUIRE(hm[M_D] >= 2 && hm[M_H] >= 1 && hm[M_L] >= 1 && hm[M_T] >= 1, "pmc_flow_sweep: bad meta header");
-  if (hm[M_VERSION] == 5)
-    return launch_tip(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
-  if (hm[M_VERSION] == 4)
-    return launch_block(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
-  if (hm[M_VERSION] == 3) {
-    PMC_REQUIRE(hm[M_KIND] == 0 || (hm[M_BINS] == 8 && hm[M_TOTAL] == 23), "pmc_flow_sweep: only bins=8 splines are built");
-    if (hm[M_KIND] == 0) return launch_mma<Affine>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
-    return launch_mma<Rqs>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));
-  }
   if (hm[M_VERSION] == 2) {
     PMC_REQUIRE(hm[M_KIND] == 0 || (hm[M_BINS] == 8 && hm[M_TOTAL] == 23), "pmc_flow_sweep: only bins=8 splines are built");
     if (hm[M_KIND] == 0) return launch_stream<Affine>(packed, meta, meta_len, hm, in, out, ladj, n, inverse, as_stream(stream));

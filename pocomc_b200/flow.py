@@ -106,19 +106,8 @@ class MaskedAutoregressiveFlow(nn.Module):
         # kernel-side weight layout: the TMA-streamed consumption-order stream when the network fits the
         # stream kernel's shared-memory budget, else the degree-sorted slab layout of the v1 kernel
         self._pack_entry = "pmc_flow_pack"
-        if config.sweep_variant == "block" and ML.block_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind):
-            # blocked sweep (csrc/flow_block.cu): dense part of every degree block on the warp tensor path
-            klay = ML.build_block(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
-            self.packed_numel = klay.numel
-            self._pack_entry = "pmc_flow_tc_pack"                  # TF32 hi / lo images of the dense weights
-        elif config.sweep_variant == "tip" and ML.tip_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind):
-            # bulk/tip sweep (csrc/flow_tip.cu, experimental): every hop's dot product split into the part finished
-            # one order position earlier and the degree group born in this position
-            klay = ML.build_stream_tip(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
-            self.packed_numel = klay.numel
-        elif ML.stream_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind, lay.bins):
-            klay = ML.build_stream(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins,
-                                   variant="mma" if config.sweep_variant == "mma" else "ffma")
+        if ML.stream_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind, lay.bins):
+            klay = ML.build_stream(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
             self.packed_numel = klay.numel
         else:
             klay = lay

@@ -254,35 +254,9 @@ def stream_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int, bins: 
     return STREAM_STAGES * slot * 4 + 8 * (2 * n_dim + n_layers * n_hidden) * 4 + 4096 <= STREAM_SMEM_BUDGET
 
 
-def _mma_slab(row_idx, col_idx_fn, n_cols):
-    """One hop's weights in mma.sync m16n8k8 B-fragment order: [n-tile][k-step][lane][2] with
-    lane = 4*g + t holding W[8*ks + t + 4*j][8*nt + g], j = 0, 1.  ``row_idx`` are the raw row keys
-    (K of them, padded with zero rows to a multiple of 8); ``col_idx_fn(c, rows)`` gives the raw indices
-    of column c for those rows (or None for a padding column)."""
-    K = len(row_idx)
-    K8 = (K + 7) // 8 * 8
-    NT = (n_cols + 7) // 8
-    dense = np.full((K8, NT * 8), -1, np.int64)
-    for c in range(n_cols):
-        col = col_idx_fn(c, row_idx)
-        if col is not None:
-            dense[:K, c] = col
-    lane = np.arange(32)
-    g, t = lane >> 2, lane & 3
-    out = np.empty((NT, K8 // 8, 32, 2), np.int64)
-    for nt in range(NT):
-        for ks in range(K8 // 8):
-            for j in range(2):
-                out[nt, ks, :, j] = dense[8 * ks + t + 4 * j, 8 * nt + g]
-    return out.reshape(-1)
-
-
 @lru_cache(maxsize=None)
-def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8,
-                 variant: str = "ffma") -> StreamLayout:
-    """variant "ffma": slabs [rows16][4] for the fp32-FMA stream kernel; "mma": B-fragment-ordered
-    slabs for the warp-MMA (3xTF32 mma.sync) stream kernel."""
-    mma = variant == "mma"
+def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8) -> StreamLayout:
+    """slabs [rows16][4] in consumption order for the fp32-FMA stream kernel (csrc/flow_sweep.cu)."""
     lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
     D, H, L, T, total, tp = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.total, lay.tp
     ng = D - 1
@@ -303,23 +277,16 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
             ek = int(gstart[k - 1 + 1]) if k >= 1 else 0          # units of degree <= k  (gstart[k] = #deg < k+1)
             src = hperm[:ek]
             wo, bo = base_r + raw_off[2 * L], base_r + raw_off[2 * L + 1]
-            if mma:
-                parts.append(_mma_slab(src, lambda c, rows: wo + (feat * total + c) * H + rows, total))
-                ntp = (total + 7) // 8 * 8
-                b = np.full(ntp, -1, np.int64)
-                b[:total] = bo + feat * total + np.arange(total)
-                parts.append(b)
-            for c in range(0 if mma else tp // 4):
+            for c in range(tp // 4):
                 blk = np.full((_pad16(ek), 4), -1, np.int64)
                 for j in range(4):
                     o = 4 * c + j
                     if o < total:
                         blk[:ek, j] = wo + (feat * total + o) * H + src
                 parts.append(blk.reshape(-1))
-            if not mma:
-                b = np.full(tp, -1, np.int64)
-                b[:total] = bo + feat * total + np.arange(total)
-                parts.append(b)
+            b = np.full(tp, -1, np.int64)
+            b[:total] = bo + feat * total + np.arange(total)
+            parts.append(b)
             g = k + 1
             if g <= ng and gsize[g - 1] > 0:
                 units = hperm[gstart[g - 1]:gstart[g]]
@@ -331,13 +298,6 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
                     wl, bl = base_r + raw_off[2 * l], base_r + raw_off[2 * l + 1]
                     rows = iperm[np.arange(g)] if l == 0 else hperm[:eg]
                     width = D if l == 0 else H
-                    if mma:
-                        parts.append(_mma_slab(rows, lambda c, rr, wl=wl, width=width: wl + units[c] * width + rr, len(units)))
-                        n8 = (len(units) + 7) // 8 * 8
-                        bb = np.full(n8, -1, np.int64)
-                        bb[:len(units)] = bl + units
-                        parts.append(bb)
-                        continue
                     for c in range(nch):
                         blk = np.full((_pad16(len(rows)), 4), -1, np.int64)
                         for j in range(4):
@@ -372,155 +332,7 @@ def build_stream(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, ki
     meta[M_MAXCH] = int(nchunk.max())
     meta[M_RAW_TSTRIDE] = lay.raw_tstride
     meta[M_BINS] = bins
-    meta[M_VERSION] = 3 if mma else 2
-    meta[M_NCHUNKS] = len(chunks)
-    meta[M_SLOT_FLOATS] = slot_floats
-    pos = META_HEADER
-    for slot_id, tab in zip((M_OFF_GSTART, M_OFF_NCHUNK, M_OFF_CHUNKS), tables):
-        meta[slot_id] = pos
-        pos += len(tab)
-    meta = np.concatenate([meta] + [np.asarray(tb, np.int64) for tb in tables])
-    assert meta.max() < 2 ** 31 and gather.max() < 2 ** 31
-    return StreamLayout(tstride, slot_floats, chunks, meta.astype(np.int32), gather.astype(np.int32))
-
-
-# ---------------------------------------------------------------------------------------------
-# "tip" stream: bulk / tip split of every hop (csrc/flow_tip.cu, experimental)
-# ---------------------------------------------------------------------------------------------
-TIP_MAXCH = 2             # the kernel keeps one group's fresh activations in 4 * TIP_MAXCH registers per lane
-
-
-def tip_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int) -> bool:
-    """Affine flows whose degree groups have at most 4 * TIP_MAXCH hidden units (H / (D - 1) <= 8: D >= 6 for
-    the reference's H = max(next_pow2(3 D), 32))."""
-    if kind != KIND_AFFINE or n_dim < 3 or n_layers < 1:
-        return False
-    return -(-n_hidden // (n_dim - 1)) <= 4 * TIP_MAXCH and stream_supported(n_dim, n_hidden, n_layers, kind)
-
-
-@lru_cache(maxsize=None)
-def build_stream_tip(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int = KIND_AFFINE,
-                     bins: int = 8) -> StreamLayout:
-    """Consumption-ordered weight stream for the bulk/tip sweep kernel.
-
-    Every dot product of the degree-ordered sweep is split into the part over inputs that were finished one
-    order position earlier (the BULK: no dependence on the value being computed right now, so its latency is
-    hidden) and the part over the inputs born in the current position (the TIP: one degree group, <= 8 units).
-    Stage k (order position k, feature iperm[k]; group g = k + 1 = sorted units [gstart[k], gstart[k+1])) holds,
-    all in float4 units:
-      out tip   : 4 nch(k-1) x (Wout[shift | scale][unit j of group k], 0, 0), then (b_shift, b_scale, 0, 0)
-      bulk of g : layer 0   nch slabs [pad16(k) rows][4]          rows = inputs of order < k
-                  layer l   nch slabs [pad16(gstart[k]) rows][4]   rows = sorted units of degree <= k
-      out bulk  : (k + 1 < D) one slab [pad16(gstart[k]) rows][4] = (Wout[shift], Wout[scale], 0, 0) of feature k + 1
-      tips of g : layer 0   per (chunk c, lane q): (bias, W0[unit, feature k], 0, 0)
-                  layer l   per (chunk c, lane q): (bias, 0, 0, 0) + nch float4 of W_l[unit, units of group g]
-    where unit = group unit 4 c + q (all zero for padding units).  meta: same header as build_stream, version 5."""
-    if not tip_supported(n_dim, n_hidden, n_layers, kind):
-        raise ValueError("flow shape not supported by the bulk/tip stream")
-    lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
-    D, H, L, T, total = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.total
-    ng = D - 1
-    hperm, degree = lay.hperm, lay.degree
-    gstart = np.searchsorted(degree, np.arange(1, ng + 2), side="left").astype(np.int64)    # gstart[i] = #units of degree <= i
-    gsize = np.diff(gstart)
-    nchunk = (gsize + 3) // 4
-    assert nchunk.max() <= TIP_MAXCH and gsize.min() > 0
-    raw_off = np.concatenate([[0], np.cumsum([int(np.prod(sh)) for sh in lay.raw_sizes])]).astype(np.int64)
-
-    def padded_units(g):
-        """raw unit ids of group g (1-based degree), padded with -1 to a multiple of 4"""
-        u = hperm[gstart[g - 1]:gstart[g]]
-        out = np.full(4 * int(nchunk[g - 1]), -1, np.int64)
-        out[:len(u)] = u
-        return out
-
-    def transform_gather(t):
-        base_r = t * lay.raw_tstride
-        iperm = np.arange(D) if t % 2 == 0 else D - 1 - np.arange(D)
-        wo, bo = base_r + raw_off[2 * L], base_r + raw_off[2 * L + 1]
-        stages = []
-        for k in range(D):
-            parts = []
-            feat = iperm[k]
-            # ---- out tip (units of group k = degree k) + bias
-            if k >= 1:
-                for u in padded_units(k):
-                    q = np.full(4, -1, np.int64)
-                    if u >= 0:
-                        q[:total] = wo + (feat * total + np.arange(total)) * H + u
-                    parts.append(q)
-            b = np.full(4, -1, np.int64)
-            b[:total] = bo + feat * total + np.arange(total)
-            parts.append(b)
-            g = k + 1
-            ek = int(gstart[k])                                   # sorted units of degree <= k
-            if g <= ng:
-                units = padded_units(g)
-                nch = int(nchunk[g - 1])
-                # ---- bulk of group g
-                for l in range(L):
-                    wl = base_r + raw_off[2 * l]
-                    rows = iperm[np.arange(k)] if l == 0 else hperm[:ek]
-                    width = D if l == 0 else H
-                    for c in range(nch):
-                        blk = np.full((_pad16(len(rows)), 4), -1, np.int64)
-                        for j in range(4):
-                            u = units[4 * c + j]
-                            if u >= 0 and len(rows):
-                                blk[:len(rows), j] = wl + u * width + rows
-                        parts.append(blk.reshape(-1))
-            if k + 1 < D:
-                # ---- out bulk of feature k + 1 over last-layer units of degree <= k
-                fnext = iperm[k + 1]
-                blk = np.full((_pad16(ek), 4), -1, np.int64)
-                for o in range(total):
-                    blk[:ek, o] = wo + (fnext * total + o) * H + hperm[:ek]
-                parts.append(blk.reshape(-1))
-            if g <= ng:
-                # ---- tips of group g
-                for l in range(L):
-                    wl, bl = base_r + raw_off[2 * l], base_r + raw_off[2 * l + 1]
-                    for c in range(nch):
-                        for q in range(4):
-                            u = units[4 * c + q]
-                            head = np.full(4, -1, np.int64)
-                            if u >= 0:
-                                head[0] = bl + u
-                                if l == 0:
-                                    head[1] = wl + u * D + feat
-                            parts.append(head)
-                            if l > 0:
-                                tipw = np.full(4 * nch, -1, np.int64)
-                                if u >= 0:
-                                    ok = units >= 0
-                                    tipw[ok] = wl + u * H + units[ok]
-                                parts.append(tipw)
-            stages.append(np.concatenate(parts))
-        return stages
-
-    stages0 = transform_gather(0)
-    sizes = np.array([len(a) for a in stages0], np.int64)
-    assert np.all(sizes % 4 == 0)
-    chunks, k0, acc, off = [], 0, 0, 0
-    for k in range(D):
-        if acc > 0 and acc + sizes[k] > STREAM_CHUNK_FLOATS:
-            chunks.append((k0, k, off, acc))
-            off += acc
-            k0, acc = k, 0
-        acc += int(sizes[k])
-    chunks.append((k0, D, off, acc))
-    chunks = np.asarray(chunks, np.int64)
-    tstride = int(sizes.sum())
-    slot_floats = int(chunks[:, 3].max())
-    gather = np.concatenate([np.concatenate(transform_gather(t)) for t in range(T)])
-    assert gather.size == T * tstride
-    tables = [gstart, nchunk, chunks.reshape(-1)]
-    meta = np.zeros(META_HEADER, np.int64)
-    meta[[M_D, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE]] = [D, H, L, T, kind, total, lay.tp, ng, tstride]
-    meta[M_MAXCH] = int(nchunk.max())
-    meta[M_RAW_TSTRIDE] = lay.raw_tstride
-    meta[M_BINS] = bins
-    meta[M_VERSION] = 5
+    meta[M_VERSION] = 2
     meta[M_NCHUNKS] = len(chunks)
     meta[M_SLOT_FLOATS] = slot_floats
     pos = META_HEADER
@@ -721,324 +533,3 @@ def build_train(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kin
         [D, Dp, H, L, T, No, tstride, bias_off, lay.raw_tstride, len(maps[0]), len(tiles), 200]
     return TrainLayout(tstride, bias_off, len(maps[0]), meta.astype(np.int32), gather.astype(np.int32), wmap.astype(np.int32),
                        np.asarray(tiles, np.int32).reshape(-1, 4))
-
-
-# ---------------------------------------------------------------------------------------------
-# blocked sweep (csrc/flow_block.cu): degree blocks, dense part on the warp tensor path, triangular
-# part as short fp32 dot products
-# ---------------------------------------------------------------------------------------------
-# The degree-ordered sweep is a (nonlinear) forward substitution: a unit of degree g needs every unit of
-# degree <= g of the layer below.  Split the degrees into blocks.  Everything a block needs from EARLIER
-# blocks is final before the block starts and is one dense product per layer ("phase A": [units of the
-# block] x [all earlier units], mma.sync m16n8k8 with a 3xTF32 split, no dependency chain); what is left
-# inside the block ("phase B") is the same hop-by-hop sweep with dot products over at most one block of
-# units.  Phase A carries 75-90 % of the multiply-accumulates.
-#
-# The kernel is an interpreter over a per-transform PROGRAM of 8-int ops whose weights sit in the stream
-# in exactly the order the ops consume them (one transform = one program pass; every transform has the
-# same program, only the weights and the feature order differ):
-#   OP_MMA   [0, src array (0: xs, l: act[l-1]), first src column, k-steps, dst array (l+1: act[l], L+1: ph),
-#             first dst row, tiles (1..3 consecutive 16-row tiles sharing the B operand), flags]
-#            flags FIRST (accumulators := bias fragments) / LAST (store to dst)
-#            weights: [FIRST: tiles x 32 lanes x 4 bias]  then per k-step, per tile: [32 lanes x 4 hi][32 lanes x 4 lo]
-#   OP_STEP  [1, k | ph_row << 16, out_rows | block_base << 16, first unit | units << 16, l0_col | l0_rows << 16,
-#             hidden rows, 0, flags]: one order position k and the degree group g = k+1 behind it.  Only the NEW
-#            values of the step travel through registers / shuffles (the critical chain x_k -> h_0 -> .. -> h_{L-1}
-#            -> their share of output k+1); everything that was final before the step ("old" rows, read from shared
-#            memory) is off that chain.  passes P = ceil(units / 4), slots = 4 P.  Weights, in order:
-#              out_old [out_rows/4][2 params][4]          output k over the block's units of degree < k
-#              l0_old  [l0_rows/4][slots][4], l0_new [slots]       layer 0: orders of the block before k, then order k
-#              per layer l >= 1: old [hidden rows/4][slots][4] (block units of degree <= k), new [slots dst][slots src]
-#              out_new [2 params][slots]   (flag NEXTOUT)  share of the group in output k+1, carried to the next step
-#            flag BLOCKFIRST: nothing is carried into this step.
-OP_MMA, OP_STEP = 0, 1
-BF_FIRST, BF_LAST, BF_NEWCHUNK, BF_BLOCKFIRST, BF_NEXTOUT = 1, 2, 4, 8, 16
-M_OFF_PROG, M_NOPS, M_HPB, M_SX, M_SO = 26, 27, 28, 29, 30
-BLOCK_CHUNK_FLOATS = 4096         # target size of one bulk copy (16 KB)
-BLOCK_STAGES = 4                  # ring depth (keep in sync with csrc/flow_block.cu)
-BLOCK_MMA_FLOATS = 3328           # weights per OP_MMA piece (k-steps x tiles x 256 floats), below one chunk
-BLOCK_MAX_STEPS = 8               # order positions per block (their 2 x 8 outputs are one 16-row MMA tile)
-BLOCK_PLAIN = 1 << 30             # gather code: plain copy (pmc_flow_tc_pack: >= 0 hi, -(g+2) lo, -1 zero)
-BLOCK_SMEM_BUDGET = 227 * 1024
-
-
-@dataclass(frozen=True)
-class BlockLayout:
-    tstride: int
-    slot_floats: int
-    n_chunks: int
-    n_ops: int
-    hpb: int               # hidden units padded block-wise to multiples of 16
-    sx: int                # row stride of xs [8 particles][sx]
-    sh: int                # row stride of act[l] [8 particles][sh]
-    so: int                # row stride of ph [8 particles][so]
-    blocks: tuple          # (glo, ghi) degree range per block
-    prog: np.ndarray       # [n_ops, 8] int32
-    chunks: np.ndarray     # [n_chunks, 4] (0, 0, float offset, float count)
-    meta: np.ndarray
-    gather: np.ndarray
-
-    @property
-    def numel(self):
-        return int(self.gather.size)
-
-    def warp_floats(self, n_dim, n_layers):
-        return 8 * n_dim + 8 * self.sx + n_layers * 8 * self.sh + 8 * self.so
-
-
-def _degree_blocks(n_dim: int, n_hidden: int, block_units: int):
-    """Consecutive degree ranges [glo, ghi): at most BLOCK_MAX_STEPS order positions and ~block_units units each."""
-    ng = n_dim - 1
-    gsize = np.bincount((np.arange(n_hidden) % ng) + 1, minlength=ng + 1)[1:]
-    blocks, g = [], 1
-    while g <= ng:
-        ghi, cnt = g, 0
-        while ghi <= ng and (cnt == 0 or cnt + gsize[ghi - 1] <= block_units + 16) and ghi - g < BLOCK_MAX_STEPS:
-            cnt += int(gsize[ghi - 1])
-            ghi += 1
-        if ghi == ng + 1 and ghi - g == BLOCK_MAX_STEPS:       # the last block also owns the final output position
-            ghi -= 1
-        blocks.append((g, ghi))
-        g = ghi
-    return blocks, gsize
-
-
-def block_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int, block_units: int = 32) -> bool:
-    """Affine transforms whose per-warp activations (8 particles) + ring fit shared memory with >= 3 warps."""
-    if kind != KIND_AFFINE or n_dim < 3 or n_hidden < 2 * block_units:
-        return False
-    blocks, gsize = _degree_blocks(n_dim, n_hidden, block_units)
-    if gsize.max() > 8:
-        return False
-    hpb = sum((int(((gsize[glo - 1:ghi - 1] + 3) // 4 * 4).sum()) + 15) // 16 * 16 for glo, ghi in blocks)
-    per_warp = (8 * n_dim + 8 * (n_dim + 24) + n_layers * 8 * (hpb + 4) + 8 * 36) * 4
-    n_ops = len(blocks) * (n_layers + 1) * (2 + hpb * 64 // BLOCK_MMA_FLOATS) + n_dim
-    return BLOCK_STAGES * BLOCK_CHUNK_FLOATS * 4 + 3 * per_warp + 32 * n_ops + 4096 <= BLOCK_SMEM_BUDGET
-
-
-@lru_cache(maxsize=None)
-def build_block(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8,
-                block_units: int = 32) -> BlockLayout:
-    if kind != KIND_AFFINE:
-        raise ValueError("the blocked sweep is built for affine (MAF) transforms")
-    lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
-    D, H, L, T, total = lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.total
-    ng = D - 1
-    hperm, degree = lay.hperm, lay.degree
-    gstart = np.searchsorted(degree, np.arange(1, ng + 2), side="left").astype(np.int64)   # gstart[g-1] = first unit of degree g
-    gsize = np.diff(gstart)
-    raw_off = np.concatenate([[0], np.cumsum([int(np.prod(sh)) for sh in lay.raw_sizes])]).astype(np.int64)
-
-    blocks, _ = _degree_blocks(D, H, block_units)
-    nb = len(blocks)
-    # padded unit index space: every degree group occupies 4 * passes slots (passes = ceil(size / 4) <= 2) so that a
-    # group starts on a 16-byte boundary; every block is padded to whole 16-row MMA tiles
-    npass = (gsize + 3) // 4
-    assert npass.max() <= 2, "more than 8 hidden units per degree"
-    u0_of = np.zeros(ng + 2, np.int64)              # padded index of the first unit of degree g
-    pb = np.zeros(nb + 1, np.int64)
-    for j, (glo, ghi) in enumerate(blocks):
-        cur = int(pb[j])
-        for g in range(glo, ghi):
-            u0_of[g] = cur
-            cur += 4 * int(npass[g - 1])
-        pb[j + 1] = pb[j] + (cur - pb[j] + 15) // 16 * 16
-    ps = np.diff(pb)
-    hpb = int(pb[-1])
-    pad2sorted = np.full(hpb, -1, np.int64)
-    for g in range(1, ng + 1):
-        pad2sorted[u0_of[g]:u0_of[g] + gsize[g - 1]] = np.arange(gstart[g - 1], gstart[g])
-    pad2unit = np.where(pad2sorted >= 0, hperm[np.maximum(pad2sorted, 0)], -1)      # padded slot -> original hidden unit
-
-    steps = [list(range(glo - 1, ghi - 1)) for glo, ghi in blocks]
-    steps[-1].append(D - 1)            # the last output has no hidden group behind it
-    max_steps = max(len(s) for s in steps)
-    os_rows = (2 * max_steps + 15) // 16 * 16
-    sx = (D + 7) // 8 * 8 + 8 + 4
-    sh = hpb + 4
-    so = os_rows + 4
-
-    lane = np.arange(32)
-    fr, fc = lane >> 2, lane & 3
-
-    def a_fragments(dense):
-        """dense [16, K8] raw indices (-1 = 0) -> per k-step hi image then lo image in m16n8k8 A-fragment order."""
-        parts = []
-        for ks in range(dense.shape[1] // 8):
-            tile = dense[:, 8 * ks:8 * ks + 8]
-            frag = np.stack([tile[fr, fc], tile[fr + 8, fc], tile[fr, fc + 4], tile[fr + 8, fc + 4]], axis=1).reshape(-1)
-            parts.append(frag)
-            parts.append(np.where(frag >= 0, -(frag + 2), -1))
-        return parts
-
-    def bias_fragment(b16):
-        b16 = np.asarray(b16, np.int64)
-        frag = np.stack([b16[fr], b16[fr], b16[fr + 8], b16[fr + 8]], axis=1).reshape(-1)
-        return np.where(frag >= 0, frag | BLOCK_PLAIN, -1)
-
-    def transform_program(t):
-        """(ops [n,8] without chunk flags, list of per-op gather arrays) of transform t."""
-        base_r = t * lay.raw_tstride
-        iperm = np.arange(D) if t % 2 == 0 else D - 1 - np.arange(D)
-        wl_off = [base_r + raw_off[2 * l] for l in range(L + 1)]
-        bl_off = [base_r + raw_off[2 * l + 1] for l in range(L + 1)]
-        ops, ws = [], []
-
-        def emit_mma(src, kcols, dst, row0, denses, biases):
-            """consecutive 16-row tiles sharing the B operand: bias + dense[16, kcols] . src[:, 0:kcols] each, split
-            into pieces of at most BLOCK_MMA_FLOATS weights"""
-            nt = len(denses)
-            frs = [a_fragments(dn) if kcols > 0 else [] for dn in denses]
-            nks = kcols // 8
-            per = max(1, BLOCK_MMA_FLOATS // (256 * nt))
-            pieces = [(k0, min(k0 + per, nks)) for k0 in range(0, nks, per)] if nks > 0 else [(0, 0)]
-            for i, (k0, k1) in enumerate(pieces):
-                flags = (BF_FIRST if i == 0 else 0) | (BF_LAST if i == len(pieces) - 1 else 0)
-                w = [bias_fragment(b) for b in biases] if i == 0 else []
-                for ks in range(k0, k1):
-                    for tl in range(nt):
-                        w += frs[tl][2 * ks:2 * ks + 2]
-                ops.append([OP_MMA, src, 8 * k0, k1 - k0, dst, row0, nt, flags])
-                ws.append(np.concatenate(w) if w else np.zeros(0, np.int64))
-
-        def tile_groups(n_tiles):
-            m = 0
-            while m < n_tiles:
-                take = min(3, n_tiles - m) if n_tiles - m != 4 else 2
-                yield list(range(m, m + take))
-                m += take
-
-        def old_rows(row_units, dst_units, width, w_off, valid=None):
-            """[rows/4][slots][4] block: weight of (dst unit slot, row) or -1; row_units / dst_units are raw unit / column
-            keys (-1 = padding)"""
-            rows, slots = len(row_units), len(dst_units)
-            full = w_off + dst_units[None, :, None] * width + row_units.reshape(-1, 1, 4)
-            ok = (dst_units >= 0)[None, :, None] & (row_units >= 0).reshape(-1, 1, 4)
-            if valid is not None:
-                ok = ok & valid.reshape(-1, 1, 4)
-            return np.where(ok, full, -1).reshape(-1)
-
-        for j, (glo, ghi) in enumerate(blocks):
-            pbj = int(pb[j])
-            # ---------------- phase A: contributions of everything before the block ----------------
-            for l in range(L):
-                kcols = (glo - 1 + 7) // 8 * 8 if l == 0 else pbj
-                for grp in tile_groups(int(ps[j]) // 16):
-                    denses, biases = [], []
-                    for m in grp:
-                        units = pad2unit[pbj + 16 * m: pbj + 16 * m + 16]
-                        ok = units >= 0
-                        dense = np.full((16, kcols), -1, np.int64)
-                        if kcols > 0:
-                            if l == 0:
-                                c = np.arange(kcols)
-                                cols = np.where(c < glo - 1, iperm[np.minimum(c, D - 1)], -1)
-                                width = D
-                            else:
-                                cols = pad2unit[:kcols]
-                                width = H
-                            dense = np.where(ok[:, None] & (cols >= 0)[None, :], wl_off[l] + units[:, None] * width + cols[None, :], -1)
-                        denses.append(dense)
-                        biases.append(np.where(ok, bl_off[l] + units, -1))
-                    emit_mma(0 if l == 0 else l, kcols, l + 1, pbj + 16 * grp[0], denses, biases)
-            st = steps[j]
-            for grp in tile_groups((2 * len(st) + 15) // 16):
-                denses, biases = [], []
-                for m in grp:
-                    r = 16 * m + np.arange(16)
-                    si, par = r // 2, r % 2
-                    ok = si < len(st)
-                    kk = np.asarray(st)[np.minimum(si, len(st) - 1)]
-                    orow = iperm[kk] * total + par
-                    dense = np.full((16, pbj), -1, np.int64)
-                    if pbj > 0:
-                        cols = pad2unit[:pbj]
-                        dense = np.where(ok[:, None] & (cols >= 0)[None, :], wl_off[L] + orow[:, None] * H + cols[None, :], -1)
-                    denses.append(dense)
-                    biases.append(np.where(ok, bl_off[L] + orow, -1))
-                emit_mma(L, pbj, L + 1, 16 * grp[0], denses, biases)
-            # ---------------- phase B: the sweep inside the block ----------------
-            for si, k in enumerate(st):
-                feat = int(iperm[k])
-                w = []
-                # output hop of position k over the block's units of degree < k (degree k itself arrives in registers)
-                out_old = int(u0_of[k]) - pbj if k >= glo else 0
-                if out_old > 0:
-                    rows = pad2unit[pbj:pbj + out_old]
-                    w.append(old_rows(rows, feat * total + np.arange(2), H, wl_off[L]))
-                g = k + 1
-                u0 = cnt = l0_d0 = l0_r = lh = 0
-                flags = (BF_BLOCKFIRST if si == 0 else 0) | (BF_NEXTOUT if si + 1 < len(st) else 0)
-                if g <= ng and gsize[g - 1] > 0:
-                    u0, cnt = int(u0_of[g]), int(gsize[g - 1])
-                    P4 = 4 * int(npass[g - 1])
-                    units = pad2unit[u0:u0 + P4]
-                    lh = u0 - pbj
-                    # layer 0: orders of the block before k ("old"), then order k itself
-                    o_lo = glo - 1
-                    l0_d0 = o_lo // 4 * 4
-                    l0_r = (k - l0_d0 + 3) // 4 * 4
-                    if l0_r > 0:
-                        orders = l0_d0 + np.arange(l0_r)
-                        okr = (orders >= o_lo) & (orders < k)
-                        w.append(old_rows(np.where(okr, iperm[np.minimum(orders, D - 1)], -1), units, D, wl_off[0]))
-                    w.append(np.where(units >= 0, wl_off[0] + units * D + feat, -1))
-                    for l in range(1, L):
-                        if lh > 0:
-                            w.append(old_rows(pad2unit[pbj:u0], units, H, wl_off[l]))
-                        nw = np.where((units >= 0)[:, None] & (units >= 0)[None, :], wl_off[l] + units[:, None] * H + units[None, :], -1)
-                        w.append(nw.reshape(-1))                       # [dst slot][src slot]
-                    if flags & BF_NEXTOUT:
-                        nfeat = int(iperm[k + 1])
-                        orow = nfeat * total + np.arange(2)
-                        w.append(np.where((units >= 0)[None, :], wl_off[L] + orow[:, None] * H + units[None, :], -1).reshape(-1))
-                assert max(k, 2 * si, out_old, pbj, u0, cnt, l0_d0, l0_r, lh) < 2 ** 15
-                ops.append([OP_STEP, k | (2 * si) << 16, out_old | pbj << 16, u0 | cnt << 16, l0_d0 | l0_r << 16, lh, 0, flags])
-                wcat = np.concatenate(w) if w else np.zeros(0, np.int64)
-                ws.append(np.where(wcat >= 0, wcat | BLOCK_PLAIN, -1))
-        return np.asarray(ops, np.int64), ws
-
-    ops0, ws0 = transform_program(0)
-    sizes = np.array([len(w) for w in ws0], np.int64)
-    assert np.all(sizes % 4 == 0)
-    chunks, off, acc = [], 0, 0
-    for i in range(len(ops0)):
-        if i == 0 or (acc > 0 and sizes[i] > 0 and acc + sizes[i] > BLOCK_CHUNK_FLOATS):
-            if i > 0:
-                chunks.append((0, 0, off, acc))
-                off += acc
-                acc = 0
-            ops0[i, 7] |= BF_NEWCHUNK
-        acc += int(sizes[i])
-    chunks.append((0, 0, off, acc))
-    chunks = np.asarray(chunks, np.int64)
-    assert np.all(chunks[:, 3] > 0)
-    tstride = int(sizes.sum())
-    slot_floats = int(chunks[:, 3].max())
-    gathers = []
-    for t in range(T):
-        ops_t, ws_t = transform_program(t)
-        assert np.array_equal(ops_t[:, :7], ops0[:, :7]) and [len(w) for w in ws_t] == list(sizes)
-        gathers.append(np.concatenate(ws_t))
-    gather = np.concatenate(gathers)
-
-    meta = np.zeros(META_HEADER, np.int64)
-    meta[[M_D, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE]] = [D, H, L, T, kind, total, lay.tp, ng, tstride]
-    meta[M_RAW_TSTRIDE] = lay.raw_tstride
-    meta[M_BINS] = bins
-    meta[M_VERSION] = 4
-    meta[M_NCHUNKS] = len(chunks)
-    meta[M_SLOT_FLOATS] = slot_floats
-    meta[[M_NOPS, M_HPB, M_SX, M_SO]] = [len(ops0), hpb, sx, so]
-    pos = META_HEADER
-    meta[M_OFF_CHUNKS] = pos
-    pos += chunks.size
-    pos = (pos + 3) // 4 * 4                       # the program is read with 16-byte loads
-    meta[M_OFF_PROG] = pos
-    body = np.zeros(pos - META_HEADER + ops0.size, np.int64)
-    body[:chunks.size] = chunks.reshape(-1)
-    body[pos - META_HEADER:] = ops0.reshape(-1)
-    meta = np.concatenate([meta, body])
-    assert np.abs(gather[gather < BLOCK_PLAIN]).max() < 2 ** 29 and meta.max() < 2 ** 31
-    return BlockLayout(tstride, slot_floats, len(chunks), len(ops0), hpb, sx, sh, so, tuple(blocks), ops0.astype(np.int32),
-                       chunks, meta.astype(np.int32), gather.astype(np.int32))

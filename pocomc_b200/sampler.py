@@ -411,38 +411,13 @@ class Sampler:
         return current_particles
 
     def _log_like(self, x):
-        """Host black box: vectorised call, pool.map or plain map, with blob extraction
-        (sampler.py:807-861)."""
+        """Host black box (sampler.py:807-861): one vectorised call, or one call per row (through ``pool.map`` when a
+        pool was given).  A row result may be ``logl`` or ``(logl, blob, ...)``; blobs come back as one array."""
         if self.vectorize:
             return self.log_likelihood(x), None
-        if self.pool is not None:
-            results = list(self.distribute(self.log_likelihood, x))
-        else:
-            results = list(map(self.log_likelihood, x))
-        try:
-            blob = [r[1:] for r in results if len(r) > 1]
-            if not len(blob):
-                raise IndexError
-            logl = np.array([float(r[0]) for r in results])
-            self.have_blobs = True
-        except (IndexError, TypeError):
-            return np.array([float(r) for r in results]), None
-        if self.blobs_dtype is not None:
-            dt = self.blobs_dtype
-        else:
-            try:
-                dt = np.atleast_1d(blob[0]).dtype
-            except ValueError:
-                dt = np.dtype("object")
-            if dt.kind in "US":
-                dt = np.dtype("object")
-        blob = np.array(blob, dtype=dt)
-        shape = blob.shape[1:]
-        if len(shape):
-            axes = np.arange(len(shape))[np.array(shape) == 1] + 1
-            if len(axes):
-                blob = np.squeeze(blob, tuple(axes))
-        return logl, blob
+        mapper = self.distribute if self.pool is not None else map
+        rows = list(mapper(self.log_likelihood, x))
+        return _split_blobs(rows, self.blobs_dtype, self)
 
     # ------------------------------------------------------------------------------------------
     # evidence / posterior / results
@@ -545,3 +520,38 @@ class Sampler:
         with open(path, 'rb') as f:
             state = dill.load(file=f)
         self.__dict__ = {**self.__dict__, **state}
+
+
+def _split_blobs(rows, blobs_dtype, owner=None):
+    """Separate per-row likelihood results into (logl [n], blobs | None).
+
+    Scalars (anything without ``len``) mean "no blobs".  With tuple-like rows the first entry is the
+    log-likelihood and the rest is the blob; the blob array takes ``blobs_dtype`` if given, else the dtype numpy
+    infers from the first blob -- except text, which is stored as objects so that strings are never truncated --
+    and length-1 trailing axes are dropped so that a single scalar blob per row yields a 1-d array."""
+    tails = None
+    try:
+        if all(len(r) > 1 for r in rows) and len(rows):
+            tails = [r[1:] for r in rows]
+        elif any(len(r) > 1 for r in rows):
+            tails = [r[1:] for r in rows if len(r) > 1]
+    except TypeError:
+        tails = None
+    if not tails:
+        return np.array([float(r) for r in rows]), None
+    logl = np.array([float(r[0]) for r in rows])
+    if owner is not None:
+        owner.have_blobs = True
+    dtype = blobs_dtype
+    if dtype is None:
+        try:
+            dtype = np.atleast_1d(tails[0]).dtype
+        except ValueError:          # ragged first blob
+            dtype = np.dtype(object)
+        if dtype.kind in ("U", "S"):
+            dtype = np.dtype(object)
+    blobs = np.array(tails, dtype=dtype)
+    unit_axes = tuple(i for i in range(1, blobs.ndim) if blobs.shape[i] == 1)
+    if unit_axes:
+        blobs = np.squeeze(blobs, unit_axes)
+    return logl, blobs

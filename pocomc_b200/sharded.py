@@ -1,4 +1,4 @@
-"""History sharded by particle -- EXPERIMENTAL building block, not yet wired into ``Sampler``.
+"""History sharded by particle -- opt-in (``config.shard_history``); validated on B200 (profiles/r2a_experimental_tests.log).
 
 ``Sampler._mutate_sharded`` already splits the mutation step over the ranks but every rank keeps the whole
 particle history (T iterations x N particles x (2 D + 3) f64), which does not fit a host at BASELINE configs 4-5.

@@ -65,73 +65,12 @@ def test_sweep_vs_oracle_sizes(preset, d, n):
     np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **tol)
 
 
-@pytest.mark.parametrize("preset,d,n", [("maf6", 32, 700), ("nsf3", 5, 100), ("maf3", 3, 17)])
-def test_warp_mma_variant_matches_oracle(preset, d, n):
-    """the opt-in warp-MMA (3xTF32 mma.sync) sweep meets the same fp32 parity bar as the FFMA kernel"""
-    from pocomc_b200 import config
-    torch.manual_seed(d + n)
-    ref = F.make_flow(d, preset)
-    old = config.sweep_variant
-    config.sweep_variant = "mma"
-    try:
-        f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
-    finally:
-        config.sweep_variant = old
-    assert int(f.flow._meta_host[22]) == 3
-    x = torch.randn(n, d)
-    with torch.no_grad():
-        z_ref, l_ref = ref().transform.call_and_ladj(x)
-        xi_ref, li_ref = ref().transform.inv.call_and_ladj(z_ref)
-        z, l = f.forward(x)
-        xi, li = f.inverse(z_ref)
-    tol = dict(rtol=5e-5, atol=5e-5) if preset.startswith("maf") else dict(rtol=5e-4, atol=5e-4)
-    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **tol)
-    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), **tol)
-    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), **tol)
-    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **tol)
-
-
-@pytest.mark.parametrize("preset,d,n", [("maf6", 32, 1000), ("maf3", 16, 7), ("maf3", 20, 333), ("maf6", 33, 80),
-                                        ("maf12", 50, 300), ("maf6", 32, 20011)])
-def test_blocked_sweep_matches_oracle(preset, d, n):
-    """opt-in blocked sweep of affine flows (csrc/flow_block.cu: dense part of every degree block on mma.sync 3xTF32,
-    triangular part hop by hop with shuffle hand-over): BOTH directions through the sweep kernel against the oracle's 1-pass
-    forward / D+1-pass inverse, ragged tiles and multi-wave launches included; fp32 bar 5e-5"""
-    from pocomc_b200 import config
-    torch.manual_seed(d * 3 + n)
-    ref = F.make_flow(d, preset)
-    old = config.sweep_variant
-    config.sweep_variant = "block"
-    try:
-        f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
-    finally:
-        config.sweep_variant = old
-    assert int(f.flow._meta_host[22]) == 4, "blocked layout not selected"
-    x = torch.randn(n, d)
-    with torch.no_grad():
-        z_ref, l_ref = ref().transform.call_and_ladj(x)
-        xi_ref, li_ref = ref().transform.inv.call_and_ladj(z_ref)
-        z, l = f.flow.sweep(x, inverse=False)
-        xi, li = f.flow.sweep(z_ref, inverse=True)
-    tol = dict(rtol=5e-5, atol=5e-5)
-    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **tol)
-    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), **tol)
-    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), **tol)
-    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **tol)
-
-
 @pytest.mark.parametrize("preset,d,n", [("maf6", 32, 1000), ("maf12", 50, 300)])
 def test_ffma_stream_variant_matches_oracle(preset, d, n):
     """the default fp32-FMA TMA-stream sweep, both directions through the sweep kernel (Flow.forward itself takes tcgen05)"""
-    from pocomc_b200 import config
     torch.manual_seed(d + 2 * n)
     ref = F.make_flow(d, preset)
-    old = config.sweep_variant
-    config.sweep_variant = "ffma"
-    try:
-        f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
-    finally:
-        config.sweep_variant = old
+    f = _mine(preset, d, [p.detach().numpy() for p in ref.parameters()])
     assert int(f.flow._meta_host[22]) == 2
     x = torch.randn(n, d)
     with torch.no_grad():

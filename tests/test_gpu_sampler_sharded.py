@@ -82,9 +82,6 @@ def test_sharded_run_equals_single_process(kwargs):
         assert got["logz"] == single["logz"]
 
 
-@pytest.mark.skipif(os.environ.get("PMC_B200_EXPERIMENTAL") != "1",
-                    reason="particle-sharded HISTORY (config.shard_history, pocomc_b200.sharded) is pinned on the CPU over "
-                           "gloo with numpy stand-ins for the kernels but has not run on GPUs yet: set PMC_B200_EXPERIMENTAL=1")
 def test_sharded_history_run_equals_single_process(monkeypatch):
     """Same bar as above with every rank storing only its block of the history (probe statistics merged in rank
     order, weights gathered as scalars, trimmed rows gathered by owner)."""

@@ -6,7 +6,7 @@ import torch
 
 import flow_ref as F
 from pocomc_b200 import made_layout as ML
-from sweep_emul import pack, pack_stream, sweep, sweep_stream, sweep_stream_mma
+from sweep_emul import pack, pack_stream, sweep, sweep_stream
 
 
 def _raw(flow):
@@ -50,16 +50,6 @@ def test_sweep_matches_oracle(preset, d, faithful_fp32_oracle):
     tol2 = 5e-3 if (d <= 5 and kind == "maf") else tol     # the x1.5 weights amplify fp32 summation-order noise
     np.testing.assert_allclose(x2, xs, rtol=tol2, atol=tol2)
     np.testing.assert_allclose(li2, lis, rtol=tol2, atol=tol2)
-    # ... and the mma.sync B-fragment ordered variant (warp-MMA kernel)
-    sm = ML.build_stream(d, F.hidden_width(d), 3, T, lay.kind, variant="mma")
-    spm = pack_stream(sm, raw)
-    assert sm.meta[ML.M_VERSION] == 3 and np.all(sm.chunks[:, 2] % 4 == 0) and np.all(sm.chunks[:, 3] % 4 == 0)
-    z3, l3 = sweep_stream_mma(lay, sm, spm, x.numpy(), inverse=False)
-    np.testing.assert_allclose(z3, zs, rtol=1e-5, atol=1e-5)
-    np.testing.assert_allclose(l3, ls, rtol=1e-5, atol=1e-5)
-    x3, li3 = sweep_stream_mma(lay, sm, spm, z.numpy(), inverse=True)
-    np.testing.assert_allclose(x3, xs, rtol=tol2, atol=tol2)
-    np.testing.assert_allclose(li3, lis, rtol=tol2, atol=tol2)
 
 
 def test_masks_match_oracle():
@@ -76,85 +66,3 @@ def test_masks_match_oracle():
 def test_one_dim_rejected():
     with pytest.raises(ValueError):
         ML.build_layout(1, 32, 3, 3, ML.KIND_AFFINE)
-
-
-@pytest.mark.parametrize("preset,d", [("maf3", 16), ("maf6", 32), ("maf3", 20), ("maf3", 33), ("maf3", 50)])
-def test_block_program_matches_oracle(preset, d):
-    """The blocked sweep's op program + weight stream (made_layout.build_block), executed by a numpy
-    interpreter that mirrors csrc/flow_block.cu (array strides, MMA fragment orders, hi/lo split),
-    reproduces the zuko oracle's forward and (D+1)-pass inverse."""
-    from sweep_emul import pack_block, sweep_block
-    torch.manual_seed(d)
-    flow = F.make_flow(d, preset)
-    kind, T = F.PRESETS[preset]
-    H = F.hidden_width(d)
-    assert ML.block_supported(d, H, 3, ML.KIND_AFFINE)
-    blk = ML.build_block(d, H, 3, T, ML.KIND_AFFINE)
-    raw = _raw(flow)
-    assert blk.meta[ML.M_VERSION] == 4 and blk.chunks[:, 3].max() == blk.slot_floats <= ML.BLOCK_CHUNK_FLOATS + 2048
-    assert np.all(blk.chunks[:, 2] % 4 == 0) and np.all(blk.chunks[:, 3] % 4 == 0)
-    packed = pack_block(blk, raw)
-    x = (torch.randn(11, d) * 1.3).float()
-    with torch.no_grad():
-        z, ladj = flow().transform.call_and_ladj(x)
-        xi, li = flow().transform.inv.call_and_ladj(z)
-    zs, ls = sweep_block(blk, packed, x.numpy(), inverse=False)
-    np.testing.assert_allclose(zs, z.numpy(), rtol=1e-4, atol=2e-5)
-    np.testing.assert_allclose(ls, ladj.numpy(), rtol=1e-4, atol=2e-5)
-    xb, lb = sweep_block(blk, packed, z.numpy(), inverse=True)
-    np.testing.assert_allclose(xb, xi.numpy(), rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(lb, li.numpy(), rtol=1e-4, atol=1e-4)
-
-
-@pytest.mark.parametrize("preset,d", [("maf3", 6), ("maf6", 10), ("maf3", 21), ("maf6", 32), ("maf3", 50)])
-def test_bulk_tip_stream_matches_oracle(preset, d, faithful_fp32_oracle):
-    """made_layout.build_stream_tip (experimental bulk/tip sweep, csrc/flow_tip.cu): the stream's gather map and the
-    bulk + tip decomposition of every dot product reproduce the oracle's forward and inverse."""
-    from sweep_emul import pack_stream, sweep_stream_tip
-    torch.manual_seed(100 + d)
-    flow = F.make_flow(d, preset)
-    kind, T = F.PRESETS[preset]
-    h = F.hidden_width(d)
-    assert ML.tip_supported(d, h, 3, ML.KIND_AFFINE)
-    lay = ML.build_layout(d, h, 3, T, ML.KIND_AFFINE)
-    st = ML.build_stream_tip(d, h, 3, T)
-    packed = pack_stream(st, _raw(flow))
-    x = (torch.randn(24, d) * 1.3).float()
-    with torch.no_grad():
-        z, ladj = flow().transform.call_and_ladj(x)
-        xi, li = flow().transform.inv.call_and_ladj(z)
-    zs, ls = sweep_stream_tip(lay, st, packed, x.numpy(), inverse=False)
-    np.testing.assert_allclose(zs, z.numpy(), rtol=1e-4, atol=2e-5)
-    np.testing.assert_allclose(ls, ladj.numpy(), rtol=1e-4, atol=2e-5)
-    xs, lis = sweep_stream_tip(lay, st, packed, z.numpy(), inverse=True)
-    np.testing.assert_allclose(xs, xi.numpy(), rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(lis, li.numpy(), rtol=1e-4, atol=1e-4)
-
-
-def test_bulk_tip_stream_support_matrix():
-    assert not ML.tip_supported(2, 32, 3, ML.KIND_AFFINE)        # one degree group of 32 units
-    assert not ML.tip_supported(32, 128, 3, ML.KIND_RQS)
-    assert ML.tip_supported(100, 512, 3, ML.KIND_AFFINE) == ML.stream_supported(100, 512, 3, ML.KIND_AFFINE)
-
-
-@pytest.mark.parametrize("ppl", [1, 2, 4])
-@pytest.mark.parametrize("preset,d,n", [("maf3", 6, 11), ("maf3", 21, 37)])
-def test_bulk_tip_lane_mapping(preset, d, n, ppl, faithful_fp32_oracle):
-    """Lane-level transliteration of csrc/flow_tip.cu (32 lanes, shuffles, the kernel's shared-memory index
-    expressions) for 1, 2 and 4 particles per lane against the oracle, ragged last warp tile included."""
-    from sweep_emul import pack_stream, sweep_tip_lanes
-    torch.manual_seed(7 * d + ppl)
-    flow = F.make_flow(d, preset)
-    kind, T = F.PRESETS[preset]
-    st = ML.build_stream_tip(d, F.hidden_width(d), 3, T)
-    packed = pack_stream(st, _raw(flow))
-    x = (torch.randn(n, d) * 1.2).float()
-    with torch.no_grad():
-        z, ladj = flow().transform.call_and_ladj(x)
-        xi, li = flow().transform.inv.call_and_ladj(z)
-    zs, ls = sweep_tip_lanes(st, packed, x.numpy(), False, ppl)
-    np.testing.assert_allclose(zs, z.numpy(), rtol=1e-4, atol=2e-5)
-    np.testing.assert_allclose(ls, ladj.numpy(), rtol=1e-4, atol=2e-5)
-    xs, lis = sweep_tip_lanes(st, packed, z.numpy(), True, ppl)
-    np.testing.assert_allclose(xs, xi.numpy(), rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(lis, li.numpy(), rtol=1e-4, atol=1e-4)
