@@ -176,7 +176,9 @@ def _draw_noise(seed, n, d, shape, steps):
     return g, z, r
 
 
-def golden_mcmc():
+def golden_mcmc(variants=(("free", False, "maf3"), ("bounded", True, "maf3"))):
+    """tag, bounded prior?, flow preset.  ("nsf", True, "nsf3") records the spline-flow variant (the reference's default
+    flow family, sampler.py:169) through the two flow-preconditioned kernels -> tests/golden/mcmc_nsf.npz."""
     D, N = 4, 96
     rng = np.random.default_rng(3)
     C = 0.6 * np.ones((D, D)) + 0.4 * np.eye(D)
@@ -185,7 +187,7 @@ def golden_mcmc():
     def loglike(x):
         return -0.5 * np.einsum("ki,ij,kj->k", x, Ci, x)
 
-    for bounded in (False, True):
+    for tag, bounded, preset in variants:
         if bounded:
             dists = [uniform(-6, 12), norm(0, 3), uniform(-6, 12), norm(0, 3)]
         else:
@@ -200,7 +202,7 @@ def golden_mcmc():
         _, ldj0 = scaler.inverse(u0)
         state = dict(u=u0, x=x0, logdetj=ldj0, logl=loglike(x0), logp=prior.logpdf(x0), beta=0.7, blobs=None)
         torch.manual_seed(4)
-        flow = pocomc.Flow(D, "maf3")
+        flow = pocomc.Flow(D, preset)
         # a few optimiser steps so the flow is not the identity-ish initialisation
         flow.fit(torch.tensor(u0, dtype=torch.float32), epochs=8, batch_size=48)
         wrapper = rtools.flow_numpy_wrapper(flow)
@@ -210,13 +212,14 @@ def golden_mcmc():
         geo_t.fit(theta0.astype(np.float64))
         geo_u.fit(u0)
         # force a genuinely heavy-tailed nu on one variant so the gamma mixture is exercised
-        tag = "bounded" if bounded else "free"
         out = dict(low=prior.bounds[:, 0], high=prior.bounds[:, 1], mu=scaler.mu, sigma=scaler.sigma,
                    Cinv=Ci, prior_kind=np.array([0 if isinstance(d.dist, type(norm)) else 1 for d in dists]),
                    u=u0, x=x0, logdetj=ldj0, logl=state["logl"], logp=state["logp"], beta=0.7,
                    theta0=theta0, ldjf0=ldjf0, **flow_state(flow))
         for kname, fn in (("tpcn_flow", rmcmc.preconditioned_pcn), ("rwm_flow", rmcmc.preconditioned_rwm),
                           ("tpcn", rmcmc.pcn), ("rwm", rmcmc.rwm)):
+            if preset != "maf3" and not kname.endswith("_flow"):
+                continue                                   # the flow-free kernels do not depend on the preset
             for nu_tag, nu in (("nufit", None), ("nu5", 5.0)):
                 if nu_tag == "nu5" and not kname.startswith("tpcn"):
                     continue
@@ -323,9 +326,13 @@ def golden_reweight():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["mcmc_nsf"]:                       # added in round 2; leaves the other fixtures untouched
+        golden_mcmc((("nsf", True, "nsf3"),))
+        sys.exit(0)
     golden_scaler()
     golden_smc()
     golden_geometry()
     golden_mcmc()
+    golden_mcmc((("nsf", True, "nsf3"),))
     golden_flow()
     golden_reweight()

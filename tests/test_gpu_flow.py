@@ -244,3 +244,28 @@ def test_fused_training_kernels_match_oracle_gradients(preset, d, n, weighted):
     np.testing.assert_allclose(g, gref, rtol=2e-4, atol=1e-4 * scale)
     # masked entries of the blob receive exactly zero gradient
     assert np.all(g[gref == 0] == 0)
+
+
+@pytest.mark.parametrize("preset,d,n_fwd,n_inv", [("maf6", 100, 1000, 200), ("maf3", 200, 1000, 64), ("maf6", 50, 2000, 500)])
+def test_config_shapes_vs_oracle(preset, d, n_fwd, n_inv):
+    """BASELINE configs[2..4] flow shapes (D, H) = (50, 256), (100, 512), (200, 1024) against the oracle itself (not only
+    the round-trip property): forward at n >= 1000 rows, and the oracle's true D+1-pass inverse on a smaller batch
+    (606 / 603 dense hyper-network passes on the host).  Weights scaled away from the near-identity initialisation."""
+    torch.manual_seed(d + 11)
+    ref = F.make_flow(d, preset)
+    with torch.no_grad():
+        for p_ in ref.parameters():
+            p_.mul_(1.2)
+    f = _mine(preset, d, [p_.detach().numpy() for p_ in ref.parameters()])
+    x = torch.randn(n_fwd, d)
+    with torch.no_grad():
+        z_ref, l_ref = ref().transform.call_and_ladj(x)
+        z, l = f.forward(x)
+        zi = z_ref[:n_inv].contiguous()
+        xi_ref, li_ref = ref().transform.inv.call_and_ladj(zi)
+        xi, li = f.inverse(zi)
+    tol = dict(rtol=5e-5, atol=5e-5 * max(1.0, float(z_ref.abs().max())))
+    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **tol)
+    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), rtol=5e-5, atol=5e-5 * max(1.0, float(l_ref.abs().max())))
+    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), rtol=5e-5, atol=5e-5 * max(1.0, float(xi_ref.abs().max())))
+    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), rtol=5e-5, atol=5e-5 * max(1.0, float(li_ref.abs().max())))

@@ -20,12 +20,12 @@ class _Geo:
     pass
 
 
-def _setup(g):
+def _setup(g, preset="maf3"):
     from pocomc_b200.flow import Flow
     from pocomc_b200.scaler import Reparameterize
     from scipy.stats import norm, uniform
     d = g["x"].shape[1]
-    flow = Flow(d, "maf3")
+    flow = Flow(d, preset)
     flat = np.concatenate([p.reshape(-1) for p in flow_param_list(g, "")])
     with torch.no_grad():
         flow.flow.raw.copy_(torch.from_numpy(flat).to(flow.flow.raw.device))
@@ -43,12 +43,17 @@ def _setup(g):
     return d, flow, scaler, loglike, logprior
 
 
-@pytest.mark.parametrize("tag", ["free", "bounded"])
+@pytest.mark.parametrize("tag", ["free", "bounded", "nsf"])
 @pytest.mark.parametrize("key", ["tpcn_flow_nufit", "tpcn_flow_nu5", "rwm_flow_nufit", "tpcn_nufit", "tpcn_nu5", "rwm_nufit"])
 def test_kernels_match_reference_runs(golden, tag, key):
+    """tag "nsf": the reference's default flow family (neural spline flow, sampler.py:169) through the flow-preconditioned
+    kernels; the spline's fp32 noise is ~10x the affine map's (tests/test_gpu_flow.py), so its bar is 2e-4."""
     from pocomc_b200 import mcmc, config
     g = golden("mcmc_" + tag)
-    d, flow, scaler, loglike, logprior = _setup(g)
+    if f"{key}_out_steps" not in g:
+        pytest.skip("flow-free kernels do not depend on the flow preset: recorded once (free / bounded)")
+    preset = "nsf3" if tag == "nsf" else "maf3"
+    d, flow, scaler, loglike, logprior = _setup(g, preset)
     config.set_rng_mode("host")
     kind = key.rsplit("_", 1)[0]
     fn = dict(tpcn_flow=mcmc.preconditioned_pcn, rwm_flow=mcmc.preconditioned_rwm, tpcn=mcmc.pcn, rwm=mcmc.rwm)[kind]
@@ -62,18 +67,39 @@ def test_kernels_match_reference_runs(golden, tag, key):
     res = fn(state, fd, od)
     assert res["steps"] == int(g[f"{key}_out_steps"])
     tol = dict(rtol=2e-5, atol=2e-5) if kind.endswith("flow") else dict(rtol=1e-10, atol=1e-10)
-    # rows whose accept decisions all agreed must match to rounding; allow at most 1% flipped rows
-    bad = 0
+    if tag == "nsf":
+        tol = dict(rtol=2e-4, atol=2e-4)
+    # Accept decisions are discrete: a row may leave the reference trajectory ONLY where some step's uniform draw sat
+    # within the fp32 flow noise of its acceptance probability (|r - alpha| < 1e-5).  Those rows are identified with
+    # the oracle (replaying the recorded noise, per-step alpha in its trace); every other row must match to rounding.
+    marginal = np.zeros(len(g["x"]), bool)
+    if kind.endswith("flow"):
+        trace = []
+        steps = [O.Noise(None if g[f"{key}_g"].ndim < 2 else g[f"{key}_g"][i], g[f"{key}_z"][i], g[f"{key}_r"][i])
+                 for i in range(len(g[f"{key}_r"]))]
+        ref_flow = F.make_flow(d, preset)
+        with torch.no_grad():
+            for p_, v in zip(ref_flow.parameters(), flow_param_list(g, "")):
+                p_.copy_(torch.from_numpy(v))
+        sp = O.ScalerParams(low=g["low"], high=g["high"], mu=g["mu"], sigma=g["sigma"])
+        O.mcmc_kernel(kind, state, lambda x: loglike(x)[0], logprior, sp,
+                      dict(t_mean=geo.t_mean, t_cov=geo.t_cov, t_nu=geo.t_nu, normal_cov=geo.normal_cov), od,
+                      flow=F.NumpyFlow(ref_flow), noise=O.ReplayNoise(steps), trace=trace)
+        for i, tr in enumerate(trace):
+            marginal |= np.abs(g[f"{key}_r"][i] - tr["alpha"]) < (1e-4 if tag == "nsf" else 1e-5)
+    bad = np.zeros(len(g["x"]), bool)
     for k in ("u", "x"):
         diff = np.abs(res[k] - g[f"{key}_out_{k}"]).max(axis=1)
-        bad = max(bad, int((diff > tol["atol"] + tol["rtol"] * np.abs(g[f"{key}_out_{k}"]).max(axis=1)).sum()))
-    assert bad <= max(1, len(g["x"]) // 100), f"{bad} rows diverged"
-    if bad == 0:
+        bad |= diff > tol["atol"] + tol["rtol"] * np.abs(g[f"{key}_out_{k}"]).max(axis=1)
+    assert not np.any(bad & ~marginal), f"{int(np.sum(bad & ~marginal))} rows diverged without a marginal accept decision"
+    if not bad.any():
         for k in ("logdetj", "logl", "logp"):
             np.testing.assert_allclose(res[k], g[f"{key}_out_{k}"], **tol)
         assert res["calls"] == int(g[f"{key}_out_calls"])
         for k in ("efficiency", "accept", "proposal_scale"):
             np.testing.assert_allclose(res[k], g[f"{key}_out_{k}"], rtol=1e-6 if kind.endswith("flow") else 1e-11)
+    else:       # a marginal flip changes the accepted set, not the acceptance probabilities of this call's last step much
+        print(f"{key}/{tag}: {int(bad.sum())} marginal row(s) flipped")
 
 
 def test_single_step_operators_vs_oracle(golden):

@@ -83,6 +83,12 @@ def _run_cases():
         return json.load(f)
 
 
+# runs of tests/golden/runs.json that reproduce the reference trajectory exactly (no flow, or maf3 flows whose fp32
+# differences never flipped an accept); run 4 (nsf3) leaves it after a marginal accept decision and keeps
+# the statistical bar only
+TRACKING_RUNS = (0, 1, 2, 3, 5)
+
+
 @pytest.mark.parametrize("k", range(6))
 def test_whole_run_tracks_reference(k):
     """Whole Sampler.run() against the UNMODIFIED reference run with the same random_state
@@ -108,6 +114,12 @@ def test_whole_run_tracks_reference(k):
     print(f"run {k}: logz {logz:.6f} ref {run['logz']:.6f} iterations {s.t}/{run['iterations']} same_path={same_path}")
     assert abs(logz - run["logz"]) < 0.5, (run["kwargs"], logz, run["logz"])
     assert abs(s.t - run["iterations"]) <= 3
+    if k in TRACKING_RUNS:
+        # seed parity (north_star: logZ within 1e-5 relative for the same seed): these runs stay on the reference's
+        # trajectory -- same temperature ladder, same number of MCMC steps per level, same evidence
+        assert same_path, (k, beta.tolist(), run["beta"])
+        assert list(np.asarray(s.results["steps"]).astype(int)) == run["steps"]
+        assert abs(logz - run["logz"]) <= 1e-5 * abs(run["logz"]), (logz, run["logz"])
 
 
 def test_save_and_resume(tmp_path):
