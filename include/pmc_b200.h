@@ -64,6 +64,18 @@ int pmc_flow_forward_tc(const float* packed, const int32_t* meta_host, int32_t m
                         const float* in, float* out, float* ladj, int64_t n, int32_t passes,
                         pmc_stream_t stream);
 
+/* ---- tensor-core (tcgen05) block-triangular sweep: Flow.inverse (flow.py:116-132 -> zuko
+ * transform.inv.call_and_ladj, the hot call of pocomc/mcmc.py:88,256) and Flow.forward of affine flows.
+ * Order positions are processed in blocks of 4: the dense dependence on all earlier blocks runs as
+ * tcgen05.mma updates of per-unit accumulators in tensor memory (3xTF32 split, passes = 3; plain TF32,
+ * passes = 1), the dependence inside a block as fp32 FMAs.  `packed` is the image described by
+ * pocomc_b200.made_layout.build_tri, produced by pmc_flow_tc_pack; `meta_host` is the table in HOST
+ * memory (launch geometry, validation), `meta_dev` the same table in device memory (read by the kernel).
+ * in/out [N, D] f32 (may alias), ladj [N] f32.                                                     */
+int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host, const int32_t* meta_dev,
+                       int32_t meta_len, const float* in, float* out, float* ladj, int64_t n,
+                       int32_t inverse, int32_t passes, pmc_stream_t stream);
+
 /* ---- Flow.fit optimiser step (flow.py:268,314-319) -------------------------------------------
  * torch.nn.utils.clip_grad_norm_(max_norm = hyper[5]; <= 0 disables) followed by
  * torch.optim.AdamW.step (amsgrad off) over the flat parameter blob, two launches.  `hyper` is a

@@ -17,6 +17,10 @@ device_prior
     True (default): when the prior handed to the MCMC kernels is ``pocomc_b200.Prior.logpdf`` of
     frozen scipy ``norm`` / ``uniform`` factors, log-prior values are computed on the GPU
     (identical formula, f64); any other prior object is called on the host like the reference does.
+inverse_path
+    ``"tri"`` (default): ``Flow.inverse`` (and the flow pull-back of every MCMC step) of affine flows whose
+    accumulators fit tensor memory (``made_layout.tri_supported``: D = 10..32 at the preset widths) runs on the tcgen05
+    block-triangular sweep (csrc/flow_tri.cu, 3xTF32 split = fp32 fidelity); ``"sweep"``: always the fp32-FMA sweep.
 forward_path
     ``"tc"`` (default): ``Flow.forward`` / ``log_prob`` without a graph run on the tcgen05 dense kernel
     (csrc/flow_tc.cu, 3xTF32 split = fp32 fidelity) when the flow is affine with H <= 128 and the batch
@@ -38,6 +42,8 @@ mean_mode = None  # None -> 1 for "host", 0 for "device"
 fit_kernels = os.environ.get("PMC_B200_FIT_KERNELS", "fused")
 fit_path = os.environ.get("PMC_B200_FIT", "graph")
 forward_path = os.environ.get("PMC_B200_FORWARD", "tc")
+inverse_path = os.environ.get("PMC_B200_INVERSE", "tri")
+tri_passes = int(os.environ.get("PMC_B200_TRI_PASSES", "3"))
 tc_min_rows = int(os.environ.get("PMC_B200_TC_MIN_ROWS", "1"))
 device_prior = os.environ.get("PMC_B200_DEVICE_PRIOR", "1") == "1"
 device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"

@@ -39,6 +39,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "TC_WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// busy-poll variant (mbarrier.test_wait never suspends the thread): for waits on the critical path of a latency chain
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_SPIN_LOOP:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_SPIN_DONE;\n"
+      "bra TC_SPIN_LOOP;\n"
+      "TC_SPIN_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 // 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -126,18 +126,29 @@ class MaskedAutoregressiveFlow(nn.Module):
             self._tc_meta_host = np.ascontiguousarray(self._tc.meta)
         self._tc_packed = None
         self._tc_key = None
+        # tensor-core block-triangular sweep (csrc/flow_tri.cu): the inverse direction of affine flows
+        self._tri = None
+        if ML.tri_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind):
+            self._tri = ML.build_tri(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+            self.register_buffer("tri_gather", torch.from_numpy(self._tri.gather.copy()), persistent=False)
+            self.register_buffer("tri_meta", torch.from_numpy(self._tri.meta.copy()), persistent=False)
+            self._tri_meta_host = np.ascontiguousarray(self._tri.meta)
+        self._tri_packed = None
+        self._tri_key = None
 
     # -- plumbing ---------------------------------------------------------------------------
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"], st["_packed_key"], st["_masks"] = None, None, None
         st["_tc_packed"], st["_tc_key"] = None, None
+        st["_tri_packed"], st["_tri_key"] = None, None
         st.pop("_fit_engine", None)
         return st
 
     def _apply(self, fn, *a, **k):
         self._packed, self._packed_key, self._masks = None, None, None
         self._tc_packed, self._tc_key = None, None
+        self._tri_packed, self._tri_key = None, None
         self.__dict__.pop("_fit_engine", None)
         return super()._apply(fn, *a, **k)
 
@@ -197,6 +208,41 @@ class MaskedAutoregressiveFlow(nn.Module):
         _lib.call("pmc_flow_forward_tc", _lib.ptr(packed), self._tc_meta_host.ctypes.data_as(_lib.C.c_void_p),
                   int(self._tc_meta_host.size), _lib.ptr(src), _lib.ptr(out), _lib.ptr(ladj), src.shape[0], int(passes))
 
+    # -- inference: tensor-core block-triangular sweep ---------------------------------------
+    def tri_available(self) -> bool:
+        return self.__dict__.get("_tri") is not None
+
+    def _use_tri(self, inverse: bool) -> bool:
+        return inverse and self.tri_available() and config.inverse_path == "tri"
+
+    def packed_tri(self) -> torch.Tensor:
+        """update slabs (TF32 hi/lo) + in-block fp32 slabs for csrc/flow_tri.cu; rebuilt when raw changes."""
+        self.ensure_cuda()
+        key = (self.raw.data_ptr(), self.raw._version)
+        if self._tri_packed is None or self._tri_key != key:
+            if self._tri_packed is None or self._tri_packed.device != self.raw.device:
+                self._tri_packed = torch.empty(self._tri.numel, dtype=torch.float32, device=self.raw.device)
+            _lib.call("pmc_flow_tc_pack", _lib.ptr(self.raw.detach()), _lib.ptr(self.tri_gather), _lib.ptr(self._tri_packed),
+                      self._tri.numel)
+            self._tri_key = key
+        return self._tri_packed
+
+    def _tri_args(self, src, out, ladj, inverse, passes=None):
+        packed = self.packed_tri()
+        if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
+            raise ValueError("the tensor-core sweep needs a contiguous CUDA float32 input")
+        return (_lib.ptr(packed), self._tri_meta_host.ctypes.data_as(_lib.C.c_void_p), _lib.ptr(self.tri_meta),
+                int(self._tri_meta_host.size), _lib.ptr(src), _lib.ptr(out), _lib.ptr(ladj), src.shape[0], 1 if inverse else 0,
+                int(config.tri_passes if passes is None else passes)), packed
+
+    @torch.no_grad()
+    def sweep_tri_into(self, src: torch.Tensor, out: torch.Tensor, ladj: torch.Tensor, inverse: bool, passes=None):
+        """latent -> data (or data -> latent) on tcgen05: CUDA f32 src/out [N, D], ladj [N]."""
+        if not self.tri_available():
+            raise ValueError("this flow has no tensor-core block-triangular sweep (made_layout.tri_supported)")
+        args, _ = self._tri_args(src, out, ladj, inverse, passes)
+        _lib.call("pmc_flow_sweep_tri", *args)
+
     # -- inference: sweep kernels -----------------------------------------------------------
     @torch.no_grad()
     def sweep(self, v: torch.Tensor, inverse: bool) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -208,6 +254,12 @@ class MaskedAutoregressiveFlow(nn.Module):
             out = torch.empty_like(src)
             ladj = torch.empty(src.shape[0], dtype=torch.float32, device=src.device)
             self.forward_tc_into(src, out, ladj)
+            return out.to(v.device), ladj.to(v.device)
+        if self._use_tri(inverse):
+            src = v.detach().to(self.raw.device, torch.float32).contiguous()
+            out = torch.empty_like(src)
+            ladj = torch.empty(src.shape[0], dtype=torch.float32, device=src.device)
+            self.sweep_tri_into(src, out, ladj, inverse)
             return out.to(v.device), ladj.to(v.device)
         packed = self.packed()
         src = v.detach().to(self.raw.device, torch.float32).contiguous()
@@ -221,6 +273,8 @@ class MaskedAutoregressiveFlow(nn.Module):
     @torch.no_grad()
     def sweep_into(self, src: torch.Tensor, out: torch.Tensor, ladj: torch.Tensor, inverse: bool):
         """Allocation-free variant for the MCMC loop: CUDA f32 src/out [N, D], ladj [N]."""
+        if self._use_tri(inverse):
+            return self.sweep_tri_into(src, out, ladj, inverse)
         packed = self.packed()
         if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
             raise ValueError("sweep_into needs a contiguous CUDA float32 input")
@@ -231,6 +285,11 @@ class MaskedAutoregressiveFlow(nn.Module):
     def bind_sweep(self, src: torch.Tensor, out: torch.Tensor, ladj: torch.Tensor, inverse: bool):
         """Pre-bound ``sweep_into`` for fixed buffers and fixed weights (the MCMC loop calls the flow with the same
         tensors every step); the returned callable keeps the packed weight image alive."""
+        if self._use_tri(inverse):
+            args, packed = self._tri_args(src, out, ladj, inverse)
+            run = _lib.bind("pmc_flow_sweep_tri", *args)
+            run.keep = (packed, self._tri_meta_host, self.tri_meta, src, out, ladj)
+            return run
         packed = self.packed()
         if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
             raise ValueError("bind_sweep needs a contiguous CUDA float32 input")
@@ -242,7 +301,7 @@ class MaskedAutoregressiveFlow(nn.Module):
 
     def mark_dirty(self):
         """``raw`` was updated in place by a kernel torch does not see (csrc/train_ops.cu): drop the packed copies."""
-        self._packed_key, self._tc_key = None, None
+        self._packed_key, self._tc_key, self._tri_key = None, None, None
 
     # -- training: autograd graph over the same parameters -----------------------------------
     def _flat_mask(self):

@@ -174,3 +174,135 @@ def sweep_stream(layout, stream, packed, x, inverse):
                     act[l_][:, gs:ge] = np.maximum(pre, 0)
             assert pos == cnt
     return cur, ladj
+
+
+# ---------------------------------------------------------------------------------------------
+# block-triangular sweep (csrc/flow_tri.cu): numpy emulation walking the SAME packed image and tables
+# ---------------------------------------------------------------------------------------------
+def pack_tri(tri, raw):
+    """pmc_flow_tc_pack on the host: >= 0 hi(raw[g]) (TF32 truncation); -(g+2) lo; g | 2^30 plain; -1 zero."""
+    g = tri.gather.astype(np.int64)
+    raw = np.asarray(raw, np.float32)
+    out = np.zeros(len(g), np.float32)
+    plain = (g >= 0) & ((g & (1 << 30)) != 0)
+    hi = (g >= 0) & ~plain
+    lo = g <= -2
+    out[plain] = raw[g[plain] & ~(1 << 30)]
+    trunc = lambda v: (v.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+    out[hi] = trunc(raw[g[hi]].copy())
+    v = raw[-g[lo] - 2].copy()
+    out[lo] = v - trunc(v.copy())
+    return out
+
+
+def sweep_tri(tri, packed, x, inverse, passes=3):
+    from pocomc_b200 import made_layout as ML
+    m = tri.meta
+    D, H, L, T, NB, Hc, col_out, ncols = (int(m[i]) for i in (ML.TRI_D, ML.TRI_H, ML.TRI_L, ML.TRI_T, ML.TRI_NB, ML.TRI_HC,
+                                                               ML.TRI_COL_OUT, ML.TRI_NCOLS))
+    G = ML.TRI_G
+    blocks = m[m[ML.TRI_OFF_BLOCKS]:m[ML.TRI_OFF_BLOCKS] + NB * ML.TRI_BLOCK_FIELDS].reshape(NB, -1)
+    nch = int(m[ML.TRI_NCHUNKS])
+    chunks = m[m[ML.TRI_OFF_CHUNKS]:m[ML.TRI_OFF_CHUNKS] + nch * ML.TRI_CHUNK_FIELDS].reshape(nch, -1)
+    f32 = np.float32
+    trunc = lambda v: (np.ascontiguousarray(v, f32).view(np.uint32) & np.uint32(0xffffe000)).view(f32)
+    v = np.array(x, f32, copy=True)
+    n = len(v)
+    ladj = np.zeros(n, f32)
+    log_slope = f32(np.log(1e-3))
+    for t in (range(T - 1, -1, -1) if inverse else range(T)):
+        P = packed[t * tri.tstride:(t + 1) * tri.tstride]
+        iperm = np.arange(D) if t % 2 == 0 else D - 1 - np.arange(D)
+        acc = np.full((n, ncols), np.nan, f32)                     # tensor memory: unwritten columns must never be read
+        for bi in range(NB):
+            k0, nst, U, W, hc, doff, dn, c0, n_urgent, n_chunks = (int(q) for q in blocks[bi])
+            E = max(U - 4, 0)
+            row = 4 + (4 if E else 0)
+            a = [None] + [np.zeros((n, W), f32) for _ in range(L)]
+            o = np.zeros((n, 2 * G), f32)
+            if bi > 0:
+                for l in range(1, L + 1):
+                    a[l] = acc[:, (l - 1) * Hc + hc:(l - 1) * Hc + hc + W].copy()
+                o = acc[:, col_out + 2 * k0:col_out + 2 * k0 + 2 * G].copy()
+                assert np.isfinite(o[:, :2 * nst]).all() and all(np.isfinite(a[l]).all() for l in range(1, L + 1))
+                o = np.nan_to_num(o)
+            xb = np.zeros((n, G), f32)
+            NR = 4 + E
+            nrv = 1 if NR == 4 else 2
+            q1 = (2 * NR + 3) // 4
+            p = doff
+
+            def take(nf4):
+                nonlocal p
+                out_ = P[p:p + 4 * nf4]
+                p += 4 * nf4
+                return out_
+
+            for j in range(G):
+                bo = take(1)
+                shift = o[:, 2 * j] + bo[0]
+                sraw = o[:, 2 * j + 1] + bo[1]
+                for c in range(j):
+                    for pp in range(2):
+                        w4 = take(1)
+                        s0, s1 = 4 * c + 2 * pp, 4 * c + 2 * pp + 1
+                        shift = shift + w4[0] * a[L][:, s0] + w4[1] * a[L][:, s1]
+                        sraw = sraw + w4[2] * a[L][:, s0] + w4[3] * a[L][:, s1]
+                    if E:
+                        w4 = take(1)
+                        shift = shift + w4[0] * a[L][:, 4 * G + c]
+                        sraw = sraw + w4[1] * a[L][:, 4 * G + c]
+                if j < nst:
+                    feat = iperm[k0 + j]
+                    ls = sraw / (f32(1) + np.abs(sraw / log_slope))
+                    if inverse:
+                        xk = (v[:, feat] - shift) * np.exp(-ls)
+                        ladj -= ls
+                        v[:, feat] = xk
+                    else:
+                        xk = v[:, feat].copy()
+                        v[:, feat] = xk * np.exp(ls) + shift
+                        ladj += ls
+                    xb[:, j] = xk
+                own = [ML.tri_slot(j, s_, G, E) for s_ in range(NR)]
+                # layer 1
+                pre = a[1][:, own] + take(nrv)[None, :NR]
+                for q in range(j // 2 + 1):
+                    blk = take(q1)[:2 * NR].reshape(NR, 2)
+                    pre = pre + xb[:, 2 * q][:, None] * blk[None, :, 0] + xb[:, 2 * q + 1][:, None] * blk[None, :, 1]
+                a[1][:, own] = np.maximum(pre, 0)
+                for l in range(2, L + 1):
+                    pre = a[l][:, own] + take(nrv)[None, :NR]
+                    for c in range(j + 1):
+                        blk = take(NR).reshape(2, NR, 2)
+                        for pp in range(2):
+                            for h in range(2):
+                                pre = pre + a[l - 1][:, 4 * c + 2 * pp + h][:, None] * blk[None, pp, :, h]
+                        if E:
+                            blk = take(2)[:NR]
+                            pre = pre + a[l - 1][:, 4 * G + c][:, None] * blk[None, :]
+                    a[l][:, own] = np.maximum(pre + a[l - 1][:, own], 0)
+            take(NR + 2)
+            assert p == doff + dn
+            for ci in range(c0, c0 + n_chunks):
+                a_src, ks0, nks, N, dcol, first, off, flags = (int(q) for q in chunks[ci])
+                if a_src == 0:
+                    A = np.zeros((n, 8), f32); A[:, :G] = xb
+                else:
+                    Ap = np.zeros((n, (W + 7) // 8 * 8), f32); Ap[:, :W] = a[a_src]
+                    A = Ap[:, 8 * ks0:8 * (ks0 + nks)]
+                img = P[off:off + nks * 2 * N * 4].reshape(nks * 2, N, 4)
+                Bh = img.transpose(1, 0, 2).reshape(N, nks * 8)
+                img = P[off + nks * 2 * N * 4:off + 2 * nks * 2 * N * 4].reshape(nks * 2, N, 4)
+                Bl = img.transpose(1, 0, 2).reshape(N, nks * 8)
+                Ah = trunc(A)
+                Al = A - Ah
+                Dm = Ah.astype(np.float64) @ Bh.T.astype(np.float64)
+                if passes > 1:
+                    Dm += Al.astype(np.float64) @ Bh.T.astype(np.float64) + Ah.astype(np.float64) @ Bl.T.astype(np.float64)
+                Dm = Dm.astype(f32)
+                if first:
+                    acc[:, dcol:dcol + N] = Dm
+                else:
+                    acc[:, dcol:dcol + N] += Dm
+    return v, ladj

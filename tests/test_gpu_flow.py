@@ -269,3 +269,47 @@ def test_config_shapes_vs_oracle(preset, d, n_fwd, n_inv):
     np.testing.assert_allclose(l.numpy(), l_ref.numpy(), rtol=5e-5, atol=5e-5 * max(1.0, float(l_ref.abs().max())))
     np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), rtol=5e-5, atol=5e-5 * max(1.0, float(xi_ref.abs().max())))
     np.testing.assert_allclose(li.numpy(), li_ref.numpy(), rtol=5e-5, atol=5e-5 * max(1.0, float(li_ref.abs().max())))
+
+
+@pytest.mark.parametrize("preset,d,n", [("maf6", 32, 1000), ("maf3", 10, 77), ("maf3", 21, 300), ("maf3", 16, 129),
+                                        ("maf6", 33, 515), ("maf6", 32, 20011), ("maf12", 14, 64), ("maf3", 9, 200), ("maf3", 17, 130), ("maf3", 36, 257), ("maf3", 8, 100)])
+def test_tensor_core_block_triangular_sweep_matches_oracle(preset, d, n):
+    """csrc/flow_tri.cu (tcgen05 right-looking block updates + in-block fp32 substitution), BOTH directions, against the
+    oracle's 1-pass forward / D+1-pass inverse: ragged last tile, several tiles per CTA, every block shape (U = 4, 5, 6);
+    fp32 bar 5e-5.  It is the default path of Flow.inverse for these shapes."""
+    from pocomc_b200 import config, made_layout as ML
+    assert ML.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE)
+    torch.manual_seed(d * 5 + n)
+    ref = F.make_flow(d, preset)
+    with torch.no_grad():
+        for p_ in ref.parameters():
+            p_.mul_(1.0 if preset == "maf12" else 1.25)        # 12 SCALED transforms are a chaotic map: rounding noise explodes
+    f = _mine(preset, d, [p_.detach().numpy() for p_ in ref.parameters()])
+    assert f.flow.tri_available() and config.inverse_path == "tri"
+    x = torch.randn(n, d)
+    m_ = min(n, 2000)                                           # the oracle's inverse is D+1 passes: bound its batch
+    with torch.no_grad():
+        z_ref, l_ref = ref().transform.call_and_ladj(x)
+        xi_ref, li_ref = ref().transform.inv.call_and_ladj(z_ref[:m_])
+    dev = f.flow.raw.device
+    out = torch.empty(n, d, device=dev); ladj = torch.empty(n, device=dev)
+    f.flow.sweep_tri_into(x.to(dev), out, ladj, inverse=False)
+    # 12 scaled transforms amplify fp32 rounding with the magnitude of the values: the absolute bar scales with it
+    tol = dict(rtol=5e-5, atol=5e-5 * max(1.0, float(z_ref.abs().max()), float(xi_ref.abs().max())))
+    np.testing.assert_allclose(out.cpu().numpy(), z_ref.numpy(), **tol)
+    np.testing.assert_allclose(ladj.cpu().numpy(), l_ref.numpy(), **tol)
+    xi, li = f.inverse(z_ref)                                    # the public call takes the tensor-core path
+    np.testing.assert_allclose(xi.numpy()[:m_], xi_ref.numpy(), **tol)
+    np.testing.assert_allclose(li.numpy()[:m_], li_ref.numpy(), **tol)
+    # in-place call (in == out) and agreement with the fp32-FMA sweep on every row
+    buf = z_ref.to(dev).clone()
+    f.flow.sweep_tri_into(buf, buf, ladj, inverse=True)
+    np.testing.assert_array_equal(buf.cpu().numpy(), xi.numpy())
+    old = config.inverse_path
+    config.inverse_path = "sweep"
+    try:
+        xs, ls = f.inverse(z_ref)
+    finally:
+        config.inverse_path = old
+    np.testing.assert_allclose(xi.numpy(), xs.numpy(), **tol)
+    np.testing.assert_allclose(li.numpy(), ls.numpy(), **tol)

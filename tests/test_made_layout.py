@@ -66,3 +66,41 @@ def test_masks_match_oracle():
 def test_one_dim_rejected():
     with pytest.raises(ValueError):
         ML.build_layout(1, 32, 3, 3, ML.KIND_AFFINE)
+
+
+@pytest.mark.parametrize("preset,d", [("maf3", 10), ("maf6", 32), ("maf3", 21), ("maf3", 16), ("maf3", 33), ("maf3", 36), ("maf3", 8)])
+def test_block_triangular_layout_matches_oracle(preset, d):
+    """made_layout.build_tri (image + tables of csrc/flow_tri.cu) walked by a numpy emulation of the kernel's schedule
+    -- right-looking block updates with hi/lo TF32 operands, in-block fp32 substitution -- reproduces the oracle's
+    1-pass forward and (D+1)-pass inverse."""
+    from sweep_emul import pack_tri, sweep_tri
+    torch.manual_seed(d)
+    flow = F.make_flow(d, preset)
+    with torch.no_grad():
+        for p_ in flow.parameters():
+            p_.mul_(1.3)
+    raw = _raw(flow)
+    T = int(preset[3:])
+    assert ML.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE)
+    tri = ML.build_tri(d, F.hidden_width(d), 3, T, ML.KIND_AFFINE)
+    assert tri.smem_bytes <= ML.TRI_SMEM_BUDGET and tri.meta[ML.TRI_NCOLS] <= 512
+    packed = pack_tri(tri, raw)
+    x = torch.randn(37, d)
+    with torch.no_grad():
+        z, l = flow().transform.call_and_ladj(x)
+        xi, li = flow().transform.inv.call_and_ladj(z)
+    zs, ls = sweep_tri(tri, packed, x.numpy(), inverse=False)
+    np.testing.assert_allclose(zs, z.numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(ls, l.numpy(), rtol=2e-5, atol=2e-5)
+    xs, lis = sweep_tri(tri, packed, z.numpy(), inverse=True)
+    np.testing.assert_allclose(xs, xi.numpy(), rtol=5e-5, atol=5e-5)
+    np.testing.assert_allclose(lis, li.numpy(), rtol=5e-5, atol=5e-5)
+    # plain TF32 (passes = 1) is visibly worse: the 3-pass split is what buys fp32 fidelity
+    z1, _ = sweep_tri(tri, packed, x.numpy(), inverse=False, passes=1)
+    assert np.abs(z1 - z.numpy()).max() > 10 * np.abs(zs - z.numpy()).max()
+
+
+def test_block_triangular_support_matrix():
+    sup = {d: ML.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE) for d in (2, 6, 10, 21, 32, 50, 100)}
+    assert sup[10] and sup[21] and sup[32] and not sup[2] and not sup[50] and not sup[100]
+    assert not ML.tri_supported(10, 32, 3, ML.KIND_RQS)
