@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- particle-steps/s of pocoMC's flow-preconditioned MCMC hot path (BASELINE.json).
 
-Workload (configs[1]): 32-D correlated Gaussian likelihood
-(C = 0.95 11^T + 0.05 I), prior N(0, 3^2)^32, n_active = 10 000 particles per GPU, flow 'maf6'
-(H = 128) trained for 200 optimiser steps, Student-t geometry fitted on the latent cloud, beta = 1.
-One bench "step" = one `_mutate`-sized call of the t-preconditioned Crank-Nicolson kernel
-(pocomc/mcmc.py:8-183): MCMC_STEPS Metropolis steps over every particle with the plateau rule
-disabled.  particle-steps/s = particles x MCMC steps / time.
+One bench "step" = one `_mutate`-sized call of the t-preconditioned Crank-Nicolson kernel (pocomc/mcmc.py:8-183):
+MCMC_STEPS Metropolis steps over every particle with the plateau rule disabled; particle-steps/s = particles x MCMC
+steps / time.  `--config` selects the workload (default 1 = the configuration BASELINE's metric is quoted on):
 
-  value : device-resident arm -- state in HBM, Philox noise and the synthetic prior/likelihood
-          evaluated on the GPU, no host traffic inside the timed region.
-  e2e   : the reference-facing call `pocomc_b200.mcmc.preconditioned_pcn(state_dict, function_dict,
-          option_dict)` with HOST numpy buffers, the likelihood and the scipy prior as host black
-          boxes (x' D2H and logl'/logp' H2D every MCMC step), state H2D and result D2H per call.
-  aux   : untimed-region extras on rank 0 at N=1 -- the tcgen05 dense flow forward (issued TFLOP/s against the
-          measured tensor peak), one Flow.fit optimiser step on the fused training kernels, and a FULL
-          Sampler.run() of BASELINE configs[0] (10-D Rosenbrock, 1000 particles) whose logZ is compared with
-          the unmodified reference's (tests/golden/rosen10.json) -- the "logZ abs-err vs ref" half of the metric.
-  --impl reference : the reference's own CPU path for the same call.  pocoMC is pure Python and
-          needs the third-party zuko (absent here and on the GPU box), so the arm runs the in-repo
-          CPU oracle port (oracle/smc_ref.py + oracle/zuko) on all host threads.
+  0  10-D Rosenbrock,            U(-10,10)^10,  1 000 particles            (README example; the reference's CPU case)
+  1  32-D correlated Gaussian,   N(0,3^2)^32,  10 000 particles            (headline; flow-preconditioned MCMC only)
+  2  50-D bimodal mixture,       U(-10,10)^50, 50 000 particles
+  3  100-D Rosenbrock,           U(-10,10)^100, 200 000 particles over 4 GPUs = 50 000 per GPU
+  4  200-D Neal funnel,          U(-30,30)^200, 1 000 000 particles over 8 GPUs = 125 000 per GPU
+  5  32-D Rosenbrock,            U(-10,10)^32, 10 000 particles            (north_star's literal target line: probit scaler path)
+
+all with flow 'maf6' trained for 200 optimiser steps on the initial cloud, Student-t geometry fitted on the latent
+cloud, beta = 1.  At N GPUs every rank holds the per-GPU particle count (weak scaling); `--scaling strong` keeps the
+TOTAL fixed at 8x the per-GPU count and gives every rank total / N.
+
+  value : device-resident arm -- state in HBM, Philox noise and the synthetic prior/likelihood evaluated on the GPU, no
+          host traffic inside the timed region.
+  e2e   : the reference-facing call `pocomc_b200.mcmc.preconditioned_pcn(state_dict, function_dict, option_dict)` with
+          HOST numpy buffers, the likelihood as a host black box (x' D2H and logl' H2D every MCMC step).
+  aux   : (config 1, N = 1) untimed-region extras: tcgen05 dense forward, a measured TF32 GEMM peak, one Flow.fit
+          optimiser step, and a FULL Sampler.run() of configs[0] against the unmodified reference's logZ.
+  --impl reference / cpu_baseline : the UNMODIFIED reference (`oracle/_ref/pocomc`, staged by oracle/make_ref.sh) --
+          its own `pocomc.mcmc.preconditioned_pcn`, `Flow`, `Reparameterize`, `Geometry` -- over `oracle/zuko` (the
+          restatement of its one missing third-party dependency), on all host threads, on a bounded sample of the same
+          workload.  Falls back to the in-repo oracle port (kind "port") only if oracle/_ref is absent.
 """
 from __future__ import annotations
 
@@ -27,6 +33,7 @@ import argparse
 import json
 import math
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -37,36 +44,61 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_PER_GPU = 10_000
-N_DIM = 32
 FLOW = "maf6"
-MCMC_STEPS = 50          # Metropolis steps per bench step (n_max of SURVEY 8d-2)
-REF_MCMC_STEPS = 1       # bounded sample for the CPU arms (one step is ~seconds on a CPU)
 TRAIN_EPOCHS = 20        # x 10 batches of 512 (train split = 5000 rows) = 200 optimiser steps
 L2_FLUSH_BYTES = 256 << 20
+
+# name, D, particles per GPU, GPUs the config is defined on, MCMC steps per bench step, CPU-sample particles
+CONFIGS = {
+    0: dict(name="10-D Rosenbrock, n_particles=1000", d=10, n=1000, gpus=1, steps=50, like="rosen", prior=("uniform", -10.0, 20.0), cpu_n=1000),
+    1: dict(name="32-D correlated Gaussian, n_particles=10000", d=32, n=10_000, gpus=1, steps=50, like="gauss", prior=("norm", 0.0, 3.0), cpu_n=10_000),
+    2: dict(name="50-D bimodal Gaussian mixture, n_particles=50000", d=50, n=50_000, gpus=1, steps=10, like="mixture", prior=("uniform", -10.0, 20.0), cpu_n=2000),
+    3: dict(name="100-D Rosenbrock, n_particles=200000 over 4 GPUs", d=100, n=50_000, gpus=4, steps=5, like="rosen", prior=("uniform", -10.0, 20.0), cpu_n=500),
+    4: dict(name="200-D funnel, n_particles=1000000 over 8 GPUs", d=200, n=125_000, gpus=8, steps=3, like="funnel", prior=("uniform", -30.0, 60.0), cpu_n=200),
+    5: dict(name="32-D Rosenbrock, U(-10,10), n_particles=10000 (north_star target line)", d=32, n=10_000, gpus=1, steps=50, like="rosen", prior=("uniform", -10.0, 20.0), cpu_n=10_000),
+}
 
 
 # ---------------------------------------------------------------------------------------------
 # workload (numpy / scipy only: shared by every arm)
 # ---------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, n, d, seed=0, row_offset=0):
-        from scipy.stats import norm
-        self.n, self.d = n, d
-        self.cov = 0.95 * np.ones((d, d)) + 0.05 * np.eye(d)
-        self.prec = np.linalg.inv(self.cov)
-        self.c0 = -0.5 * (d * math.log(2 * math.pi) + np.linalg.slogdet(self.cov)[1])
-        self.prior_sd = 3.0
-        self.dists = [norm(0.0, self.prior_sd)] * d
-        rng = np.random.default_rng(seed)
-        self.prior_samples = rng.normal(0.0, self.prior_sd, size=(2 * N_PER_GPU, d))     # scaler.fit input (same on all ranks)
-        chol = np.linalg.cholesky(self.cov)
-        rng_x = np.random.default_rng([seed, 1, row_offset])
-        self.x0 = rng_x.normal(size=(n, d)) @ chol.T
+    def __init__(self, cfg, n, seed=0, row_offset=0):
+        from scipy.stats import norm, uniform
+        from pocomc_b200 import synthetic as S
+        self.cfg, self.n, self.d = cfg, n, cfg["d"]
+        d = self.d
+        kind, a, b = cfg["prior"]
+        self.dists = [(norm if kind == "norm" else uniform)(a, b)] * d
+        self.prior_kind = 0 if kind == "norm" else 1
+        self.prior_loc, self.prior_scale = a, b
         self.bounds = np.array([dd.support() for dd in self.dists])
+        self.like = dict(gauss=lambda: S.CorrelatedGaussian(d), rosen=lambda: S.Rosenbrock(), mixture=lambda: S.GaussianMixture(),
+                         funnel=lambda: S.Funnel())[cfg["like"]]()
+        rng = np.random.default_rng(seed)
+        self.prior_samples = np.stack([dd.rvs(size=4096, random_state=rng) for dd in self.dists], axis=1)   # scaler.fit input (same on all ranks)
+        self.x0 = self.cloud(n, np.random.default_rng([seed, 1, row_offset]))
+
+    def cloud(self, n, rng):
+        """a crude posterior-like cloud to start the chains from (throughput does not depend on it being exact)"""
+        d, like = self.d, self.cfg["like"]
+        if like == "gauss":
+            return rng.normal(size=(n, d)) @ np.linalg.cholesky(self.like.cov).T
+        if like == "mixture":
+            sign = np.where(rng.random(n) < 0.5, 1.0, -1.0)[:, None]
+            return sign * self.like.p0 + self.like.p1 * rng.normal(size=(n, d))
+        if like == "rosen":
+            x = np.empty((n, d))
+            x[:, ::2] = rng.normal(0.8, 0.3, size=(n, (d + 1) // 2))
+            x[:, 1::2] = x[:, ::2][:, :d // 2] ** 2 + rng.normal(0.0, 0.15, size=(n, d // 2))
+            return np.clip(x, -9.9, 9.9)
+        x0 = rng.normal(0.0, 1.5, size=n)
+        x = rng.normal(size=(n, d)) * np.exp(0.5 * x0)[:, None]
+        x[:, 0] = x0
+        return np.clip(x, -29.0, 29.0)
 
     def loglike(self, x):
-        return -0.5 * np.einsum("ij,ij->i", x @ self.prec, x) + self.c0
+        return self.like(x)
 
     def logprior(self, x):
         out = np.zeros(len(x))
@@ -83,6 +115,7 @@ def clocks_sampler(stop_evt, out):
                               "-i", os.environ.get("LOCAL_RANK", "0")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except OSError:
         return
+
     def reader():
         for line in p.stdout:
             out.append(line.strip())
@@ -112,75 +145,145 @@ def summarise_clocks(lines):
     return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(cfg_id, cfg, n_local, n_gpus, mcmc_steps, scaling):
+    return {"workload": f"configs[{min(cfg_id, 4)}{'*' if cfg_id == 5 else ''}]: {cfg['name']}; flow-preconditioned MCMC only (tpCN, {FLOW}, beta=1)",
+            "config_id": cfg_id, "n_particles_per_gpu": n_local, "n_particles_total": n_local * n_gpus, "n_dim": cfg["d"], "flow": FLOW,
+            "mcmc_steps_per_bench_step": mcmc_steps, "kernel": "preconditioned_pcn",
+            "parallelism": (f"particle-shard x{n_gpus} ({scaling})" if n_gpus > 1 else "single GPU") +
+                           (f"; the config is defined on {cfg['gpus']} GPUs: this run holds one GPU's shard" if cfg["gpus"] > n_gpus else ""),
+            "l2": "the MCMC state of one shard is L2-resident within a bench step by design; L2 flushed (256 MiB write) between bench steps"}
+
+
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
+# reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------------
-def cpu_problem(wl, flow_params=None, threads=None):
-    """Build the CPU-side problem with the oracle (test infrastructure used as the timed CPU baseline)."""
+def reference_problem(wl, flow_params=None, threads=None, n_sub=None):
+    """The same `_mutate` call on the UNMODIFIED reference (oracle/_ref) over oracle/zuko; returns (run(steps) -> seconds, kind)."""
     import torch
+    ref = os.path.join(ROOT, "oracle", "_ref")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import flow_ref as F
-    import smc_ref as O
     if threads:
         torch.set_num_threads(threads)
+    n = wl.n if n_sub is None else min(n_sub, wl.n)
+    x0 = wl.x0[:n]
+    if not os.path.isdir(os.path.join(ref, "pocomc")):
+        return _port_problem(wl, x0, flow_params), "port"
+    sys.path.insert(0, ref)
+    import pocomc as rpc                                     # the reference, not this repo
+    from pocomc import mcmc as rmcmc
+    from pocomc.geometry import Geometry as RGeometry
+    from pocomc.scaler import Reparameterize as RReparameterize
+    from pocomc.tools import flow_numpy_wrapper as rwrap
+    assert os.path.abspath(rpc.__file__).startswith(ref), rpc.__file__
+    scaler = RReparameterize(wl.d, bounds=wl.bounds)
+    scaler.fit(wl.prior_samples)
+    u0 = scaler.forward(x0)
+    ldj0 = scaler.inverse(u0)[1]
+    torch.manual_seed(0)
+    flow = rpc.Flow(wl.d, FLOW)
+    if flow_params is not None:
+        with torch.no_grad():
+            for p_, v in zip(flow.flow.parameters(), flow_params):
+                p_.copy_(torch.as_tensor(v).reshape(p_.shape))
+    else:
+        flow.fit(torch.tensor(u0, dtype=torch.float32), validation_split=0.5, epochs=TRAIN_EPOCHS, batch_size=512, patience=10 ** 6,
+                 annealing=False)
+    theta0 = rwrap(flow).forward(u0)[0]
+    geo = RGeometry()
+    geo.fit(theta0.astype(np.float64))
+    state = dict(u=u0, x=x0, logdetj=ldj0, logl=wl.loglike(x0), logp=wl.logprior(x0), beta=1.0, blobs=None)
+    fd = dict(loglike=lambda x: (wl.loglike(x), None), logprior=wl.logprior, scaler=scaler, flow=flow, theta_geometry=geo, u_geometry=geo)
+
+    def run(mcmc_steps):
+        od = dict(n_max=mcmc_steps, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / wl.d ** 0.5)
+        t0 = time.perf_counter()
+        res = rmcmc.preconditioned_pcn({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in state.items()}, fd, od)
+        dt = time.perf_counter() - t0
+        assert res["steps"] == mcmc_steps
+        return dt
+    run.n = n
+    return run, "reference"
+
+
+def _port_problem(wl, x0, flow_params):
+    import torch
+    import flow_ref as F
+    import smc_ref as O
     scaler = O.scaler_fit(wl.prior_samples, wl.bounds[:, 0], wl.bounds[:, 1])
-    u0 = O.scaler_forward(wl.x0, scaler)
+    u0 = O.scaler_forward(x0, scaler)
     _, ldj0 = O.scaler_inverse(u0, scaler)
     torch.manual_seed(0)
     flow = F.make_flow(wl.d, FLOW)
     if flow_params is not None:
         F.load_params(flow, flow_params)
     else:
-        F.fit(flow, torch.tensor(u0, dtype=torch.float32), validation_split=0.5, epochs=TRAIN_EPOCHS, batch_size=512,
-              patience=10 ** 6)
+        F.fit(flow, torch.tensor(u0, dtype=torch.float32), validation_split=0.5, epochs=TRAIN_EPOCHS, batch_size=512, patience=10 ** 6)
     nf = F.NumpyFlow(flow)
     theta0, _ = nf.forward(u0)
     t_mean, t_cov, t_nu = O.fit_mvstud(theta0.astype(np.float64))
-    if not np.isfinite(t_nu):
-        t_nu = 1e6
-    geo = dict(t_mean=t_mean, t_cov=t_cov, t_nu=t_nu)
-    state = dict(u=u0, x=wl.x0, logdetj=ldj0, logl=wl.loglike(wl.x0), logp=wl.logprior(wl.x0), beta=1.0)
-    return O, nf, scaler, geo, state
+    geo = dict(t_mean=t_mean, t_cov=t_cov, t_nu=t_nu if np.isfinite(t_nu) else 1e6)
+    state = dict(u=u0, x=x0, logdetj=ldj0, logl=wl.loglike(x0), logp=wl.logprior(x0), beta=1.0)
 
-
-def cpu_steps(O, nf, scaler, geo, state, wl, mcmc_steps):
-    t0 = time.perf_counter()
-    res = O.mcmc_kernel("tpcn_flow", state, wl.loglike, wl.logprior, scaler, geo,
-                        dict(n_max=mcmc_steps, n_steps=10 ** 9, proposal_scale=2.38 / wl.d ** 0.5), flow=nf)
-    dt = time.perf_counter() - t0
-    assert res["steps"] == mcmc_steps
-    return dt
+    def run(mcmc_steps):
+        t0 = time.perf_counter()
+        res = O.mcmc_kernel("tpcn_flow", state, wl.loglike, wl.logprior, scaler, geo,
+                            dict(n_max=mcmc_steps, n_steps=10 ** 9, proposal_scale=2.38 / wl.d ** 0.5), flow=nf)
+        assert res["steps"] == mcmc_steps
+        return time.perf_counter() - t0
+    run.n = len(x0)
+    return run
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    cfg = CONFIGS[args.config]
     threads = os.cpu_count() or 1
-    wl = Workload(N_PER_GPU, N_DIM)
+    wl = Workload(cfg, cfg["cpu_n"])
     np.random.seed(0)
-    prob = cpu_problem(wl, threads=threads)
+    run, kind = reference_problem(wl, threads=threads)
     for _ in range(args.warmup):
-        cpu_steps(*prob, wl, REF_MCMC_STEPS)
-    times = [cpu_steps(*prob, wl, REF_MCMC_STEPS) for _ in range(args.steps)]
+        run(1)
+    times = [run(1) for _ in range(args.steps)]
     total = float(np.sum(times))
-    value = wl.n * REF_MCMC_STEPS * args.steps / total
-    sample = f"{REF_MCMC_STEPS} tpCN step(s) x {wl.n} particles per bench step (oracle port of mcmc.py:8-183 + zuko MAF inverse)"
+    value = run.n * args.steps / total
+    sample = (f"1 tpCN step x {run.n} particles per bench step"
+              + (f" (a {run.n}-particle sample of the {cfg['n']}-particle shard; per-particle cost is size-independent)" if run.n < cfg["n"] else "")
+              + ("; unmodified pocomc.mcmc.preconditioned_pcn + pocomc.Flow over oracle/zuko" if kind == "reference" else "; oracle port"))
     line = dict(impl="reference", metric="particle-steps/sec", value=value, unit="particle-steps/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32 flow / f64 SMC state", data="synthetic",
-                config=workload_config(1, REF_MCMC_STEPS),
-                cpu_baseline=dict(value=value, unit="particle-steps/s", cores=threads, kind="port", sample=sample),
+                scaling=args.scaling, vs_baseline=None, dtype="f32 flow / f64 SMC state", data="synthetic",
+                config=workload_config(args.config, cfg, cfg["n"], 1, 1, args.scaling),
+                cpu_baseline=dict(value=value, unit="particle-steps/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="particle-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, mcmc_steps):
-    return {"workload": f"{N_DIM}-D correlated Gaussian, n_particles={N_PER_GPU} per GPU, flow-precond MCMC only "
-                        f"(tpCN, {FLOW}, beta=1)", "n_particles_per_gpu": N_PER_GPU, "n_particles_total": N_PER_GPU * n_gpus,
-            "n_dim": N_DIM, "flow": FLOW, "mcmc_steps_per_bench_step": mcmc_steps, "kernel": "preconditioned_pcn",
-            "parallelism": f"particle-shard x{n_gpus}" if n_gpus > 1 else "single GPU",
-            "l2": "state (~10 MB) is L2-resident within a bench step by design; L2 flushed (256 MiB write) between bench steps"}
+# ---------------------------------------------------------------------------------------------
+# roofline helpers
+# ---------------------------------------------------------------------------------------------
+def committed_traffic(kernel_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full captures (profiles/roofline_traffic.json:
+    kernel-name regex -> bytes, source file).  None (and a note) when no committed capture matches the kernel that ran."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except OSError:
+        return None, "profiles/roofline_traffic.json missing"
+    for entry in table:
+        if re.search(entry["kernel"], kernel_name):
+            return float(entry["dram_bytes_per_launch"]), entry["source"]
+    return None, f"no committed ncu capture for kernel {kernel_name!r}"
+
+
+def tri_issued_flop(tri_meta, n):
+    """FLOP the tcgen05 updates of one block-triangular sweep issue: sum over chunks of 2 * 128 * N * 8 * k-steps * 3 passes,
+    per 128-particle tile and per transform (made_layout.build_tri tables)."""
+    from pocomc_b200 import made_layout as ML
+    m = tri_meta
+    nch = int(m[ML.TRI_NCHUNKS])
+    ch = m[m[ML.TRI_OFF_CHUNKS]:m[ML.TRI_OFF_CHUNKS] + nch * ML.TRI_CHUNK_FIELDS].reshape(nch, -1)
+    per_tile = float(np.sum(2.0 * 128 * ch[:, 3] * 8 * ch[:, 2] * 3))
+    return per_tile * int(m[ML.TRI_T]) * math.ceil(n / 128)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -189,9 +292,9 @@ def workload_config(n_gpus, mcmc_steps):
 def run_b200(args):
     import torch
     import pocomc_b200 as pc
-    from pocomc_b200 import config, dist, mcmc as M
+    from pocomc_b200 import _lib, config, dist, mcmc as M
     from pocomc_b200 import made_layout as ML
-    from pocomc_b200.synthetic import CorrelatedGaussian, DevicePrior
+    from pocomc_b200.synthetic import DevicePrior
 
     rank, world = dist.init_from_env()
     if not torch.cuda.is_available():
@@ -205,18 +308,24 @@ def run_b200(args):
             threadpool_limits(limits=share)
         except ImportError:
             pass
-    n_local = N_PER_GPU
+    cfg = CONFIGS[args.config]
+    D, MCMC_STEPS = cfg["d"], cfg["steps"]
+    if args.scaling == "strong":
+        total = 8 * cfg["n"]
+        n_local = (total // world + 255) // 256 * 256
+    else:
+        n_local = cfg["n"]
     n_global = n_local * world
-    wl = Workload(n_local, N_DIM, row_offset=rank * n_local)
+    wl = Workload(cfg, n_local, row_offset=rank * n_local)
 
     # ---- untimed setup: scaler, flow training, geometry (identical on every rank) ----
     np.random.seed(0)
     torch.manual_seed(0)
-    scaler = pc.scaler.Reparameterize(N_DIM, bounds=wl.bounds)
+    scaler = pc.scaler.Reparameterize(D, bounds=wl.bounds)
     scaler.fit(wl.prior_samples)
-    wl0 = Workload(N_PER_GPU, N_DIM, row_offset=0)            # rank-0 cloud trains the (replicated) flow
-    u_train = scaler.forward(wl0.x0)
-    flow = pc.Flow(N_DIM, FLOW)
+    wl0 = wl if rank == 0 and n_local >= 10_000 else Workload(cfg, min(10_000, max(n_local, 2000)), row_offset=0)   # rank-0 cloud trains the (replicated) flow
+    u_train = scaler.forward(wl0.x0[:10_000])
+    flow = pc.Flow(D, FLOW)
     flow.fit(torch.tensor(u_train, dtype=torch.float32), validation_split=0.5, epochs=TRAIN_EPOCHS, batch_size=512,
              patience=10 ** 6, annealing=False)
     theta_train = pc.tools.flow_numpy_wrapper(flow).forward(u_train)[0]
@@ -225,9 +334,8 @@ def run_b200(args):
     u0 = scaler.forward(wl.x0)
     ldj0 = scaler.inverse(u0)[1]
     state = dict(u=u0, x=wl.x0, logdetj=ldj0, logl=wl.loglike(wl.x0), logp=wl.logprior(wl.x0), beta=1.0, blobs=None)
-    like_dev = CorrelatedGaussian(N_DIM)
-    prior_dev = DevicePrior(np.zeros(N_DIM, np.int32), np.zeros(N_DIM), np.full(N_DIM, wl.prior_sd))
-    blocks = int(pc._lib.load().pmc_mh_partials_size(n_local, N_DIM)) // (N_DIM + 4)
+    prior_dev = DevicePrior(np.full(D, wl.prior_kind, np.int32), np.full(D, wl.prior_loc), np.full(D, wl.prior_scale))
+    blocks = int(_lib.load().pmc_mh_partials_size(n_local, D)) // (D + 4)
     shard = (rank * n_local, n_global, [blocks] * world) if world > 1 else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
@@ -247,8 +355,8 @@ def run_b200(args):
     config.set_rng_mode("device")
     sweep_events = []
     fd = dict(loglike=lambda x: (wl.loglike(x), None), logprior=wl.logprior, scaler=scaler, flow=flow,
-              theta_geometry=geo, u_geometry=geo, loglike_device=like_dev.device, logprior_device=prior_dev)
-    od = dict(n_max=MCMC_STEPS, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / N_DIM ** 0.5, shard=shard,
+              theta_geometry=geo, u_geometry=geo, loglike_device=wl.like.device, logprior_device=prior_dev)
+    od = dict(n_max=MCMC_STEPS, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / D ** 0.5, shard=shard,
               seed=1234, sweep_events=None)
     eng = M.McmcEngine(M.KIND_TPCN_FLOW, state, fd, od)
 
@@ -265,6 +373,7 @@ def run_b200(args):
     th = threading.Thread(target=clocks_sampler, args=(stop_evt, clock_lines), daemon=True)
     th.start()
     barrier()
+    calls0 = _lib.entry_calls()
     torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -273,9 +382,8 @@ def run_b200(args):
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
+    launches = _lib.entry_calls() - calls0          # COUNTED: every libpmc_b200 entry point invoked in the timed region launches >= 1 kernel
     t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    launches = eng.launches
-    eng.launches = 0
     sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in sweep_events]))
     eng.sweep_events = None
     accept_dev = eng.accept
@@ -284,7 +392,7 @@ def run_b200(args):
     prior = pc.Prior(wl.dists)          # what Sampler passes: prior.logpdf (device fast path for norm/uniform factors)
     fd_host = dict(loglike=lambda x: (wl.loglike(x), None), logprior=prior.logpdf, scaler=scaler, flow=flow,
                    theta_geometry=geo, u_geometry=geo)
-    od_host = dict(n_max=MCMC_STEPS, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / N_DIM ** 0.5, shard=shard, seed=1234)
+    od_host = dict(n_max=MCMC_STEPS, n_steps=10 ** 9, progress_bar=None, proposal_scale=2.38 / D ** 0.5, shard=shard, seed=1234)
 
     def e2e_step():
         flush.fill_(1)
@@ -292,77 +400,86 @@ def run_b200(args):
         assert res["steps"] == MCMC_STEPS
         return res
 
+    e2e_steps = args.steps if n_local * D <= 2_000_000 else max(1, args.steps // 2)
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         e2e_step()
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     stop_evt.set()
     th.join(timeout=3)
 
-    per_call_h2d = n_local * (2 * N_DIM + 3) * 8
-    per_call_d2h = n_local * (2 * N_DIM + 3) * 8
-    per_mcmc_d2h = n_local * (N_DIM * 8 + 1) + (M.CTL_MU + N_DIM) * 8     # x', finite mask, controller block
-    per_mcmc_h2d = n_local * 8                                             # logl' (log-prior evaluated on the GPU)
-    h2d = per_call_h2d + MCMC_STEPS * per_mcmc_h2d
-    d2h = per_call_d2h + MCMC_STEPS * per_mcmc_d2h
+    per_call = n_local * (2 * D + 3) * 8
+    per_mcmc_d2h = n_local * (D * 8 + 1) + (M.CTL_MU + D) * 8     # x', finite mask, controller block
+    per_mcmc_h2d = n_local * 8                                    # logl' (log-prior evaluated on the GPU)
+    h2d = per_call + MCMC_STEPS * per_mcmc_h2d
+    d2h = per_call + MCMC_STEPS * per_mcmc_d2h
 
-    # ---- roofline of the dominant kernel (flow inverse sweep) ------------------------------------
+    # ---- roofline of the dominant kernel (flow inverse) -------------------------------------------
     lay = flow.flow.layout
-    macs = ML.useful_macs(lay)                      # per particle, all transforms
-    flop = 2.0 * macs * n_local
+    useful = 2.0 * ML.useful_macs(lay) * n_local                  # 2 * nnz(masks) per particle: the algorithmic minimum
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-    achieved_tf = flop / (sweep_ms * 1e-3) / 1e12
+    mod = flow.flow
+    if mod.tri_available() and config.inverse_path == "tri":
+        kernel = "made_sweep_tri_kernel<true, 4> (flow inverse: tcgen05 block-triangular sweep)"
+        issued = tri_issued_flop(mod._tri_meta_host, n_local)
+        note = ("tcgen05.mma kind::tf32 right-looking updates (3xTF32 split) + in-block fp32 substitution; achieved = issued MMA FLOP per "
+                "launch (sum over update chunks of 2*128*N*8*k-steps*3 passes per 128-particle tile) / launch time; latency-bound at one "
+                "128-particle tile per SM (TMEM holds one tile's accumulators): per block of 4 order positions one mbarrier round trip "
+                "through the tensor pipe (~1 us) + ~1000 warp instructions of substitution (DESIGN.md section 4)")
+    else:
+        kernel = "made_sweep_stream_kernel<Affine> (flow inverse: fp32-FMA degree-ordered sweep)" if ML.stream_supported(D, lay.n_hidden, lay.n_layers, lay.kind) \
+            else "made_sweep_kernel<Affine> (flow inverse: fp32-FMA sweep, weights through L2)"
+        issued = useful
+        note = "fp32 FMA sweep on CUDA cores (no tensor-core path for this flow shape yet); achieved = useful FLOP (2*nnz(masks)) / launch time"
+    achieved_tf = issued / (sweep_ms * 1e-3) / 1e12
+    traffic, traffic_src = committed_traffic(kernel)
     roofline = dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
-                    traffic=2084608.0,      # bytes per launch: dram read 2.08 MB + write 0 (ncu --set full, profiles/r1c_sweep_v3_ncu.txt)
-                    kernel="made_sweep_stream_kernel<Affine> (flow inverse, degree-ordered sweep)",
+                    traffic=traffic, traffic_source=traffic_src, kernel=kernel,
                     peak_source="MEASURED_PEAKS.json bf16 burst" if peaks else "fallback 1.59 PFLOP/s",
-                    flop_per_launch=flop, avg_launch_ms=sweep_ms,
-                    note="fp32 FMA sweep on CUDA cores, bound by shared-memory wavefronts (128 FMA per 5 wavefronts caps the FMA pipe at 20 %, "
-                         "DESIGN.md section 7); 2*nnz(masks) useful FLOP per particle; share of step = "
-                         f"{sweep_ms * MCMC_STEPS * args.steps / (t_dev * 1e3):.2f}")
+                    flop_per_launch=issued, useful_flop_per_launch=useful, useful_tflops=useful / (sweep_ms * 1e-3) / 1e12,
+                    avg_launch_ms=sweep_ms, share_of_step=sweep_ms * MCMC_STEPS * args.steps / (t_dev * 1e3), note=note)
 
     value = n_global * MCMC_STEPS * args.steps / t_dev
-    e2e_value = n_global * MCMC_STEPS * args.steps / t_e2e
+    e2e_value = n_global * MCMC_STEPS * e2e_steps / t_e2e
     line = dict(metric="particle-steps/sec", value=value, unit="particle-steps/s", n_gpus=world, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True, scaling="weak",
+                warmup=args.warmup, ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True, scaling=args.scaling,
                 vs_baseline=None, dtype="f32 flow / f64 SMC state", data="synthetic",
-                config=workload_config(world, MCMC_STEPS), clocks=summarise_clocks(clock_lines),
+                config=workload_config(args.config, cfg, n_local, world, MCMC_STEPS, args.scaling), clocks=summarise_clocks(clock_lines),
                 e2e=dict(value=e2e_value, unit="particle-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=1e3 * t_e2e / args.steps, rng="device Philox", callbacks="host numpy likelihood (black box); pc.Prior of scipy norm factors evaluated on the GPU"),
+                         ms_per_step=1e3 * t_e2e / e2e_steps, steps=e2e_steps, rng="device Philox",
+                         callbacks="host numpy likelihood (black box); pc.Prior of scipy norm / uniform factors evaluated on the GPU"),
                 gpu_launches=launches, roofline=roofline, accept_rate=accept_dev)
-    line["roofline"].update(fp32_fma_peak_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
-                            frac_of_fp32_fma_peak=achieved_tf / (148 * 128 * 2 * 1.965e9 / 1e12))
-    if rank == 0 and world == 1 and not args.no_aux:
-        line["aux"] = aux_measurements(flow, peaks)
+    if rank == 0 and world == 1 and not args.no_aux and args.config == 1:
+        line["aux"] = aux_measurements(flow, peaks, D)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         params = [p.detach().cpu().numpy() for _, p in sorted(flow_param_arrays(flow))]
-        prob = cpu_problem(wl, flow_params=params, threads=threads)
-        dt = cpu_steps(*prob, wl, REF_MCMC_STEPS)
-        dt = min(dt, cpu_steps(*prob, wl, REF_MCMC_STEPS))
-        line["cpu_baseline"] = dict(value=wl.n * REF_MCMC_STEPS / dt, unit="particle-steps/s", cores=threads, kind="port",
-                                    sample=f"{REF_MCMC_STEPS} tpCN step x {wl.n} particles, same trained flow weights, best of 2 "
-                                           "(oracle port: vectorised numpy + zuko-restated MAF inverse with D+1 passes)")
+        run, kind = reference_problem(wl, flow_params=params, threads=threads, n_sub=cfg["cpu_n"])
+        dt = run(1)
+        if dt < 10.0:
+            dt = min(dt, run(1))
+        line["cpu_baseline"] = dict(value=run.n / dt, unit="particle-steps/s", cores=threads, kind=kind,
+                                    sample=f"1 tpCN step x {run.n} particles ({'the whole shard' if run.n == n_local else 'a sample of the shard'}), same trained "
+                                           f"flow weights; {'unmodified reference (oracle/_ref) over oracle/zuko' if kind == 'reference' else 'oracle port'}")
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
-
 # ---------------------------------------------------------------------------------------------
-# auxiliary measurements (rank 0, N = 1): tensor-core forward, training step, full-run logZ
+# auxiliary measurements (rank 0, N = 1, config 1): tensor-core forward, training step, full-run logZ
 # ---------------------------------------------------------------------------------------------
-def aux_measurements(flow, peaks):
+def aux_measurements(flow, peaks, n_dim):
     import torch
     import pocomc_b200 as pc
     from pocomc_b200.flow import _FitEngine
@@ -380,31 +497,51 @@ def aux_measurements(flow, peaks):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    # (1) Flow.forward on tcgen05 (csrc/flow_tc.cu): 1 M particles >> L2, 3xTF32
+    # (0) a MEASURED TF32 GEMM peak (cuBLAS, 8192^3) next to the bf16 one of MEASURED_PEAKS.json
+    try:
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ms = min(timeit(lambda: torch.matmul(a, b), 5) for _ in range(3))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        out["tf32_gemm_peak_tflops"] = 2 * 8192 ** 3 / (ms * 1e-3) / 1e12
+        del a, b
+    except Exception as e:      # diagnostics only
+        out["tf32_gemm_peak_tflops"] = repr(e)
+    tf32_peak = out["tf32_gemm_peak_tflops"] if isinstance(out["tf32_gemm_peak_tflops"], float) else None
     mod = flow.flow
+    # (1) Flow.forward on tcgen05 (csrc/flow_tc.cu): 1 M particles >> L2, 3xTF32
     if mod.tc_available():
         n = 1 << 20
-        x = torch.randn(n, N_DIM, device="cuda")
+        x = torch.randn(n, n_dim, device="cuda")
         z = torch.empty_like(x)
         l = torch.empty(n, device="cuda")
         lay = mod.layout
-        kx, nout, h = (N_DIM + 7) // 8 * 8, (2 * N_DIM + 15) // 16 * 16, lay.n_hidden
-        # issued MMA FLOP per particle: per transform 3 passes x 2 x (Kx*H + (L-1)*H*H + H*Nout) + the bias k-steps
+        kx, nout, h = (n_dim + 7) // 8 * 8, (2 * n_dim + 15) // 16 * 16, lay.n_hidden
         per_t = 2 * (kx * h + (lay.n_layers - 1) * h * h + h * nout) + 2 * 8 * (lay.n_layers * h + nout)
         ms3 = timeit(lambda: mod.forward_tc_into(x, z, l, 3), 10)
-        ms_sweep = timeit(lambda: mod.sweep_into(x[:100_000], z[:100_000], l[:100_000], False), 3) * (n / 100_000)
         issued = 3 * per_t * lay.n_transforms * n / (ms3 * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops", 1590.0))
         out["flow_forward_tcgen05"] = dict(particles=n, ms=ms3, particles_per_s=n / (ms3 * 1e-3), issued_tflops=issued,
                                            useful_tflops=issued / 3, frac_of_bf16_peak=issued / peak,
-                                           frac_of_tf32_peak=issued / (peak / 2), sweep_kernel_ms_extrapolated=ms_sweep,
-                                           note="kind::tf32 MMAs, 3-pass split for fp32 fidelity; TF32 peak taken as half the measured bf16 peak")
+                                           frac_of_measured_tf32_gemm_peak=(issued / tf32_peak) if tf32_peak else None)
+        # (1b) the block-triangular inverse at the same size (every SM holds a tile: throughput, not one-wave latency)
+        if mod.tri_available():
+            ms_inv = timeit(lambda: mod.sweep_tri_into(x, z, l, True), 5)
+            iss = tri_issued_flop(mod._tri_meta_host, n) / (ms_inv * 1e-3) / 1e12
+            out["flow_inverse_tcgen05"] = dict(particles=n, ms=ms_inv, particles_per_s=n / (ms_inv * 1e-3), issued_tflops=iss,
+                                               frac_of_bf16_peak=iss / peak, frac_of_measured_tf32_gemm_peak=(iss / tf32_peak) if tf32_peak else None)
+            pc.config.inverse_path = "sweep"
+            ms_ffma = timeit(lambda: mod.sweep_into(x[:200_000], z[:200_000], l[:200_000], True), 3) * (n / 200_000)
+            pc.config.inverse_path = "tri"
+            out["flow_inverse_tcgen05"]["ffma_sweep_ms_extrapolated"] = ms_ffma
         del x, z, l
     # (2) one optimiser step of Flow.fit (batch 512) on the fused kernels inside a CUDA graph
     try:
-        f2 = pc.Flow(N_DIM, FLOW)
+        f2 = pc.Flow(n_dim, FLOW)
         eng = _FitEngine(f2.flow)
-        xt = torch.randn(8192, N_DIM, device="cuda")
+        xt = torch.randn(8192, n_dim, device="cuda")
         wt = torch.rand(8192, device="cuda") + 0.1
         eng.load(xt, wt)
         eng.reset_optimizer(1e-3, 0.0, 1.0)
@@ -415,7 +552,7 @@ def aux_measurements(flow, peaks):
         for _ in range(5):
             eng.run_epoch(batches, 512, True)
         torch.cuda.synchronize()
-        out["fit_step"] = dict(batch=512, flow=FLOW, n_dim=N_DIM, us_per_optimizer_step=(time.perf_counter() - t0) / 80 * 1e6,
+        out["fit_step"] = dict(batch=512, flow=FLOW, n_dim=n_dim, us_per_optimizer_step=(time.perf_counter() - t0) / 80 * 1e6,
                                path="fused forward/backward + grouped weight-gradient GEMM + clip/AdamW, one CUDA graph launch"
                                if eng.fused else "autograd in a CUDA graph")
     except Exception as e:      # diagnostics only
@@ -454,7 +591,7 @@ def aux_measurements(flow, peaks):
 
 
 def flow_param_arrays(flow):
-    """(index, tensor) per module-order parameter tensor of the flat blob (for the oracle flow)."""
+    """(index, tensor) per module-order parameter tensor of the flat blob (for the reference / oracle flow)."""
     out, k = [], 0
     for t in range(flow.flow.layout.n_transforms):
         for w, b in flow.flow.transform_params(t):
@@ -468,6 +605,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE configs index (5 = the literal 10k x 32-D Rosenbrock line)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the untimed auxiliary measurements (tcgen05 forward, fit step, full run)")
     args = ap.parse_args()

@@ -213,6 +213,19 @@ int pmc_mh_accept_update(int32_t kind, double beta, double nu, float* pos32, dou
                          const double* r, const uint8_t* finite, double* alpha_out,
                          double* partials, int64_t n, int32_t d, pmc_stream_t stream);
 
+/* pmc_mh_accept_update and pmc_mcmc_finalize in ONE launch (single-GPU runs): the thread block that finishes last
+ * reduces the block partials and adapts the controller.  The launch is a no-op once ctl[PMC_CTL_STOP] is set, so
+ * the host may queue several MCMC steps before reading the controller back and still stop exactly where
+ * mcmc.py:170-180 stops.  `ticket`: one device uint32, zero before the first launch (the kernel resets it).        */
+int pmc_mh_accept_finalize(int32_t kind, double beta, double nu, float* pos32, double* u, double* x,
+                           double* logdetj, double* logl, double* logp, float* logdetj_flow,
+                           const double* prop64, const double* u_p, const double* x_p,
+                           const double* logdetj_p, const double* logl_p, const double* logp_p,
+                           const float* logdetj_flow_p, const double* m_cur, const double* m_prop,
+                           const double* r, const uint8_t* finite, double* alpha_out, double* partials,
+                           double* ctl, uint32_t* ticket, int32_t mean_mode, int32_t n_steps,
+                           int32_t n_max, int64_t n, int32_t d, pmc_stream_t stream);
+
 /* Scalar adaptation + stop rule (mcmc.py:152-180 and the three siblings), on device:
  * reduces `partials` in fixed order, updates ctl (sigma, mu, step, best, cnt, stop, accept...).
  * mean_mode 1 reproduces np.mean(theta f32, axis=0)'s sequential f32 accumulation exactly
@@ -228,6 +241,9 @@ int pmc_mcmc_finalize(int32_t kind, double* ctl, const double* partials, int64_t
  * number of GPUs.  gamma_shape <= 0 skips g.                                                   */
 int pmc_rng_fill(uint64_t seed, uint64_t step, int64_t particle_offset, double gamma_shape,
                  double* g, double* z, double* r, int64_t n, int32_t d, pmc_stream_t stream);
+/* same draws with the step counter read on the device: step = ctl[PMC_CTL_STEP] + 1 (lets the host queue steps) */
+int pmc_rng_fill_ctl(uint64_t seed, const double* ctl, int64_t particle_offset, double gamma_shape,
+                     double* g, double* z, double* r, int64_t n, int32_t d, pmc_stream_t stream);
 
 /* ---- persistent-sampling weights (pocomc/particles.py:215-231, tools.py:56-93) --------------
  * History logl [T, N] f64 and the running log-denominator den [T, N] =

@@ -41,8 +41,10 @@ SIGNATURES = {
     "pmc_apply_bc": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_mh_partials_size": (_I64, [_I64, _I32]),
     "pmc_mh_accept_update": (C.c_int, [_I32, _F64, _F64] + [_P] * 20 + [_I64, _I32, _P]),
+    "pmc_mh_accept_finalize": (C.c_int, [_I32, _F64, _F64] + [_P] * 22 + [_I32, _I32, _I32, _I64, _I32, _P]),
     "pmc_mcmc_finalize": (C.c_int, [_I32, _P, _P, _I64, _P, _I32, _I32, _I32, _I64, _I32, _P]),
     "pmc_rng_fill": (C.c_int, [_U64, _U64, _I64, _F64, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_rng_fill_ctl": (C.c_int, [_U64, _P, _I64, _F64, _P, _P, _P, _I64, _I32, _P]),
     "pmc_ps_append": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _P]),
     "pmc_ps_scratch_size": (_I64, [_I64]),
     "pmc_ps_reduce": (C.c_int, [_P, _P, _F64, _I32, _I64, _I64, _P, _P, _P]),
@@ -133,10 +135,20 @@ def check(code: int, what: str = ""):
         raise RuntimeError(f"libpmc_b200 {what} failed ({code}): {msg.decode() if msg else '?'}")
 
 
+_entry_calls = [0]
+
+
+def entry_calls() -> int:
+    """Number of libpmc_b200 compute entry points invoked so far by this process (each launches at least one kernel):
+    the counter behind bench.py's ``gpu_launches``."""
+    return _entry_calls[0]
+
+
 def call(name: str, *args):
     """Call an int-returning entry point on the current torch stream; raise on a non-zero code."""
     require_cuda()
     lib = load()
+    _entry_calls[0] += 1
     check(getattr(lib, name)(*args, stream_ptr()), name)
 
 
@@ -147,7 +159,10 @@ def bind(name: str, *args):
     fn = getattr(load(), name)
     get_stream, get_dev = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
 
+    counter = _entry_calls
+
     def run():
+        counter[0] += 1
         code = fn(*args, C.c_void_p(get_stream(get_dev())))
         if code != 0:
             check(code, name)

@@ -202,6 +202,15 @@ apply_bc_kernel(double* __restrict__ x, const int* __restrict__ bc, const double
 // ------------------------------------------------------------------------------------------
 // Metropolis accept + masked update + block partial sums
 // ------------------------------------------------------------------------------------------
+constexpr int FIN_TILE_FLOATS = 8192, FIN_TILE_COLS = 256;
+__device__ __forceinline__ void finalize_body(int kind, double* __restrict__ ctl, const double* __restrict__ partials, int n_blocks,
+                                              const float* __restrict__ pos32, int mean_mode, int n_steps, int n_max, long long n, int d,
+                                              double* tot, float* tile);
+
+// FUSED: the launch also runs the step's scalar adaptation (finalize_body) in the block that finishes last, and does
+// nothing at all once the controller's stop flag is set -- so a host that queues several steps without reading the
+// controller back cannot run past the reference's stopping point (mcmc.py:170-180).
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
 mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, double* __restrict__ u,
                  double* __restrict__ x, double* __restrict__ logdetj, double* __restrict__ logl,
@@ -211,8 +220,12 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
                  const double* __restrict__ logp_p, const float* __restrict__ ldjf_p,
                  const double* __restrict__ m_cur, const double* __restrict__ m_prop,
                  const double* __restrict__ r, const uint8_t* __restrict__ finite,
-                 double* __restrict__ alpha_out, double* __restrict__ partials, long long n, int d) {
+                 double* __restrict__ alpha_out, double* __restrict__ partials, long long n, int d,
+                 double* __restrict__ ctl, unsigned int* __restrict__ ticket, int mean_mode, int n_steps, int n_max) {
   extern __shared__ double sh[];  // [8 warps][d] theta sums + [8][4] scalars
+  __shared__ float fin_tile[FUSED ? FIN_TILE_FLOATS + FIN_TILE_COLS : 1];
+  __shared__ unsigned int is_last;
+  if (FUSED && ctl[PMC_CTL_STOP] != 0.0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* th = sh + (size_t)warp * d;
   double* sc = sh + (size_t)8 * d + warp * 4;
@@ -296,14 +309,24 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
     else if (want_theta) { for (int w = 0; w < 8; ++w) s += sh[(size_t)w * d + (j - 4)]; }
     out[j] = s;
   }
+  if (FUSED) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    finalize_body(kind, ctl, partials, (int)gridDim.x, pos32, mean_mode, n_steps, n_max, n, d, sh, fin_tile);
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
 }
 
-__global__ void __launch_bounds__(256)
-mcmc_finalize_kernel(int kind, double* __restrict__ ctl, const double* __restrict__ partials, int n_blocks,
-                     const float* __restrict__ pos32, int mean_mode, int n_steps, int n_max, long long n, int d) {
-  extern __shared__ double tot[];  // [d + 4]
-  constexpr int TILE_FLOATS = 8192, TILE_COLS = 256;
-  __shared__ float tile[TILE_FLOATS + TILE_COLS];   // [rows][cols + 1] staging of theta for the sequential mean
+// sigma / mu adaptation and the plateau rule from the block partials (mcmc.py:152-180); one 256-thread block.
+// tot: [d + 4] doubles of shared memory, tile: [FIN_TILE_FLOATS + FIN_TILE_COLS] floats of shared memory.
+__device__ __forceinline__ void finalize_body(int kind, double* __restrict__ ctl, const double* __restrict__ partials, int n_blocks,
+                                              const float* __restrict__ pos32, int mean_mode, int n_steps, int n_max, long long n, int d,
+                                              double* tot, float* tile) {
+  constexpr int TILE_FLOATS = FIN_TILE_FLOATS, TILE_COLS = FIN_TILE_COLS;
   const bool tpf = (kind == PMC_KIND_TPCN_FLOW);
   const bool seq_mean = tpf && mean_mode != 0;
   for (int j = threadIdx.x; j < d + 4; j += blockDim.x) {
@@ -385,6 +408,14 @@ mcmc_finalize_kernel(int kind, double* __restrict__ ctl, const double* __restric
   }
 }
 
+__global__ void __launch_bounds__(256)
+mcmc_finalize_kernel(int kind, double* __restrict__ ctl, const double* __restrict__ partials, int n_blocks,
+                     const float* __restrict__ pos32, int mean_mode, int n_steps, int n_max, long long n, int d) {
+  extern __shared__ double tot[];  // [d + 4]
+  __shared__ float tile[FIN_TILE_FLOATS + FIN_TILE_COLS];   // [rows][cols + 1] staging of theta for the sequential mean
+  finalize_body(kind, ctl, partials, n_blocks, pos32, mean_mode, n_steps, n_max, n, d, tot, tile);
+}
+
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG (throughput mode; parity mode uploads numpy's legacy stream instead)
 // ------------------------------------------------------------------------------------------
@@ -415,8 +446,9 @@ __device__ __forceinline__ void box_muller(uint4 c, double& n0, double& n1) {
 }
 
 __global__ void __launch_bounds__(256)
-rng_fill_kernel(uint64_t seed, uint64_t step, long long offset, double shape, double* __restrict__ g,
+rng_fill_kernel(uint64_t seed, uint64_t step, const double* __restrict__ ctl, long long offset, double shape, double* __restrict__ g,
                 double* __restrict__ z, double* __restrict__ r, long long n, int d) {
+  if (ctl) step = (uint64_t)ctl[PMC_CTL_STEP] + 1;      // the step about to run, read where the previous step left it
   const Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
   const int half = (d + 1) / 2;
   const long long total = n * (half + 1);
@@ -620,9 +652,33 @@ extern "C" int pmc_mh_accept_update(int32_t kind, double beta, double nu, float*
   PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_update: tpCN kinds need the Mahalanobis distances");
   if (n == 0) return 0;
   const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
-  mh_accept_kernel<<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
+  mh_accept_kernel<false><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
       kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
-      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d);
+      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, nullptr, nullptr, 0, 0, 0);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_mh_accept_finalize(int32_t kind, double beta, double nu, float* pos32, double* u, double* x,
+                                      double* logdetj, double* logl, double* logp, float* logdetj_flow,
+                                      const double* prop64, const double* u_p, const double* x_p,
+                                      const double* logdetj_p, const double* logl_p, const double* logp_p,
+                                      const float* logdetj_flow_p, const double* m_cur, const double* m_prop,
+                                      const double* r, const uint8_t* finite, double* alpha_out, double* partials,
+                                      double* ctl, uint32_t* ticket, int32_t mean_mode, int32_t n_steps, int32_t n_max,
+                                      int64_t n, int32_t d, pmc_stream_t stream) {
+  PMC_REQUIRE(kind >= 0 && kind <= 3, "pmc_mh_accept_finalize: bad kind");
+  PMC_REQUIRE(u && x && logdetj && logl && logp && u_p && x_p && logdetj_p && logl_p && logp_p && r && partials && ctl && ticket,
+              "pmc_mh_accept_finalize: null pointer");
+  const bool flow = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_RWM_FLOW);
+  const bool tp = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_TPCN);
+  PMC_REQUIRE(!flow || (pos32 && prop64 && logdetj_flow && logdetj_flow_p), "pmc_mh_accept_finalize: flow kinds need theta + flow log-dets");
+  PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_finalize: tpCN kinds need the Mahalanobis distances");
+  PMC_REQUIRE(n > 0, "pmc_mh_accept_finalize: empty batch");
+  const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
+  mh_accept_kernel<true><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
+      kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
+      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, ctl, ticket, mean_mode, n_steps, n_max);
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -643,7 +699,17 @@ extern "C" int pmc_rng_fill(uint64_t seed, uint64_t step, int64_t particle_offse
   PMC_REQUIRE(z && n >= 0 && d >= 1, "pmc_rng_fill: bad arguments");
   if (n == 0) return 0;
   const int blocks = grid_for(n * ((d + 1) / 2 + 1), 256, 8);
-  rng_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, step, particle_offset, gamma_shape, g, z, r, n, d);
+  rng_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, step, nullptr, particle_offset, gamma_shape, g, z, r, n, d);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_rng_fill_ctl(uint64_t seed, const double* ctl, int64_t particle_offset, double gamma_shape, double* g,
+                                double* z, double* r, int64_t n, int32_t d, pmc_stream_t stream) {
+  PMC_REQUIRE(z && ctl && n >= 0 && d >= 1, "pmc_rng_fill_ctl: bad arguments");
+  if (n == 0) return 0;
+  const int blocks = grid_for(n * ((d + 1) / 2 + 1), 256, 8);
+  rng_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, 0, ctl, particle_offset, gamma_shape, g, z, r, n, d);
   PMC_LAUNCH_CHECK();
   return 0;
 }

@@ -60,6 +60,9 @@ class McmcEngine:
                 from .synthetic import DevicePrior
                 self.logprior_device = DevicePrior(*spec)
         self.scaler = function_dict.get('scaler')
+        if not hasattr(self.scaler, '_params'):          # e.g. the reference's own Reparameterize (drop-in use from its Sampler)
+            from .scaler import Reparameterize
+            self.scaler = Reparameterize.adopt(self.scaler)
         geometry = function_dict.get('theta_geometry' if self.use_flow else 'u_geometry')
         self.with_bc = (self.scaler.periodic is not None) or (self.scaler.reflective is not None)
         # -- options (mcmc.py:51-54)
@@ -131,6 +134,7 @@ class McmcEngine:
         self.logp_p = torch.empty(n, **f64)
         self.alpha = torch.empty(n, **f64)
         self.partials = torch.empty(int(_lib.load().pmc_mh_partials_size(n, d)), **f64)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)      # last-block-done counter of the fused accept + adapt launch
         # pinned staging
         self.h_x = _lib.pinned('x', (n, d), torch.float64)
         self.h_fin = _lib.pinned('fin', n, torch.uint8)
@@ -156,6 +160,7 @@ class McmcEngine:
         self._rng_fill = self._sweep = self._logprior = None
         self._stream = torch.cuda.current_stream()     # the engine lives for one kernel call on the caller's stream; looking it up costs ~20 us per step
         self._accept = {}
+        self._accept_fused = {}
         self.sc, self._sc_keep, _ = self.scaler._params(True)
         if self.with_bc and self._sc_keep["bc"] is not None:
             self.sc.bc = _lib.ptr(self._sc_keep["bc"])
@@ -175,12 +180,10 @@ class McmcEngine:
             hn[n:n + n * d] = np.random.randn(ng, d)[lo:lo + n].reshape(-1)
             self.z.copy_(self.h_noise[n:n + n * d].view(n, d), non_blocking=True)
         else:
-            if self._rng_fill is None:       # the step counter is the one argument that changes: a ctypes cell read at call time
-                self._rng_step = C.c_uint64(0)
-                self._rng_fill = _lib.bind("pmc_rng_fill", C.c_uint64(self.seed), self._rng_step, int(self.row_offset),
+            if self._rng_fill is None:       # the step counter is read on the device (ctl[STEP] + 1): nothing changes per call
+                self._rng_fill = _lib.bind("pmc_rng_fill_ctl", C.c_uint64(self.seed), _lib.ptr(self.ctl), int(self.row_offset),
                                            (d + self.nu) / 2 if self.tp else 0.0, _lib.ptr(self.g), _lib.ptr(self.z),
                                            _lib.ptr(self.r), n, d)
-            self._rng_step.value = self.step + 1
             self._rng_fill()
 
     def propose(self):
@@ -278,6 +281,21 @@ class McmcEngine:
             hn[n + n * d:] = np.random.rand(ng)[lo:lo + n]                       # mcmc.py:137
             self.r.copy_(self.h_noise[n + n * d:], non_blocking=True)
         key = calls is None
+        if not self.sharded:
+            # one launch: Metropolis update + block partials, and the block that finishes last adapts sigma / mu and
+            # applies the plateau rule (no-op once the stop flag is set)
+            if key not in self._accept_fused:
+                self._accept_fused[key] = _lib.bind(
+                    "pmc_mh_accept_finalize", self.kind, self.beta, self.nu, _lib.ptr(self.theta), _lib.ptr(self.u),
+                    _lib.ptr(self.x), _lib.ptr(self.logdetj), _lib.ptr(self.logl), _lib.ptr(self.logp), _lib.ptr(self.ldjf),
+                    _lib.ptr(self.prop64), _lib.ptr(self.u_p), _lib.ptr(self.x_p), _lib.ptr(self.ldj_p),
+                    _lib.ptr(self.logl_p), _lib.ptr(self.logp_p), _lib.ptr(self.ldjf_p), _lib.ptr(self.m_cur),
+                    _lib.ptr(self.m_prop), _lib.ptr(self.r), _lib.ptr(self.finite) if calls is None else None,
+                    _lib.ptr(self.alpha), _lib.ptr(self.partials), _lib.ptr(self.ctl), _lib.ptr(self.ticket), self.mean_mode,
+                    self.n_steps, self.n_max, n, d)
+            self._accept_fused[key]()
+            return
+        key = calls is None
         if key not in self._accept:
             self._accept[key] = _lib.bind(
                 "pmc_mh_accept_update", self.kind, self.beta, self.nu, _lib.ptr(self.theta), _lib.ptr(self.u),
@@ -292,10 +310,6 @@ class McmcEngine:
             _lib.call("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(parts), parts.shape[0], _lib.ptr(self.theta),
                       self.mean_mode, self.n_steps, self.n_max, self.n_global, d)
             return
-        if self._finalize is None:
-            self._finalize = _lib.bind("pmc_mcmc_finalize", self.kind, _lib.ptr(self.ctl), _lib.ptr(self.partials), 0,
-                                       _lib.ptr(self.theta), self.mean_mode, self.n_steps, self.n_max, n, d)
-        self._finalize()
 
     def read_controller(self):
         self.ctl_host.copy_(self.ctl, non_blocking=True)
@@ -317,16 +331,61 @@ class McmcEngine:
         self.loop()
         return self.results()
 
+    def _steps_before_check(self, c):
+        """How many steps may be queued before the controller is read back.  Exactness does not depend on it (queued
+        steps become no-ops once the stop flag is set); this only avoids queueing work that the plateau rule of
+        mcmc.py:170-180 would discard: the counter grows by at most one per step."""
+        if c is None:
+            return 1
+        sigma = max(abs(float(c[CTL_SIGMA])), 1e-300)
+        ratio = (2.38 / np.sqrt(self.d)) / sigma
+        if self.kind == KIND_RWM_FLOW:
+            ratio = min(1.0, ratio)
+        left = min(self.n_steps * ratio ** 2 - float(c[CTL_CNT]), self.n_max - float(c[CTL_STEP]))
+        return int(max(1, min(8, np.floor(left))))
+
+    def _after_step(self, c, step_calls, blobs_p):
+        if self.have_blobs:
+            acc = (self.r < self.alpha).cpu().numpy()
+            self.blobs[acc] = blobs_p[acc]                                   # mcmc.py:148-149
+        if self.progress_bar is not None:                                    # mcmc.py:159-167
+            self.progress_bar.update_stats(dict(
+                calls=self.progress_bar.info['calls'] + step_calls, acc=self.accept, steps=self.step,
+                logP=float(c[CTL_TRACK]) if self.tp else float((self.logl + self.logp).mean().item()),
+                eff=self.sigma / (2.38 / np.sqrt(self.d))))
+
     def loop(self):
         """MCMC steps until the plateau rule or n_max fires (mcmc.py:72-180); state stays on the GPU."""
         device_eval = self.loglike_device is not None and self.logprior_device is not None and not self.have_blobs
+        per_step = (1 if self.rng_mode == "device" else 0) + 1 + (1 if self.use_flow else 0) + 1 + (2 if self.sharded else 1)
+        if device_eval and self.rng_mode == "device" and not self.sharded:
+            # nothing of a step needs the host: queue several steps per controller read-back.  Every kernel of a step
+            # reads its scalars (sigma, mu, step) from the device controller block; the fused accept + adapt launch is
+            # a no-op after the stop flag is set, so the state stops changing exactly where the reference stops.
+            c = None
+            while True:
+                k = self._steps_before_check(c)
+                for _ in range(k):
+                    self.draw_noise()
+                    self.propose()
+                    self.pull_back()
+                    self.evaluate_device()
+                    self.accept_and_adapt(None)
+                done_before = self.step
+                c = self.read_controller()
+                self.launches += (per_step + 2) * k
+                step_calls = int(c[CTL_CALLS]) - self.n_calls
+                self.n_calls = int(c[CTL_CALLS])
+                if self.step > done_before or self.stop:
+                    self._after_step(c, step_calls, None)
+                if self.stop:
+                    break
+            return
         while True:
             self.draw_noise()
             self.propose()
             self.pull_back()
-            # rng_fill (device mode) + propose + [sweep] + scaler + [prior + likelihood] + accept + finalize
-            self.launches += (1 if self.rng_mode == "device" else 0) + 2 + (1 if self.use_flow else 0) + 2 \
-                + (2 if device_eval else 0)
+            self.launches += per_step + (2 if device_eval else 0) + (1 if (not device_eval and self.logprior_device is not None) else 0)
             if device_eval:
                 calls, blobs_p = self.evaluate_device()
             else:
@@ -339,14 +398,7 @@ class McmcEngine:
                 self.n_calls = int(c[CTL_CALLS])
             else:
                 step_calls = calls
-            if self.have_blobs:
-                acc = (self.r < self.alpha).cpu().numpy()
-                self.blobs[acc] = blobs_p[acc]                                   # mcmc.py:148-149
-            if self.progress_bar is not None:                                    # mcmc.py:159-167
-                self.progress_bar.update_stats(dict(
-                    calls=self.progress_bar.info['calls'] + step_calls, acc=self.accept, steps=self.step,
-                    logP=float(c[CTL_TRACK]) if self.tp else float((self.logl + self.logp).mean().item()),
-                    eff=self.sigma / (2.38 / np.sqrt(self.d))))
+            self._after_step(c, step_calls, blobs_p)
             if self.stop:
                 break
 

@@ -61,6 +61,21 @@ class Reparameterize:
         self._create_masks()
         self._dev = None
 
+    @classmethod
+    def adopt(cls, other):
+        """A ``pocomc_b200`` scaler with the fitted state of any object that looks like the reference's
+        ``pocomc.scaler.Reparameterize`` (attributes ndim, low, high, periodic, reflective, transform, scale, diagonal,
+        mu, sigma) -- what lets the reference's own ``Sampler`` call this package's MCMC kernels unchanged."""
+        if isinstance(other, cls):
+            return other
+        if not getattr(other, "diagonal", True):
+            raise NotImplementedError("only the diagonal affine transformation is implemented")
+        new = cls(int(other.ndim), bounds=np.stack([np.asarray(other.low, np.float64), np.asarray(other.high, np.float64)], axis=1),
+                  periodic=other.periodic, reflective=other.reflective, transform=other.transform, scale=bool(other.scale))
+        new.mu = None if other.mu is None else np.asarray(other.mu, dtype=np.float64)
+        new.sigma = None if other.sigma is None else np.asarray(other.sigma, dtype=np.float64)
+        return new
+
     # -- masks (scaler.py:459-490) ------------------------------------------------------------
     def _create_masks(self):
         lo, hi = np.isfinite(self.low), np.isfinite(self.high)
