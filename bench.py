@@ -311,7 +311,9 @@ def run_b200(args):
     cfg = CONFIGS[args.config]
     D, MCMC_STEPS = cfg["d"], cfg["steps"]
     if args.scaling == "strong":
-        total = 8 * cfg["n"]
+        # fixed TOTAL: the config's own total where it is defined on several GPUs, else 64 x the per-GPU count (a total
+        # small enough for one tile wave per GPU would only measure the latency floor of one sweep)
+        total = cfg["n"] * cfg["gpus"] if cfg["gpus"] > 1 else 64 * cfg["n"]
         n_local = (total // world + 255) // 256 * 256
     else:
         n_local = cfg["n"]

@@ -300,6 +300,10 @@ int pmc_lse(const double* logw, int64_t n, double* scratch, double* out2, pmc_st
 /* bootstrap: for b < n_boot: out[b] = logsumexp(logw[idx[b, :]]) - log n                        */
 int pmc_lse_bootstrap(const double* logw, const int64_t* idx, int64_t n, int64_t n_boot,
                       double* out, pmc_stream_t stream);
+/* the same bootstrap with the resampling indices drawn on the device (Philox4x32-10 keyed by seed, row, position):
+ * no [n_boot, n] index matrix in host or device memory; n < 2^32.                      */
+int pmc_lse_bootstrap_rng(const double* logw, int64_t n, int64_t n_boot, uint64_t seed, double* out,
+                          pmc_stream_t stream);
 
 /* ---- synthetic likelihoods / priors evaluated on device --------------------------------------
  * Used by bench.py's device-resident throughput arm and by the opt-in device fast path for

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pmc_trim_scratch_size": (_I64, [_I64]),
     "pmc_lse": (C.c_int, [_P, _I64, _P, _P, _P]),
     "pmc_lse_bootstrap": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
+    "pmc_lse_bootstrap_rng": (C.c_int, [_P, _I64, _I64, _U64, _P, _P]),
     "pmc_loglike": (C.c_int, [_I32, _P, _P, _P, _F64, _F64, _P, _I64, _I32, _P]),
     "pmc_logprior": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
 }

@@ -303,6 +303,44 @@ lse_bootstrap_kernel(const double* __restrict__ logw, const long long* __restric
 }
 
 
+// same statistic with the resampling indices drawn ON the device: row b uses idx_i = floor(u_i * n) with u_i from a
+// Philox4x32-10 counter keyed by (seed, b, i / 4) -- no [n_boot, n] index matrix exists anywhere (sampler.py:913 draws
+// it row by row with np.random.choice; section 8 f2)
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__global__ void __launch_bounds__(RED_THREADS)
+lse_bootstrap_rng_kernel(const double* __restrict__ logw, long long n, long long n_boot, unsigned long long seed,
+                         double* __restrict__ out) {
+  __shared__ double sh[24];
+  for (long long b = blockIdx.x; b < n_boot; b += gridDim.x) {
+    Lse3 a; a.init();
+    for (long long i4 = threadIdx.x; i4 * 4 < n; i4 += blockDim.x) {
+      const uint4 r = philox4x32(make_uint4((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)b, (uint32_t)(b >> 32) ^ 0x626f6f74u),
+                                 (uint32_t)seed, (uint32_t)(seed >> 32));
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (i4 * 4 + q < n) {
+          long long j = (long long)(((unsigned long long)rr[q] * (unsigned long long)n) >> 32);   // floor(u n), u = r / 2^32
+          a.push(logw[j < n ? j : n - 1]);
+        }
+      }
+    }
+    a = block_merge(a, sh);
+    if (threadIdx.x == 0) out[b] = a.m + log(a.s1) - log((double)n);
+    __syncthreads();
+  }
+}
+
+
 // ---- plain weight statistics (tools.py:56-93 on an explicit weight vector) -------------------
 __global__ void __launch_bounds__(RED_THREADS)
 wstats_partial_kernel(const double* __restrict__ w, long long m, double* __restrict__ scratch) {
@@ -483,6 +521,16 @@ extern "C" int pmc_lse_bootstrap(const double* logw, const int64_t* idx, int64_t
   if (n_boot == 0) return 0;
   const int blocks = (int)std::min<long long>(n_boot, (long long)sm_count() * 8);
   lse_bootstrap_kernel<<<blocks, RED_THREADS, 0, as_stream(stream)>>>(logw, (const long long*)idx, n, n_boot, out);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_lse_bootstrap_rng(const double* logw, int64_t n, int64_t n_boot, uint64_t seed, double* out,
+                                     pmc_stream_t stream) {
+  PMC_REQUIRE(logw && out && n >= 1 && n < (1ll << 32), "pmc_lse_bootstrap_rng: bad arguments");
+  if (n_boot == 0) return 0;
+  const int blocks = (int)std::min<long long>(n_boot, (long long)sm_count() * 8);
+  lse_bootstrap_rng_kernel<<<blocks, RED_THREADS, 0, as_stream(stream)>>>(logw, n, n_boot, (unsigned long long)seed, out);
   PMC_LAUNCH_CHECK();
   return 0;
 }

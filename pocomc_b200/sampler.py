@@ -441,8 +441,12 @@ class Sampler:
         logw = logl + logp + logdetj - logq
         m = len(logw)
         n_boot = int(np.maximum(n, 1000))
-        boot = np.stack([np.random.choice(m, m) for _ in range(n_boot)])    # host stream, reference order
-        logz, boots = lse_device(logw, boot)
+        if config.rng_mode == "device":
+            # resampling indices drawn inside the kernel: no index matrix; one host draw keys the counters
+            logz, boots = lse_device(logw, n_boot=n_boot, seed=int(np.random.randint(0, 2 ** 62)))
+        else:
+            # bit-faithful host stream, reference order (one np.random.choice(m, m) per replicate), 256 rows at a time
+            logz, boots = lse_device(logw, n_boot=n_boot, boot_rows=lambda k: np.stack([np.random.choice(m, m) for _ in range(k)]))
         self.calls += m
         self.pbar.update_stats(dict(calls=self.calls))
         self.logz = logz

@@ -56,7 +56,7 @@ class CorrelatedGaussian(_DeviceLikelihood):
         self.p0 = -0.5 * (n_dim * math.log(2 * math.pi) + np.linalg.slogdet(self.cov)[1])
 
     def __call__(self, x):
-        return -0.5 * np.einsum("ki,ij,kj->k", x, self.prec, x) + self.p0
+        return -0.5 * np.einsum("ij,ij->i", x @ self.prec, x) + self.p0        # one GEMM + a row-wise dot (a 3-operand einsum is ~40x slower)
 
     def analytic_logz(self, prior_sd):
         c = self.cov + prior_sd ** 2 * np.eye(self.n_dim)

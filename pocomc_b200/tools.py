@@ -86,9 +86,14 @@ def weight_stats_device(w: torch.Tensor, uss_k: int = 0) -> torch.Tensor:
     return out3
 
 
-def lse_device(logw, boot_idx=None):
-    """logsumexp(logw) - log n and, per bootstrap row b, logsumexp(logw[boot_idx[b]]) - log n
-    (sampler.py:910-913) on the GPU; numpy in / (float, numpy) out."""
+def lse_device(logw, boot_idx=None, n_boot=0, boot_rows=None, seed=None):
+    """logsumexp(logw) - log n and the bootstrap replicates logsumexp(logw[idx_b]) - log n (sampler.py:910-913) on the
+    GPU; numpy in / (float, numpy) out.  The resampling indices come from one of
+      * ``boot_idx``  : an explicit [B, n] index matrix (tests);
+      * ``boot_rows`` : a callable ``rows(k) -> [k, n] int64`` drawing the NEXT k rows from the host stream (the
+        reference draws ``np.random.choice(n, n)`` row by row): consumed in chunks of 256 rows, so host and device hold
+        O(256 n) indices instead of the O(n^2) matrix;
+      * ``seed``      : drawn on the device (Philox), no index matrix at all -- ``config.rng_mode == "device"``."""
     lw = _to_dev(logw)
     n = lw.numel()
     scratch = torch.empty(int(_lib.load().pmc_ps_scratch_size(n)), dtype=torch.float64, device=lw.device)
@@ -99,6 +104,19 @@ def lse_device(logw, boot_idx=None):
         idx = torch.as_tensor(np.ascontiguousarray(boot_idx, dtype=np.int64)).to(lw.device)
         res = torch.empty(idx.shape[0], dtype=torch.float64, device=lw.device)
         _lib.call("pmc_lse_bootstrap", _lib.ptr(lw), _lib.ptr(idx), n, idx.shape[0], _lib.ptr(res))
+        boots = res.cpu().numpy()
+    elif boot_rows is not None and n_boot > 0:
+        res = torch.empty(n_boot, dtype=torch.float64, device=lw.device)
+        done = 0
+        while done < n_boot:
+            k = min(256, n_boot - done)
+            idx = torch.as_tensor(np.ascontiguousarray(boot_rows(k), dtype=np.int64)).to(lw.device)
+            _lib.call("pmc_lse_bootstrap", _lib.ptr(lw), _lib.ptr(idx), n, k, _lib.ptr(res[done:]))
+            done += k
+        boots = res.cpu().numpy()
+    elif seed is not None and n_boot > 0:
+        res = torch.empty(n_boot, dtype=torch.float64, device=lw.device)
+        _lib.call("pmc_lse_bootstrap_rng", _lib.ptr(lw), n, n_boot, _lib.C.c_uint64(int(seed)), _lib.ptr(res))
         boots = res.cpu().numpy()
     return float(out[0].item()), boots
 
