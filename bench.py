@@ -276,14 +276,21 @@ def committed_traffic(kernel_name):
 
 
 def tri_issued_flop(tri_meta, n):
-    """FLOP the tcgen05 updates of one block-triangular sweep issue: sum over chunks of 2 * 128 * N * 8 * k-steps * 3 passes,
-    per 128-particle tile and per transform (made_layout.build_tri tables)."""
-    from pocomc_b200 import made_layout as ML
-    m = tri_meta
-    nch = int(m[ML.TRI_NCHUNKS])
-    ch = m[m[ML.TRI_OFF_CHUNKS]:m[ML.TRI_OFF_CHUNKS] + nch * ML.TRI_CHUNK_FIELDS].reshape(nch, -1)
-    per_tile = float(np.sum(2.0 * 128 * ch[:, 3] * 8 * ch[:, 2] * 3))
-    return per_tile * int(m[ML.TRI_T]) * math.ceil(n / 128)
+    """FLOP the tcgen05 groups of one windowed block-triangular sweep issue, per 128-particle tile and per transform
+    (tri_layout.build_tri tables): right-looking updates 2 * 128 * N * K per block and layer, left-looking window
+    initialisations 2 * 128 * N * K(all earlier slots) per window and layer; 3 passes (3xTF32)."""
+    from pocomc_b200 import tri_layout as TL
+    m = np.asarray(tri_meta, np.int64)
+    nb, nw = int(m[TL.TRI_NB]), int(m[TL.TRI_NW])
+    blocks = m[m[TL.TRI_OFF_BLOCKS]:m[TL.TRI_OFF_BLOCKS] + nb * TL.TB_FIELDS].reshape(nb, -1)
+    wins = m[m[TL.TRI_OFF_WINDOWS]:m[TL.TRI_OFF_WINDOWS] + nw * TL.TW_FIELDS].reshape(nw, -1)
+    mac = 0.0
+    for b in blocks:
+        if not (b[TL.TB_FLAGS] & 1):
+            mac += b[TL.TB_UPD_N] * (8 + 2 * b[TL.TB_KP]) + b[TL.TB_OUT_N] * b[TL.TB_KP]
+    for w in wins[1:]:
+        mac += w[TL.TW_WP] * (w[TL.TW_KX] + 2 * w[TL.TW_KH]) + w[TL.TW_OP] * w[TL.TW_KH]
+    return 2.0 * 128 * mac * 3 * int(m[TL.TRI_T]) * math.ceil(n / 128)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -65,16 +65,22 @@ int pmc_flow_forward_tc(const float* packed, const int32_t* meta_host, int32_t m
                         pmc_stream_t stream);
 
 /* ---- tensor-core (tcgen05) block-triangular sweep: Flow.inverse (flow.py:116-132 -> zuko
- * transform.inv.call_and_ladj, the hot call of pocomc/mcmc.py:88,256) and Flow.forward of affine flows.
- * Order positions are processed in blocks of 4: the dense dependence on all earlier blocks runs as
- * tcgen05.mma updates of per-unit accumulators in tensor memory (3xTF32 split, passes = 3; plain TF32,
- * passes = 1), the dependence inside a block as fp32 FMAs.  `packed` is the image described by
- * pocomc_b200.made_layout.build_tri, produced by pmc_flow_tc_pack; `meta_host` is the table in HOST
- * memory (launch geometry, validation), `meta_dev` the same table in device memory (read by the kernel).
- * in/out [N, D] f32 (may alias), ladj [N] f32.                                                     */
+ * transform.inv.call_and_ladj, the hot call of pocomc/mcmc.py:88,256) and Flow.forward of affine flows
+ * of any preset width (D = 8 .. 200, H = 32 .. 1024).
+ * Order positions are processed in blocks of 4, blocks in windows whose per-unit accumulators fit tensor
+ * memory: the dense dependence on earlier blocks runs as tcgen05.mma (right-looking updates inside a
+ * window, a left-looking initialisation from a scratch area when a window starts; 3xTF32 split,
+ * passes = 3; plain TF32, passes = 1), the dependence inside a block as fp32 FMAs.  `packed` is the image
+ * described by pocomc_b200.tri_layout.build_tri, produced by pmc_flow_tc_pack; `meta_host` is the table in
+ * HOST memory (launch geometry, validation), `meta_dev` the same table in device memory (read by the
+ * kernel).  in/out [N, D] f32 (may alias), ladj [N] f32.  `workspace`: device scratch of at least
+ * pmc_flow_sweep_tri_workspace(meta_host, meta_len, n) floats (0 for flows that fit one window; the
+ * pointer may then be NULL); the query returns -1 on a bad table.                                   */
+int64_t pmc_flow_sweep_tri_workspace(const int32_t* meta_host, int32_t meta_len, int64_t n);
 int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host, const int32_t* meta_dev,
                        int32_t meta_len, const float* in, float* out, float* ladj, int64_t n,
-                       int32_t inverse, int32_t passes, pmc_stream_t stream);
+                       int32_t inverse, int32_t passes, float* workspace, int64_t workspace_floats,
+                       pmc_stream_t stream);
 
 /* ---- Flow.fit optimiser step (flow.py:268,314-319) -------------------------------------------
  * torch.nn.utils.clip_grad_norm_(max_norm = hyper[5]; <= 0 disables) followed by

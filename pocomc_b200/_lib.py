@@ -27,7 +27,8 @@ SIGNATURES = {
     "pmc_flow_base_logprob": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "pmc_flow_tc_pack": (C.c_int, [_P, _P, _P, _I64, _P]),
     "pmc_flow_forward_tc": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I64, _I32, _P]),
-    "pmc_flow_sweep_tri": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "pmc_flow_sweep_tri_workspace": (_I64, [_P, _I32, _I64]),
+    "pmc_flow_sweep_tri": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P]),
     "pmc_adamw_scratch_size": (_I64, []),
     "pmc_adamw_clip_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "pmc_adamw_clip_step_ex": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),

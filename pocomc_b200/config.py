@@ -19,7 +19,7 @@ device_prior
     (identical formula, f64); any other prior object is called on the host like the reference does.
 inverse_path
     ``"tri"`` (default): ``Flow.inverse`` (and the flow pull-back of every MCMC step) of affine flows whose
-    accumulators fit tensor memory (``made_layout.tri_supported``: D = 10..32 at the preset widths) runs on the tcgen05
+    accumulators fit tensor memory (``tri_layout.tri_supported``: D >= 8 at the preset widths) runs on the tcgen05
     block-triangular sweep (csrc/flow_tri.cu, 3xTF32 split = fp32 fidelity); ``"sweep"``: always the fp32-FMA sweep.
 forward_path
     ``"tc"`` (default): ``Flow.forward`` / ``log_prob`` without a graph run on the tcgen05 dense kernel

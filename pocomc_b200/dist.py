@@ -17,7 +17,7 @@ import torch
 import torch.distributed as td
 
 __all__ = ["init_from_env", "is_active", "world", "shard_range", "shard_counts", "gather_blocks", "allreduce_sum_det",
-           "allreduce_sum_int", "merge_weight_stats", "combine_weight_stats",
+           "allreduce_sum_int", "broadcast_from_rank0", "barrier", "merge_weight_stats", "combine_weight_stats",
            "gather_history_scalars", "split_history_index"]
 
 
@@ -75,6 +75,10 @@ def gather_blocks(local: torch.Tensor, counts=None) -> torch.Tensor:
         return local
     if _host_staged(local):
         return gather_blocks(local.cpu(), counts).to(local.device)
+    if not local.is_cuda and td.get_backend() == "nccl":
+        # NCCL moves device memory only: host arrays (history rows, index lists) are staged through this rank's GPU
+        dev = torch.device("cuda", torch.cuda.current_device())
+        return gather_blocks(local.to(dev), counts).cpu()
     ws = td.get_world_size()
     if counts is None:
         counts = [local.shape[0]] * ws
@@ -111,6 +115,21 @@ def allreduce_sum_int(value: int) -> int:
     t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
     td.all_reduce(t)
     return int(t.item())
+
+
+def broadcast_from_rank0(array: np.ndarray) -> np.ndarray:
+    """rank 0's copy of a host array on every rank (seeds, prior samples: whatever every replica must agree on)"""
+    if not is_active():
+        return array
+    dev = "cpu" if td.get_backend() == "gloo" else torch.device("cuda", torch.cuda.current_device())
+    t = torch.from_numpy(np.ascontiguousarray(array)).to(dev)
+    td.broadcast(t, src=0)
+    return t.cpu().numpy()
+
+
+def barrier():
+    if is_active():
+        td.barrier()
 
 
 def merge_weight_stats(parts: np.ndarray) -> np.ndarray:

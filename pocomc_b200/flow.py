@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from . import _lib, config
 from . import made_layout as ML
+from . import tri_layout as TL
 from .tools import torch_double_to_float
 
 __all__ = ["Flow", "regularization_loss", "MaskedAutoregressiveFlow"]
@@ -128,27 +129,28 @@ class MaskedAutoregressiveFlow(nn.Module):
         self._tc_key = None
         # tensor-core block-triangular sweep (csrc/flow_tri.cu): the inverse direction of affine flows
         self._tri = None
-        if ML.tri_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind):
-            self._tri = ML.build_tri(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
+        if TL.tri_supported(lay.n_dim, lay.n_hidden, lay.n_layers, lay.kind):
+            self._tri = TL.build_tri(lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms, lay.kind, lay.bins)
             self.register_buffer("tri_gather", torch.from_numpy(self._tri.gather.copy()), persistent=False)
             self.register_buffer("tri_meta", torch.from_numpy(self._tri.meta.copy()), persistent=False)
             self._tri_meta_host = np.ascontiguousarray(self._tri.meta)
         self._tri_packed = None
         self._tri_key = None
+        self._tri_ws = None
 
     # -- plumbing ---------------------------------------------------------------------------
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"], st["_packed_key"], st["_masks"] = None, None, None
         st["_tc_packed"], st["_tc_key"] = None, None
-        st["_tri_packed"], st["_tri_key"] = None, None
+        st["_tri_packed"], st["_tri_key"], st["_tri_ws"] = None, None, None
         st.pop("_fit_engine", None)
         return st
 
     def _apply(self, fn, *a, **k):
         self._packed, self._packed_key, self._masks = None, None, None
         self._tc_packed, self._tc_key = None, None
-        self._tri_packed, self._tri_key = None, None
+        self._tri_packed, self._tri_key, self._tri_ws = None, None, None
         self.__dict__.pop("_fit_engine", None)
         return super()._apply(fn, *a, **k)
 
@@ -227,19 +229,34 @@ class MaskedAutoregressiveFlow(nn.Module):
             self._tri_key = key
         return self._tri_packed
 
+    def _tri_workspace(self, n: int):
+        """scratch area of the windowed sweep (flows wider than one tensor-memory window): one slab per resident CTA"""
+        if self._tri.ws_floats == 0:
+            return None, 0
+        need = int(_lib.load().pmc_flow_sweep_tri_workspace(self._tri_meta_host.ctypes.data_as(_lib.C.c_void_p),
+                                                            int(self._tri_meta_host.size), int(n)))
+        if need < 0:
+            _lib.check(2, "pmc_flow_sweep_tri_workspace")
+        ws = self.__dict__.get("_tri_ws")
+        if ws is None or ws.numel() < need or ws.device != self.raw.device:
+            ws = torch.empty(need, dtype=torch.float32, device=self.raw.device)
+            self._tri_ws = ws
+        return ws, need
+
     def _tri_args(self, src, out, ladj, inverse, passes=None):
         packed = self.packed_tri()
         if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
             raise ValueError("the tensor-core sweep needs a contiguous CUDA float32 input")
+        ws, need = self._tri_workspace(src.shape[0])
         return (_lib.ptr(packed), self._tri_meta_host.ctypes.data_as(_lib.C.c_void_p), _lib.ptr(self.tri_meta),
                 int(self._tri_meta_host.size), _lib.ptr(src), _lib.ptr(out), _lib.ptr(ladj), src.shape[0], 1 if inverse else 0,
-                int(config.tri_passes if passes is None else passes)), packed
+                int(config.tri_passes if passes is None else passes), _lib.ptr(ws), int(need)), (packed, ws)
 
     @torch.no_grad()
     def sweep_tri_into(self, src: torch.Tensor, out: torch.Tensor, ladj: torch.Tensor, inverse: bool, passes=None):
         """latent -> data (or data -> latent) on tcgen05: CUDA f32 src/out [N, D], ladj [N]."""
         if not self.tri_available():
-            raise ValueError("this flow has no tensor-core block-triangular sweep (made_layout.tri_supported)")
+            raise ValueError("this flow has no tensor-core block-triangular sweep (tri_layout.tri_supported)")
         args, _ = self._tri_args(src, out, ladj, inverse, passes)
         _lib.call("pmc_flow_sweep_tri", *args)
 
@@ -286,9 +303,9 @@ class MaskedAutoregressiveFlow(nn.Module):
         """Pre-bound ``sweep_into`` for fixed buffers and fixed weights (the MCMC loop calls the flow with the same
         tensors every step); the returned callable keeps the packed weight image alive."""
         if self._use_tri(inverse):
-            args, packed = self._tri_args(src, out, ladj, inverse)
+            args, keep = self._tri_args(src, out, ladj, inverse)
             run = _lib.bind("pmc_flow_sweep_tri", *args)
-            run.keep = (packed, self._tri_meta_host, self.tri_meta, src, out, ladj)
+            run.keep = (keep, self._tri_meta_host, self.tri_meta, src, out, ladj)
             return run
         packed = self.packed()
         if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):

@@ -533,304 +533,3 @@ def build_train(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kin
         [D, Dp, H, L, T, No, tstride, bias_off, lay.raw_tstride, len(maps[0]), len(tiles), 200]
     return TrainLayout(tstride, bias_off, len(maps[0]), meta.astype(np.int32), gather.astype(np.int32), wmap.astype(np.int32),
                        np.asarray(tiles, np.int32).reshape(-1, 4))
-
-
-# ---------------------------------------------------------------------------------------------
-# block-triangular sweep on tcgen05 (csrc/flow_tri.cu): Flow.inverse (and forward) of affine flows
-# ---------------------------------------------------------------------------------------------
-# The degree-ordered sweep is a nonlinear forward substitution.  Order positions (stages) are cut into blocks of
-# TRI_G; the hidden units born in a block (degree groups k0+1 .. k0+8) form one K-slab.  Everything a block needs
-# from EARLIER blocks is dense: after a block is finished, its activations (a [128 particles x K] A tile per layer,
-# hi/lo TF32 images in shared memory) update the pre-activation accumulators of ALL later units with one
-# tcgen05.mma group per layer (right-looking; accumulators live in tensor memory, one column per unit slot and per
-# output).  What is left inside a block -- the block-triangular dependencies between its own TRI_G groups -- runs as fp32
-# FMAs with one thread per particle and the block's activations in registers.  TRI_G = 4 keeps the fully unrolled
-# in-block code of one block shape at ~7 KB, inside the SM's 32 KB instruction cache: with blocks of 8 (43-64 KB of
-# straight-line code per shape) the substitution threads spent half their cycles waiting for instructions
-# (profiles/r2d_tri_g8_ncu.txt).
-TRI_G = int(__import__("os").environ.get("PMC_TRI_G", "4"))      # 4 or 8 (csrc/flow_tri.cu is built for both)
-TRI_VERSION = 203
-(TRI_D, TRI_H, TRI_L, TRI_T, TRI_NB, TRI_HC, TRI_COL_OUT, TRI_NCOLS, TRI_TSTRIDE, TRI_NCHUNKS, TRI_SLOT_BYTES, TRI_DSLOT_BYTES,
- TRI_TILE_BYTES, TRI_OFF_BLOCKS, TRI_OFF_CHUNKS, TRI_VER, TRI_NSTAGES, TRI_GSIZE, TRI_HEADER) = range(19)
-TRI_BLOCK_FIELDS = 10     # k0, nstages, U, W (slots; the K extent of the A tiles is W rounded up to 8), hc (first hidden column), diag offset (floats), diag floats, chunk0, n_urgent, n_chunks
-TRI_CHUNK_FIELDS = 8      # a_src (0 = x tile, l = layer-l tile), ks0, nks, N, dcol, first (1: overwrite), offset (floats), flags (1 last urgent, 2 last of block)
-TRI_SMEM_BUDGET = 227 * 1024
-TRI_BSLOT_TARGET = 24 * 1024
-# one update group per block (every later column at once) instead of "next block first, the rest behind it": the MMA
-# issuer is a single thread and its instruction stream, not the tensor pipe, bounds the update (profiles/r2k)
-TRI_SPLIT_UPDATES = False
-TRI_MAX_STAGES = 16       # update-slab ring: as many slots as shared memory allows, at most this (csrc/flow_tri.cu)
-
-
-def tri_slot(j, s, G, E):
-    """column / K index of unit s of in-block group j: four regular columns per group, extras behind them."""
-    return 4 * j + s if s < 4 else 4 * G + E * j + (s - 4)
-
-
-def tri_diag_floats(G: int, U: int) -> int:
-    """floats of one block's FFMA weight slab (format walked in lock step by csrc/flow_tri.cu: tri_stage; float4
-    granularity).  NR = 4 + E destination units per group; sources come in PAIRS (packed fp32 FMAs: one float2 of
-    weights (w[src 2p], w[src 2p+1]) per destination unit):
-      stage j:  out bias f4 | out weights of source groups 0..j-1: 2 f4 (+1 f4 extras)
-                layer-1 bias | layer-1 weights of x pairs 0..j>>1: NR float2 each
-                layers 2, 3: bias | source groups 0..j: NR f4 regular (+ 2 f4 for the extra source)
-    plus a tail pad of one group (the kernel prefetches one group ahead)."""
-    E = max(U - 4, 0)
-    if E > 1:
-        raise ValueError("block shapes with more than 5 units per group are not built")
-    NR = 4 + E
-    nrv = 1 if NR == 4 else 2
-    q1 = (2 * NR + 3) // 4
-    n = 0
-    for j in range(G):
-        n += 1 + j * (2 + (1 if E else 0))
-        n += nrv + (j // 2 + 1) * q1
-        n += 2 * (nrv + (j + 1) * (NR + (2 if E else 0)))
-    return 4 * (n + NR + 2)
-
-
-@dataclass(frozen=True)
-class TriLayout:
-    tstride: int           # floats per transform in the packed image
-    meta: np.ndarray       # int32
-    gather: np.ndarray     # int32 [T * tstride]  (pmc_flow_tc_pack codes)
-    smem_bytes: int
-    blocks: tuple          # per block dict (host-side description, used by the emulator / tests)
-    chunks: tuple
-
-    @property
-    def numel(self):
-        return int(self.gather.size)
-
-
-def _tri_blocks(D: int, H: int):
-    G = TRI_G
-    ng = D - 1
-    deg = (np.arange(H) % ng) + 1
-    hperm = np.argsort(deg, kind="stable")
-    gstart = np.searchsorted(deg[hperm], np.arange(1, ng + 2), side="left")
-    gsize = np.diff(gstart)
-    blocks = []
-    hc = 0
-    for b in range((D + G - 1) // G):
-        k0 = b * G
-        nst = min(D, k0 + G) - k0
-        groups = [g for g in range(k0 + 1, k0 + nst + 1) if g <= ng]
-        U = int(max([gsize[g - 1] for g in groups], default=0))
-        E = max(U - 4, 0)
-        W = 4 * G + E * G
-        unit = np.full(W, -1, np.int64)                  # slot -> original hidden unit
-        for g in groups:
-            for s in range(int(gsize[g - 1])):
-                unit[tri_slot(g - (k0 + 1), s, G, E)] = hperm[gstart[g - 1] + s]
-        blocks.append(dict(k0=k0, nst=nst, U=U, E=E, W=W, Kp=(W + 7) // 8 * 8, Nb=(W + 15) // 16 * 16, hc=hc, unit=unit))
-        hc += blocks[-1]["Nb"]
-    return blocks, hc
-
-
-def tri_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int) -> bool:
-    if kind != KIND_AFFINE or n_layers != 3 or n_dim < 2:
-        return False
-    blocks, Hc = _tri_blocks(n_dim, n_hidden)
-    if any(b["U"] > 5 for b in blocks) or len(blocks) < 2:
-        return False
-    if n_layers * Hc + (2 * n_dim + 15) // 16 * 16 > 512:
-        return False
-    try:
-        return build_tri(n_dim, n_hidden, n_layers, 1, kind).smem_bytes <= TRI_SMEM_BUDGET
-    except ValueError:
-        return False
-
-
-@lru_cache(maxsize=None)
-def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8) -> TriLayout:
-    if kind != KIND_AFFINE or n_layers != 3:
-        raise ValueError("the tcgen05 block-triangular sweep is built for affine flows with 3 hidden layers")
-    lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
-    D, H, L, T, G = n_dim, n_hidden, n_layers, n_transforms, TRI_G
-    blocks, Hc = _tri_blocks(D, H)
-    NB = len(blocks)
-    if any(b["U"] > 5 for b in blocks) or NB < 2:
-        raise ValueError("degree groups too wide (or too few order positions) for the block-triangular sweep")
-    col_out = L * Hc
-    n_out_cols = (2 * D + 15) // 16 * 16
-    ncols = col_out + n_out_cols
-    if ncols > 512:
-        raise ValueError("accumulators exceed tensor memory (512 columns)")
-    raw_off = np.concatenate([[0], np.cumsum([int(np.prod(s)) for s in lay.raw_sizes])]).astype(np.int64)
-    PLAIN = TC_BIAS_FLAG
-
-    # destination column -> (kind, index) tables shared by every transform
-    col_unit = np.full(Hc, -1, np.int64)                 # hidden column -> original unit
-    for b in blocks:
-        col_unit[b["hc"]:b["hc"] + b["W"]] = b["unit"]
-
-    def transform_parts(t):
-        base = t * lay.raw_tstride
-        iperm = np.arange(D) if t % 2 == 0 else D - 1 - np.arange(D)
-        w = [base + raw_off[2 * l] for l in range(L + 1)]
-        bia = [base + raw_off[2 * l + 1] for l in range(L + 1)]
-        parts, chunk_rows, block_rows = [], [], []
-        off = 0
-        for bi, b in enumerate(blocks):
-            k0, nst, U, E, W, unit = b["k0"], b["nst"], b["U"], b["E"], b["W"], b["unit"]
-            row = 4 + (4 if E else 0)
-            # ---- diagonal (FFMA) slab: see tri_diag_floats for the format ----
-            NR = 4 + E
-            nrv = 1 if NR == 4 else 2
-            q1 = (2 * NR + 3) // 4
-
-            def wsrc(widx, width, dst_unit, src_key):
-                """raw index of W_widx[dst_unit, src_key] or -1"""
-                return -1 if (dst_unit < 0 or src_key < 0) else w[widx] + dst_unit * width + src_key
-
-            d = []
-            for j in range(G):
-                k = k0 + j
-                valid_stage = j < nst
-                feat = iperm[k] if valid_stage else -1
-                row_s = 2 * feat if valid_stage else -1            # output rows (shift, scale_raw) of this order position
-                bo = np.full(4, -1, np.int64)
-                if valid_stage:
-                    bo[0], bo[1] = bia[L] + row_s, bia[L] + row_s + 1
-                d.append(bo)
-                for c in range(j):
-                    for p in range(2):
-                        u0, u1 = unit[4 * c + 2 * p], unit[4 * c + 2 * p + 1]
-                        d.append(np.array([wsrc(L, H, row_s, u0), wsrc(L, H, row_s, u1),
-                                           wsrc(L, H, row_s + 1 if valid_stage else -1, u0),
-                                           wsrc(L, H, row_s + 1 if valid_stage else -1, u1)], np.int64))
-                    if E:
-                        ue = unit[4 * G + c]
-                        d.append(np.array([wsrc(L, H, row_s, ue), wsrc(L, H, row_s + 1 if valid_stage else -1, ue), -1, -1], np.int64))
-                own_unit = np.array([unit[tri_slot(j, s_, G, E)] for s_ in range(NR)], np.int64)
-                bb = np.full(4 * nrv, -1, np.int64)
-                ok = own_unit >= 0
-                bb[:NR][ok] = bia[0] + own_unit[ok]
-                d.append(bb)
-                for q in range(j // 2 + 1):
-                    blk = np.full(4 * q1, -1, np.int64)
-                    for s_ in range(NR):
-                        for h in range(2):
-                            i = 2 * q + h
-                            if i <= j and k0 + i < D:
-                                blk[2 * s_ + h] = wsrc(0, D, own_unit[s_], iperm[k0 + i])
-                    d.append(blk)
-                for l in range(1, L):
-                    bb = np.full(4 * nrv, -1, np.int64)
-                    bb[:NR][ok] = bia[l] + own_unit[ok]
-                    d.append(bb)
-                    for c in range(j + 1):
-                        blk = np.full(4 * NR, -1, np.int64)
-                        for p in range(2):
-                            for s_ in range(NR):
-                                for h in range(2):
-                                    blk[(p * NR + s_) * 2 + h] = wsrc(l, H, own_unit[s_], unit[4 * c + 2 * p + h])
-                        d.append(blk)
-                        if E:
-                            blk = np.full(8, -1, np.int64)
-                            for s_ in range(NR):
-                                blk[s_] = wsrc(l, H, own_unit[s_], unit[4 * G + c])
-                            d.append(blk)
-            d.append(np.full(4 * (NR + 2), -1, np.int64))              # tail pad: the kernel prefetches one group ahead
-            d = np.concatenate(d)
-            assert len(d) == tri_diag_floats(G, U), (len(d), tri_diag_floats(G, U))
-            d = np.where(d >= 0, d | PLAIN, -1)
-            diag_off, diag_n = off, len(d)
-            parts.append(d)
-            off += len(d)
-            # ---- update (MMA) slabs: urgent = next block's columns, rest = everything after it ----
-            chunk0 = len(chunk_rows)
-            n_urgent = 0
-            if bi + 1 < NB:
-                nxt = blocks[bi + 1]
-                # outputs: every remaining output column in ONE urgent update; widths are multiples of 16, so when the
-                # remainder is 8 mod 16 the update starts 8 columns early, on this block's own (already consumed) outputs
-                rem = n_out_cols - 2 * G * (bi + 1)
-                o_start = 2 * G * (bi + 1) - (8 if rem % 16 else 0)
-                if TRI_SPLIT_UPDATES:
-                    ranges = [("u", nxt["hc"], nxt["hc"] + nxt["Nb"], o_start, n_out_cols)]
-                    if bi + 2 < NB:
-                        ranges.append(("r", blocks[bi + 2]["hc"], Hc, 0, 0))
-                else:
-                    ranges = [("u", nxt["hc"], Hc, o_start, n_out_cols)]
-                for tag, h0, h1, o0, o1 in ranges:
-                    for ld in range(1, L + 2):                          # destination: hidden layer ld, or outputs (L + 1)
-                        if ld <= L:
-                            c0, c1, dcol = h0, h1, (ld - 1) * Hc + h0
-                        else:
-                            c0, c1, dcol = o0, o1, col_out + o0
-                        N = c1 - c0
-                        if N <= 0:
-                            continue
-                        K = 8 if ld == 1 else b["Kp"]
-                        idx = np.full((N, K), -1, np.int64)
-                        for n in range(N):
-                            if ld <= L:
-                                u_dst = col_unit[c0 + n]
-                                if u_dst < 0:
-                                    continue
-                                if ld == 1:
-                                    for i in range(min(8, nst)):
-                                        idx[n, i] = w[0] + u_dst * D + iperm[k0 + i]
-                                else:
-                                    ok = np.nonzero(unit >= 0)[0]
-                                    idx[n, ok] = w[ld - 1] + u_dst * H + unit[ok]
-                            else:
-                                col = c0 + n
-                                kk, c = col // 2, col % 2
-                                if kk >= D or kk < k0 + nst:
-                                    continue                      # padding columns / this block's own consumed outputs
-                                ok = np.nonzero(unit >= 0)[0]
-                                idx[n, ok] = w[L] + (2 * iperm[kk] + c) * H + unit[ok]
-                        # split into chunks of whole k-steps that fit a ring slot
-                        per_ks = N * 8 * 4 * 2
-                        max_ks = max(1, TRI_BSLOT_TARGET // per_ks)
-                        ks = 0
-                        while ks < K // 8:
-                            nks = min(max_ks, K // 8 - ks)
-                            sub = idx[:, 8 * ks:8 * (ks + nks)]
-                            img = sub.reshape(N, nks * 2, 4).transpose(1, 0, 2).reshape(-1)        # [k/4][N][4]
-                            parts.append(img)
-                            parts.append(np.where(img >= 0, -(img + 2), -1))
-                            chunk_rows.append([0 if ld == 1 else ld - 1, ks, nks, N, dcol, 1 if (bi == 0 and ks == 0) else 0, off, 0])
-                            off += 2 * len(img)
-                            ks += nks
-                    if tag == "u":
-                        chunk_rows[-1][7] |= 1
-                        n_urgent = len(chunk_rows) - chunk0
-                chunk_rows[-1][7] |= 2
-            block_rows.append([k0, nst, U, W, b["hc"], diag_off, diag_n, chunk0, n_urgent, len(chunk_rows) - chunk0])
-        return np.concatenate(parts), chunk_rows, block_rows
-
-    gathers = []
-    for t in range(T):
-        gthr, chunk_rows, block_rows = transform_parts(t)
-        gathers.append(gthr)
-    tstride = len(gathers[0])
-    assert all(len(g) == tstride for g in gathers) and tstride % 4 == 0
-    chunk_rows = np.asarray(chunk_rows, np.int64).reshape(-1, TRI_CHUNK_FIELDS)
-    block_rows = np.asarray(block_rows, np.int64)
-    chunk_bytes = chunk_rows[:, 2] * chunk_rows[:, 3] * 64 if len(chunk_rows) else np.zeros(1, np.int64)
-    slot_bytes = int((chunk_bytes.max() + 1023) // 1024 * 1024)
-    dslot_bytes = int((block_rows[:, 6].max() * 4 + 1023) // 1024 * 1024)
-    tile_bytes = int(max(b["Kp"] for b in blocks)) * 512
-    if len(chunk_rows) > 96 or NB > 12:
-        raise ValueError("too many update chunks / blocks for the kernel's tables")
-    fixed = L * 2 * tile_bytes + 2 * 4096 + 2 * dslot_bytes + 8192        # + the kernel's static tables and barriers
-    stages = min(TRI_MAX_STAGES, (TRI_SMEM_BUDGET - fixed) // slot_bytes)
-    if stages < 2:
-        raise ValueError("shared memory budget exceeded")
-    smem = fixed + stages * slot_bytes
-    meta = np.zeros(TRI_HEADER, np.int64)
-    meta[[TRI_D, TRI_H, TRI_L, TRI_T, TRI_NB, TRI_HC, TRI_COL_OUT, TRI_NCOLS, TRI_TSTRIDE, TRI_NCHUNKS, TRI_SLOT_BYTES,
-          TRI_DSLOT_BYTES, TRI_TILE_BYTES, TRI_VER, TRI_NSTAGES, TRI_GSIZE]] = \
-        [D, H, L, T, NB, Hc, col_out, ncols, tstride, len(chunk_rows), slot_bytes, dslot_bytes, tile_bytes, TRI_VERSION, stages, G]
-    meta[TRI_OFF_BLOCKS] = TRI_HEADER
-    meta[TRI_OFF_CHUNKS] = TRI_HEADER + block_rows.size
-    meta = np.concatenate([meta, block_rows.reshape(-1), chunk_rows.reshape(-1)])
-    gather = np.concatenate(gathers)
-    assert np.abs(gather).max() < 2 ** 31 and meta.max() < 2 ** 31
-    return TriLayout(tstride, meta.astype(np.int32), gather.astype(np.int32), int(smem),
-                     tuple({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in b.items()} for b in blocks),
-                     tuple(map(tuple, chunk_rows.tolist())))

@@ -404,10 +404,13 @@ class McmcEngine:
 
     def results(self):
         """Download the final state in the reference's result-dict layout (mcmc.py:182-183)."""
-        return dict(u=self.u.cpu().numpy(), x=self.x.cpu().numpy(), logdetj=self.logdetj.cpu().numpy(),
-                    logl=self.logl.cpu().numpy(), logp=self.logp.cpu().numpy(), blobs=self.blobs,
-                    efficiency=self.sigma, accept=self.accept, steps=self.step, calls=self.n_calls,
-                    proposal_scale=self.sigma)
+        out = dict(u=self.u.cpu().numpy(), x=self.x.cpu().numpy(), logdetj=self.logdetj.cpu().numpy(),
+                   logl=self.logl.cpu().numpy(), logp=self.logp.cpu().numpy(), blobs=self.blobs,
+                   efficiency=self.sigma, accept=self.accept, steps=self.step, calls=self.n_calls,
+                   proposal_scale=self.sigma)
+        if self.sharded and self.loglike_device is not None and self.logprior_device is not None and not self.have_blobs:
+            out["calls_global"] = True           # counted from the all-gathered partials: already the sum over ranks
+        return out
 
 
 @torch.no_grad()

@@ -62,6 +62,11 @@ class Sampler:
         if n_ess is not None:
             n_effective = n_ess
             warnings.warn("n_ess is deprecated. Use n_effective instead.", DeprecationWarning, stacklevel=2)
+        if random_state is None and dist.is_active():
+            # particle-sharded runs are REPLICATED state machines: every rank must draw the same prior samples, resampling
+            # indices and MCMC noise, or the ranks take different branches (and collectives deadlock).  Without a seed from
+            # the user, rank 0 picks one for everybody.
+            random_state = int(dist.broadcast_from_rank0(np.array([np.random.randint(0, 2 ** 31 - 1)], dtype=np.int64))[0])
         if random_state is not None:                                         # sampler.py:195-197
             np.random.seed(random_state)
             torch.manual_seed(random_state)
@@ -187,6 +192,8 @@ class Sampler:
 
         if self.prior_samples is None:
             self.prior_samples = self.sample_prior(self.n_prior)
+            if dist.is_active():             # a user prior with its own RNG must not split the replicas
+                self.prior_samples = dist.broadcast_from_rank0(np.asarray(self.prior_samples, dtype=np.float64))
             self.scaler.fit(self.prior_samples)
 
         if self.warmup:                                                    # sampler.py:442-489
@@ -315,7 +322,9 @@ class Sampler:
         out = dict(res)
         out["u"], out["x"] = np.ascontiguousarray(full[:, :d]), np.ascontiguousarray(full[:, d:2 * d])
         out["logdetj"], out["logl"], out["logp"] = (np.ascontiguousarray(full[:, 2 * d + i]) for i in range(3))
-        out["calls"] = dist.allreduce_sum_int(res["calls"])
+        # host-evaluated likelihoods count this rank's rows; the device-callback path reads the controller block, which the
+        # fixed-order reduction already made global
+        out["calls"] = res["calls"] if res.get("calls_global") else dist.allreduce_sum_int(res["calls"])
         if self.have_blobs:
             parts = [None] * ws
             torch.distributed.all_gather_object(parts, res["blobs"])
@@ -500,12 +509,26 @@ class Sampler:
     # ------------------------------------------------------------------------------------------
     # checkpointing (sampler.py:1023-1061)
     # ------------------------------------------------------------------------------------------
+    def _state_path(self, path):
+        """Replicated runs: one file, written by rank 0.  Particle-sharded history (config.shard_history): every rank owns a
+        slice of the history, so rank r > 0 writes / reads ``<path>.rank<r>`` next to rank 0's ``<path>``."""
+        rank, ws = dist.world()
+        from .sharded import ShardedParticles
+        sharded = ws > 1 and isinstance(self.particles, ShardedParticles)
+        p = Path(path)
+        return rank, ws, sharded, (p if rank == 0 or not sharded else p.with_name(p.name + f".rank{rank}"))
+
     def save_state(self, path: Union[str, Path]):
         """Atomic dill dump of the sampler's attributes (device mirrors are dropped by the
-        members' own ``__getstate__`` and rebuilt lazily after ``load_state``)."""
-        print(f'Saving PMC state to {path}')
-        Path(path).parent.mkdir(exist_ok=True)
-        temp_path = Path(path).with_suffix('.temp')
+        members' own ``__getstate__`` and rebuilt lazily after ``load_state``); sampler.py:1023-1049."""
+        rank, ws, sharded, mine = self._state_path(path)
+        if ws > 1 and not sharded and rank != 0:
+            dist.barrier()                        # rank 0 writes the (identical) replicated state
+            return
+        if rank == 0:
+            print(f'Saving PMC state to {path}')
+        mine.parent.mkdir(exist_ok=True)
+        temp_path = mine.with_name(mine.name + '.temp')
         with open(temp_path, 'wb') as f:
             state = self.__dict__.copy()
             del state['pbar']
@@ -518,10 +541,13 @@ class Sampler:
             dill.dump(file=f, obj=state)
             f.flush()
             os.fsync(f.fileno())
-        os.rename(temp_path, path)
+        os.rename(temp_path, mine)
+        dist.barrier()
 
     def load_state(self, path: Union[str, Path]):
-        with open(path, 'rb') as f:
+        """sampler.py:1051-1061; under a sharded history every rank reads its own slice back."""
+        _, _, _, mine = self._state_path(path)
+        with open(mine if mine.exists() else path, 'rb') as f:
             state = dill.load(file=f)
         self.__dict__ = {**self.__dict__, **state}
 

@@ -196,40 +196,58 @@ def pack_tri(tri, raw):
 
 
 def sweep_tri(tri, packed, x, inverse, passes=3):
-    from pocomc_b200 import made_layout as ML
+    """numpy walk of the windowed block-triangular schedule over the packed image of tri_layout.build_tri: tensor memory as
+    a NaN-initialised [n, 512] array (unwritten columns must never be read), the scratch area as per-layer [n, K] arrays,
+    the chunk stream consumed with a running pointer exactly like the kernel's producer / issuer."""
+    from pocomc_b200 import tri_layout as TL
     m = tri.meta
-    D, H, L, T, NB, Hc, col_out, ncols = (int(m[i]) for i in (ML.TRI_D, ML.TRI_H, ML.TRI_L, ML.TRI_T, ML.TRI_NB, ML.TRI_HC,
-                                                               ML.TRI_COL_OUT, ML.TRI_NCOLS))
-    G = ML.TRI_G
-    blocks = m[m[ML.TRI_OFF_BLOCKS]:m[ML.TRI_OFF_BLOCKS] + NB * ML.TRI_BLOCK_FIELDS].reshape(NB, -1)
-    nch = int(m[ML.TRI_NCHUNKS])
-    chunks = m[m[ML.TRI_OFF_CHUNKS]:m[ML.TRI_OFF_CHUNKS] + nch * ML.TRI_CHUNK_FIELDS].reshape(nch, -1)
+    D, L, T, NB, NW, G, KC = (int(m[i]) for i in (TL.TRI_D, TL.TRI_L, TL.TRI_T, TL.TRI_NB, TL.TRI_NW, TL.TRI_GSIZE, TL.TRI_KCHUNK))
+    blocks = m[m[TL.TRI_OFF_BLOCKS]:m[TL.TRI_OFF_BLOCKS] + NB * TL.TB_FIELDS].reshape(NB, -1).astype(np.int64)
+    wins = m[m[TL.TRI_OFF_WINDOWS]:m[TL.TRI_OFF_WINDOWS] + NW * TL.TW_FIELDS].reshape(NW, -1).astype(np.int64)
     f32 = np.float32
     trunc = lambda v: (np.ascontiguousarray(v, f32).view(np.uint32) & np.uint32(0xffffe000)).view(f32)
     v = np.array(x, f32, copy=True)
     n = len(v)
     ladj = np.zeros(n, f32)
     log_slope = f32(np.log(1e-3))
+
+    def mma(A, Bh, Bl):
+        Ah = trunc(A)
+        Al = A - Ah
+        Dm = Ah.astype(np.float64) @ Bh.T.astype(np.float64)
+        if passes > 1:
+            Dm += Al.astype(np.float64) @ Bh.T.astype(np.float64) + Ah.astype(np.float64) @ Bl.T.astype(np.float64)
+        return Dm.astype(f32)
+
     for t in (range(T - 1, -1, -1) if inverse else range(T)):
         P = packed[t * tri.tstride:(t + 1) * tri.tstride]
         iperm = np.arange(D) if t % 2 == 0 else D - 1 - np.arange(D)
-        acc = np.full((n, ncols), np.nan, f32)                     # tensor memory: unwritten columns must never be read
+        acc = np.full((n, 512), np.nan, f32)
+        scratch = [np.zeros((n, int(m[TL.TRI_KX_TOTAL])), f32)] + [np.zeros((n, int(m[TL.TRI_KH_TOTAL])), f32) for _ in range(L)]
+        cp = int(m[TL.TRI_CHUNK_OFF])                                # running pointer into the chunk stream
+
+        def take_b(N, K):
+            nonlocal cp
+            hi = P[cp:cp + N * K].reshape(K // 4, N, 4).transpose(1, 0, 2).reshape(N, K)
+            lo = P[cp + N * K:cp + 2 * N * K].reshape(K // 4, N, 4).transpose(1, 0, 2).reshape(N, K)
+            cp += 2 * N * K
+            return hi, lo
+
         for bi in range(NB):
-            k0, nst, U, W, hc, doff, dn, c0, n_urgent, n_chunks = (int(q) for q in blocks[bi])
-            E = max(U - 4, 0)
-            row = 4 + (4 if E else 0)
+            k0, nst, NR, W, Kp, win, wc, oc, doff, dn, ks, upd_N, upd_dcol, out_N, out_dcol, flags = (int(q) for q in blocks[bi])
+            b0w, nbw, Wp, Op, col_out, Kh, Kx, _ = (int(q) for q in wins[win])
+            E = NR - 4
+            nrv, q1 = (1 if NR == 4 else 2), (2 * NR + 3) // 4
+            first_block = (win == 0 and bi == 0)
             a = [None] + [np.zeros((n, W), f32) for _ in range(L)]
             o = np.zeros((n, 2 * G), f32)
-            if bi > 0:
+            if not first_block:
                 for l in range(1, L + 1):
-                    a[l] = acc[:, (l - 1) * Hc + hc:(l - 1) * Hc + hc + W].copy()
-                o = acc[:, col_out + 2 * k0:col_out + 2 * k0 + 2 * G].copy()
-                assert np.isfinite(o[:, :2 * nst]).all() and all(np.isfinite(a[l]).all() for l in range(1, L + 1))
+                    a[l] = acc[:, (l - 1) * Wp + wc:(l - 1) * Wp + wc + W].copy()
+                o = acc[:, col_out + oc:col_out + oc + 2 * G].copy()
+                assert np.isfinite(o[:, :2 * nst]).all() and all(np.isfinite(a[l]).all() for l in range(1, L + 1)), (t, bi)
                 o = np.nan_to_num(o)
             xb = np.zeros((n, G), f32)
-            NR = 4 + E
-            nrv = 1 if NR == 4 else 2
-            q1 = (2 * NR + 3) // 4
             p = doff
 
             def take(nf4):
@@ -248,10 +266,15 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
                         s0, s1 = 4 * c + 2 * pp, 4 * c + 2 * pp + 1
                         shift = shift + w4[0] * a[L][:, s0] + w4[1] * a[L][:, s1]
                         sraw = sraw + w4[2] * a[L][:, s0] + w4[3] * a[L][:, s1]
-                    if E:
+                    if E == 1:
                         w4 = take(1)
                         shift = shift + w4[0] * a[L][:, 4 * G + c]
                         sraw = sraw + w4[1] * a[L][:, 4 * G + c]
+                    elif E == 2:
+                        w4 = take(1)
+                        e0, e1 = 4 * G + 2 * c, 4 * G + 2 * c + 1
+                        shift = shift + w4[0] * a[L][:, e0] + w4[1] * a[L][:, e1]
+                        sraw = sraw + w4[2] * a[L][:, e0] + w4[3] * a[L][:, e1]
                 if j < nst:
                     feat = iperm[k0 + j]
                     ls = sraw / (f32(1) + np.abs(sraw / log_slope))
@@ -264,8 +287,7 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
                         v[:, feat] = xk * np.exp(ls) + shift
                         ladj += ls
                     xb[:, j] = xk
-                own = [ML.tri_slot(j, s_, G, E) for s_ in range(NR)]
-                # layer 1
+                own = [TL.tri_slot(j, s_, G, E) for s_ in range(NR)]
                 pre = a[1][:, own] + take(nrv)[None, :NR]
                 for q in range(j // 2 + 1):
                     blk = take(q1)[:2 * NR].reshape(NR, 2)
@@ -278,31 +300,48 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
                         for pp in range(2):
                             for h in range(2):
                                 pre = pre + a[l - 1][:, 4 * c + 2 * pp + h][:, None] * blk[None, pp, :, h]
-                        if E:
+                        if E == 1:
                             blk = take(2)[:NR]
                             pre = pre + a[l - 1][:, 4 * G + c][:, None] * blk[None, :]
+                        elif E == 2:
+                            blk = take(3).reshape(NR, 2)
+                            pre = pre + a[l - 1][:, 4 * G + 2 * c][:, None] * blk[None, :, 0] + a[l - 1][:, 4 * G + 2 * c + 1][:, None] * blk[None, :, 1]
                     a[l][:, own] = np.maximum(pre + a[l - 1][:, own], 0)
-            take(NR + 2)
             assert p == doff + dn
-            for ci in range(c0, c0 + n_chunks):
-                a_src, ks0, nks, N, dcol, first, off, flags = (int(q) for q in chunks[ci])
-                if a_src == 0:
-                    A = np.zeros((n, 8), f32); A[:, :G] = xb
-                else:
-                    Ap = np.zeros((n, (W + 7) // 8 * 8), f32); Ap[:, :W] = a[a_src]
-                    A = Ap[:, 8 * ks0:8 * (ks0 + nks)]
-                img = P[off:off + nks * 2 * N * 4].reshape(nks * 2, N, 4)
-                Bh = img.transpose(1, 0, 2).reshape(N, nks * 8)
-                img = P[off + nks * 2 * N * 4:off + 2 * nks * 2 * N * 4].reshape(nks * 2, N, 4)
-                Bl = img.transpose(1, 0, 2).reshape(N, nks * 8)
-                Ah = trunc(A)
-                Al = A - Ah
-                Dm = Ah.astype(np.float64) @ Bh.T.astype(np.float64)
-                if passes > 1:
-                    Dm += Al.astype(np.float64) @ Bh.T.astype(np.float64) + Ah.astype(np.float64) @ Bl.T.astype(np.float64)
-                Dm = Dm.astype(f32)
-                if first:
-                    acc[:, dcol:dcol + N] = Dm
-                else:
-                    acc[:, dcol:dcol + N] += Dm
+            # the block's activations: A tiles (K padded to a multiple of 8) and, when another window follows, the scratch area
+            Ax = np.zeros((n, 8), f32); Ax[:, :G] = xb
+            At = [Ax]
+            for l in range(1, L + 1):
+                Ap = np.zeros((n, Kp), f32); Ap[:, :W] = a[l]
+                At.append(Ap)
+            if NW > 1:
+                scratch[0][:, 8 * bi:8 * bi + 8] = Ax
+                for l in range(1, L + 1):
+                    scratch[l][:, ks:ks + Kp] = At[l]
+            if not (flags & 1):
+                first = first_block
+                for op in (1, 2, 3, 4):
+                    N, dcol = (upd_N, (op - 1) * Wp + upd_dcol) if op < 4 else (out_N, col_out + out_dcol)
+                    A = At[op - 1]
+                    Bh, Bl = take_b(N, A.shape[1])
+                    Dm = mma(A, Bh, Bl)
+                    if first:
+                        acc[:, dcol:dcol + N] = Dm
+                    else:
+                        acc[:, dcol:dcol + N] += Dm
+            elif not (flags & 2):
+                nb0, nnb, nWp, nOp, ncol_out, nKh, nKx, _ = (int(q) for q in wins[win + 1])
+                for op in (1, 2, 3, 4):
+                    ktot = nKx if op == 1 else nKh
+                    N, dcol = (nWp, (op - 1) * nWp) if op < 4 else (nOp, ncol_out)
+                    for k_ in range(0, ktot, KC):
+                        ke = min(KC, ktot - k_)
+                        A = scratch[op - 1][:, k_:k_ + ke]
+                        Bh, Bl = take_b(N, ke)
+                        Dm = mma(A, Bh, Bl)
+                        if k_ == 0:
+                            acc[:, dcol:dcol + N] = Dm
+                        else:
+                            acc[:, dcol:dcol + N] += Dm
+        assert cp == tri.tstride, (cp, tri.tstride)
     return v, ladj

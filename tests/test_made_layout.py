@@ -68,7 +68,8 @@ def test_one_dim_rejected():
         ML.build_layout(1, 32, 3, 3, ML.KIND_AFFINE)
 
 
-@pytest.mark.parametrize("preset,d", [("maf3", 10), ("maf6", 32), ("maf3", 21), ("maf3", 16), ("maf3", 33), ("maf3", 36), ("maf3", 8)])
+@pytest.mark.parametrize("preset,d", [("maf3", 10), ("maf6", 32), ("maf3", 21), ("maf3", 16), ("maf3", 33), ("maf3", 36), ("maf3", 8),
+                                      ("maf3", 25), ("maf3", 50), ("maf3", 12), ("maf3", 100)])
 def test_block_triangular_layout_matches_oracle(preset, d):
     """made_layout.build_tri (image + tables of csrc/flow_tri.cu) walked by a numpy emulation of the kernel's schedule
     -- right-looking block updates with hi/lo TF32 operands, in-block fp32 substitution -- reproduces the oracle's
@@ -81,9 +82,10 @@ def test_block_triangular_layout_matches_oracle(preset, d):
             p_.mul_(1.3)
     raw = _raw(flow)
     T = int(preset[3:])
-    assert ML.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE)
-    tri = ML.build_tri(d, F.hidden_width(d), 3, T, ML.KIND_AFFINE)
-    assert tri.smem_bytes <= ML.TRI_SMEM_BUDGET and tri.meta[ML.TRI_NCOLS] <= 512
+    from pocomc_b200 import tri_layout as TL
+    assert TL.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE)
+    tri = TL.build_tri(d, F.hidden_width(d), 3, T, ML.KIND_AFFINE)
+    assert tri.smem_bytes <= TL.TRI_SMEM_BUDGET and tri.meta[TL.TRI_NCOLS] <= 512
     packed = pack_tri(tri, raw)
     x = torch.randn(37, d)
     with torch.no_grad():
@@ -101,6 +103,11 @@ def test_block_triangular_layout_matches_oracle(preset, d):
 
 
 def test_block_triangular_support_matrix():
-    sup = {d: ML.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE) for d in (2, 6, 10, 21, 32, 50, 100)}
-    assert sup[10] and sup[21] and sup[32] and not sup[2] and not sup[50] and not sup[100]
-    assert not ML.tri_supported(10, 32, 3, ML.KIND_RQS)
+    from pocomc_b200 import tri_layout as TL
+    sup = {d: TL.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE) for d in (2, 6, 10, 21, 32, 50, 100, 200)}
+    assert sup[10] and sup[21] and sup[32] and sup[50] and sup[100] and sup[200] and not sup[2] and not sup[6]
+    assert not TL.tri_supported(10, 32, 3, ML.KIND_RQS)
+    # one window (no scratch area) up to 36 dimensions, several windows beyond
+    assert TL.build_tri(32, 128, 3, 1, ML.KIND_AFFINE).ws_floats == 0
+    big = TL.build_tri(200, 1024, 3, 1, ML.KIND_AFFINE)
+    assert big.meta[TL.TRI_NW] >= 6 and big.ws_floats > 0 and big.smem_bytes <= TL.TRI_SMEM_BUDGET

@@ -12,6 +12,7 @@ f = pc.Flow(d, preset)
 with torch.no_grad():
     f.flow.raw.mul_(1.2)
 m = f.flow
+IT = int(os.environ.get("ITER", 20))
 for n in [int(v) for v in os.environ.get("N", "10000").split(",")]:
     x = torch.randn(n, d, device="cuda")
     ref, lref = torch.empty_like(x), torch.empty(n, device="cuda")
@@ -26,16 +27,16 @@ for n in [int(v) for v in os.environ.get("N", "10000").split(",")]:
             torch.cuda.synchronize()
             rec[f"maxdiff_p{passes}"] = float((out - ref).abs().max())
             rec[f"maxdiff_ladj_p{passes}"] = float((ladj - lref).abs().max())
-            for _ in range(3): m.sweep_tri_into(x, out, ladj, inverse=inverse, passes=passes)
+            for _ in range(min(3, IT)): m.sweep_tri_into(x, out, ladj, inverse=inverse, passes=passes)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(20): m.sweep_tri_into(x, out, ladj, inverse=inverse, passes=passes)
+            for _ in range(IT): m.sweep_tri_into(x, out, ladj, inverse=inverse, passes=passes)
             e1.record(); torch.cuda.synchronize()
-            rec[f"tri_us_p{passes}"] = e0.elapsed_time(e1) / 20 * 1e3
+            rec[f"tri_us_p{passes}"] = e0.elapsed_time(e1) / IT * 1e3
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(3): m.sweep_into(x, ref, lref, inverse=inverse)
+        for _ in range(min(3, IT)): m.sweep_into(x, ref, lref, inverse=inverse)
         e0.record()
-        for _ in range(20): m.sweep_into(x, ref, lref, inverse=inverse)
+        for _ in range(IT): m.sweep_into(x, ref, lref, inverse=inverse)
         e1.record(); torch.cuda.synchronize()
-        rec["ffma_us"] = e0.elapsed_time(e1) / 20 * 1e3
+        rec["ffma_us"] = e0.elapsed_time(e1) / IT * 1e3
         print(json.dumps(rec), flush=True)
