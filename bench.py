@@ -262,7 +262,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # roofline helpers
 # ---------------------------------------------------------------------------------------------
-def committed_traffic(kernel_name):
+def committed_traffic(kernel_name, n, n_dim):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full captures (profiles/roofline_traffic.json:
     kernel-name regex -> bytes, source file).  None (and a note) when no committed capture matches the kernel that ran."""
     try:
@@ -270,9 +270,9 @@ def committed_traffic(kernel_name):
     except OSError:
         return None, "profiles/roofline_traffic.json missing"
     for entry in table:
-        if re.search(entry["kernel"], kernel_name):
+        if re.search(entry["kernel"], kernel_name) and int(entry.get("n_dim", n_dim)) == n_dim and int(entry.get("n", n)) == n:
             return float(entry["dram_bytes_per_launch"]), entry["source"]
-    return None, f"no committed ncu capture for kernel {kernel_name!r}"
+    return None, f"no committed ncu capture of {kernel_name!r} at n={n}, n_dim={n_dim}"
 
 
 def tri_issued_flop(tri_meta, n):
@@ -438,19 +438,19 @@ def run_b200(args):
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     mod = flow.flow
     if mod.tri_available() and config.inverse_path == "tri":
-        kernel = "made_sweep_tri_kernel<true, 4> (flow inverse: tcgen05 block-triangular sweep)"
+        kernel = "made_sweep_tri_kernel<true> (flow inverse: windowed tcgen05 block-triangular sweep)"
         issued = tri_issued_flop(mod._tri_meta_host, n_local)
-        note = ("tcgen05.mma kind::tf32 right-looking updates (3xTF32 split) + in-block fp32 substitution; achieved = issued MMA FLOP per "
-                "launch (sum over update chunks of 2*128*N*8*k-steps*3 passes per 128-particle tile) / launch time; latency-bound at one "
-                "128-particle tile per SM (TMEM holds one tile's accumulators): per block of 4 order positions one mbarrier round trip "
-                "through the tensor pipe (~1 us) + ~1000 warp instructions of substitution (DESIGN.md section 4)")
+        note = ("tcgen05.mma kind::tf32 (3xTF32 split): right-looking updates inside a tensor-memory window, left-looking window "
+                "initialisation from the fp32 scratch area, in-block fp32 substitution; achieved = issued MMA FLOP per launch (2*128*N*K per "
+                "group, 3 passes, per 128-particle tile and transform) / launch time; one 128-particle tile per SM (TMEM holds one tile's "
+                "window) -- the substitution chain, the operand stream from L2 and the tensor pipe take turns (DESIGN.md section 4)")
     else:
         kernel = "made_sweep_stream_kernel<Affine> (flow inverse: fp32-FMA degree-ordered sweep)" if ML.stream_supported(D, lay.n_hidden, lay.n_layers, lay.kind) \
             else "made_sweep_kernel<Affine> (flow inverse: fp32-FMA sweep, weights through L2)"
         issued = useful
         note = "fp32 FMA sweep on CUDA cores (no tensor-core path for this flow shape yet); achieved = useful FLOP (2*nnz(masks)) / launch time"
     achieved_tf = issued / (sweep_ms * 1e-3) / 1e12
-    traffic, traffic_src = committed_traffic(kernel)
+    traffic, traffic_src = committed_traffic(kernel, n_local, D)
     roofline = dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf,
                     traffic=traffic, traffic_source=traffic_src, kernel=kernel,
                     peak_source="MEASURED_PEAKS.json bf16 burst" if peaks else "fallback 1.59 PFLOP/s",

@@ -24,7 +24,8 @@ inverse_path
 forward_path
     ``"tc"`` (default): ``Flow.forward`` / ``log_prob`` without a graph run on the tcgen05 dense kernel
     (csrc/flow_tc.cu, 3xTF32 split = fp32 fidelity) when the flow is affine with H <= 128 and the batch
-    has at least ``tc_min_rows`` rows; ``"sweep"``: always the degree-ordered sweep kernel.
+    has at least ``tc_min_rows`` rows, and on the block-triangular tcgen05 sweep (csrc/flow_tri.cu) when it is affine and
+    wider (H = 256 / 512 / 1024); ``"sweep"``: always the degree-ordered fp32-FMA sweep kernel.
 fit_path
     ``"graph"`` (default): every optimiser step of ``Flow.fit`` is one CUDA-graph launch (batch gather,
     autograd forward/backward, fused clip + AdamW kernel, loss accumulation) -- same arithmetic and RNG

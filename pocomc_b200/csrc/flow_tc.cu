@@ -14,8 +14,8 @@
 //     issued by a producer thread; an issuer thread feeds the tensor core; both are decoupled from the
 //     128 epilogue threads by mbarriers only (no __syncthreads in the steady state);
 //   * fp32 fidelity (the reference flow is fp32; parity bar 2e-5): every product is evaluated as
-//     a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with hi = value truncated to TF32 (the tensor core truncates,
-//     measured in tests/tc_probe.cu) and lo = value - hi (exact), fp32 accumulation in TMEM.
+//     a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with hi = value rounded to TF32 (the tensor core itself truncates,
+//     measured in tests/tc_probe.cu: a truncated hi biases every product) and lo = value - hi (exact), fp32 accumulation in TMEM.
 //     passes = 1 issues only the hi*hi term (plain TF32, for throughput experiments).
 //
 //   * biases ride on the tensor core too: the last weight chunk of every layer carries one extra k-step
@@ -296,7 +296,7 @@ made_forward_tc_kernel(const TcParams p) {
   if (warp == 4) tmem_dealloc<512>(tm);
 }
 
-// hi/lo aware pack: gather[i] >= 0 -> hi(raw[g]); gather[i] <= -2 -> lo(raw[-g-2]); -1 -> 0;
+// hi/lo aware pack: gather[i] >= 0 -> hi(raw[g]) = nearest TF32; gather[i] <= -2 -> lo(raw[-g-2]) = nearest TF32 of the rest; -1 -> 0;
 // entries flagged with bit 30 (biases) are copied unsplit
 __global__ void pack_tc_kernel(const float* __restrict__ raw, const int* __restrict__ gather, float* __restrict__ packed, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -305,10 +305,10 @@ __global__ void pack_tc_kernel(const float* __restrict__ raw, const int* __restr
     float v = 0.f;
     if (g >= 0) {
       if (g & (1 << 30)) v = raw[g & ~(1 << 30)];
-      else v = __uint_as_float(__float_as_uint(raw[g]) & 0xffffe000u);
+      else v = tf32_round(raw[g]);
     } else if (g <= -2) {
       const float x = raw[-g - 2];
-      v = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+      v = tf32_round(x - tf32_round(x));
     }
     packed[i] = v;
   }

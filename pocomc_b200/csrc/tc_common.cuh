@@ -168,9 +168,14 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// fp32 -> (hi, lo) with hi a valid TF32 value (13 low mantissa bits clear) and hi + lo == x exactly
+// fp32 -> nearest TF32 value (ties away from zero, what cvt.rna.tf32.f32 returns), as two integer operations
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// fp32 -> (hi, lo) with hi a valid TF32 value (13 low mantissa bits clear) and hi + lo == x exactly.  hi is ROUNDED to
+// nearest: |lo| <= 2^-12 |x| keeps 12 significant bits, of which the tensor core (which truncates its fp32 operands to TF32)
+// drops at most one -- a 2^-24 relative error -- and the rounding error of hi has no preferred sign.  With a truncated hi
+// the 3-pass product was biased by up to 2^-21 per factor, which the 24 chained layers of a maf6 flow summed to ~3e-5.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  hi = tf32_round(x);
   lo = x - hi;
 }
 

