@@ -138,6 +138,73 @@ class MaskedAutoregressiveFlow(nn.Module):
         self._tri_key = None
         self._tri_ws = None
 
+    # -- the inner plugin seam: a ready ``zuko.flows.Flow`` (pocomc/flow.py:87-88) -------------------------------------
+    @staticmethod
+    def _zuko_linears(hyper):
+        """(linear layer, wrapped in a residual block?) of a zuko MaskedMLP, in evaluation order"""
+        out = []
+        for layer in hyper.children():
+            lin = getattr(layer, "f", layer)           # Residual(f) wraps the hidden -> hidden layers
+            if hasattr(lin, "weight") and hasattr(lin, "mask"):
+                out.append((lin, lin is not layer))
+            elif type(layer).__name__ not in ("ReLU",):
+                raise ValueError(f"unsupported hyper-network layer {type(layer).__name__}: the kernels are built for ReLU masked MLPs")
+        return out
+
+    @classmethod
+    def from_zuko(cls, flow):
+        """Adopt a user-built ``zuko.flows.MAF`` / ``NSF`` (what pocomc's ``Flow(n_dim, flow=<zuko flow>)`` accepts): read
+        its structure, check that it is one the kernels implement -- alternating feature order, 3 residual hidden layers
+        of equal width, ReLU, affine or 8..-bin spline heads, zuko's own hidden-unit degree assignment (the masks are
+        compared entry by entry) -- and copy its parameters into the flat blob.  Anything else raises ValueError."""
+        ts = getattr(flow, "transform", None)
+        ts = list(ts) if isinstance(ts, (nn.ModuleList, list, tuple)) else ([ts] if ts is not None else [])
+        if not ts or not all(hasattr(t, "hyper") and hasattr(t, "order") for t in ts):
+            raise ValueError("not a zuko masked-autoregressive flow (no .transform[i].hyper / .order)")
+        features = int(ts[0].order.numel())
+        lin0 = cls._zuko_linears(ts[0].hyper)
+        if len(lin0) != 4:
+            raise ValueError(f"the kernels are built for 3 hidden layers, this flow has {len(lin0) - 1}")
+        hidden = int(lin0[0][0].weight.shape[0])
+        total = int(lin0[-1][0].weight.shape[0]) // features
+        if total == 2:
+            kind, bins = ML.KIND_AFFINE, 8
+        elif total >= 5 and (total + 1) % 3 == 0:
+            kind, bins = ML.KIND_RQS, (total + 1) // 3
+        else:
+            raise ValueError(f"{total} parameters per feature: neither an affine (2) nor a spline (3 bins - 1) head")
+        if kind == ML.KIND_RQS and bins != 8:
+            raise ValueError("spline kernels are built for bins = 8 (zuko.flows.NSF default, pocomc/flow.py:65-86)")
+        self = cls(features, hidden, 3, len(ts), kind, bins)
+        lay, chunks = self.layout, []
+        for t, tr in enumerate(ts):
+            want = np.arange(features) if t % 2 == 0 else features - 1 - np.arange(features)
+            if not np.array_equal(tr.order.detach().cpu().numpy(), want) or int(getattr(tr, "passes", features)) != features:
+                raise ValueError("feature orders must alternate (zuko randperm=False) with fully autoregressive transforms (passes = features)")
+            lins = cls._zuko_linears(tr.hyper)
+            if len(lins) != 4 or [r for _, r in lins] != [False, True, True, False]:
+                raise ValueError("the kernels are built for hidden_features=[H]*3 with residual=True (pocomc/flow.py:55-86)")
+            for (lin, _), mask, shape in zip(lins, ML.masks(lay, t), lay.raw_sizes[0::2]):
+                if tuple(lin.weight.shape) != tuple(shape) or lin.bias is None:
+                    raise ValueError(f"layer shape {tuple(lin.weight.shape)} does not match hidden_features=[{hidden}]*3")
+                if not np.array_equal(lin.mask.detach().cpu().numpy().astype(bool), mask):
+                    raise ValueError("hyper-network masks differ from zuko's MaskedMLP degree assignment: cannot adopt this flow")
+                chunks += [lin.weight.detach().reshape(-1), lin.bias.detach().reshape(-1)]
+        with torch.no_grad():
+            self.raw.copy_(torch.cat([c.to(torch.float32).cpu() for c in chunks]))
+        return self
+
+    @torch.no_grad()
+    def export_to(self, flow):
+        """write the (trained) parameters back into the zuko module they were adopted from"""
+        off, raw = 0, self.raw.detach().cpu()
+        for tr in flow.transform:
+            for lin, _ in self._zuko_linears(tr.hyper):
+                for prm in (lin.weight, lin.bias):
+                    prm.copy_(raw[off:off + prm.numel()].view_as(prm))
+                    off += prm.numel()
+        assert off == raw.numel()
+
     # -- plumbing ---------------------------------------------------------------------------
     def __getstate__(self):
         st = self.__dict__.copy()
@@ -728,9 +795,14 @@ class Flow:
             self.flow = MaskedAutoregressiveFlow(n_dim, n_hidden, 3, transforms, kind)
         elif isinstance(flow, MaskedAutoregressiveFlow):
             self.flow = flow
+        elif isinstance(flow, nn.Module) and hasattr(flow, "transform") and hasattr(flow, "base"):
+            # the reference's inner plugin seam (flow.py:87-88): a ready zuko.flows.Flow.  Its parameters are copied into the
+            # flat blob the kernels read; ``fit`` writes the trained values back into the user's module.
+            self.flow = MaskedAutoregressiveFlow.from_zuko(flow)
+            self.foreign = flow
         else:
             raise ValueError('Invalid flow type. Choose from: maf3, maf6, maf12, nsf3, nsf6, nsf12, '
-                             'or provide a MaskedAutoregressiveFlow object.')
+                             'or provide a zuko.flows.Flow (MAF / NSF) object.')
         if torch.cuda.is_available():
             self.flow.ensure_cuda()
 
@@ -884,6 +956,8 @@ class Flow:
             print()
             print('Time total:     %5.2f sec' % total)
             print('Time per epoch: %5.2f sec' % (total / epochs))
+        if getattr(self, "foreign", None) is not None:
+            module.export_to(self.foreign)        # the user's zuko module sees the trained parameters, like flow.py:268-370
         return history
 
 

@@ -64,3 +64,36 @@ def test_plateau_lr_mirrors_torch_scheduler():
         mine.step(float(v))
         assert abs(opt.param_groups[0]['lr'] - mine.lr) < 1e-15
     assert mine.lr < 1e-3
+
+
+@pytest.mark.parametrize("kind,d,h", [("maf", 5, 48), ("nsf", 6, 40)])
+def test_adopts_a_ready_zuko_flow(kind, d, h):
+    """pocomc/flow.py:87-88: ``Flow(n_dim, flow=<zuko.flows.Flow>)``.  The module's parameters land in the flat blob in
+    module order, the structure (width, transforms, head) is read off the module, and the trained blob can be written back."""
+    import zuko
+    torch.manual_seed(4)
+    kw = dict(transforms=4, hidden_features=[h] * 3, residual=True)
+    user = zuko.flows.MAF(d, **kw) if kind == "maf" else zuko.flows.NSF(features=d, bins=8, **kw)
+    mine = Flow(d, user)
+    lay = mine.flow.layout
+    assert (lay.n_dim, lay.n_hidden, lay.n_layers, lay.n_transforms) == (d, h, 3, 4)
+    flat = torch.cat([p.detach().reshape(-1) for p in user.parameters()])
+    assert torch.equal(flat, mine.flow.raw.detach().cpu())
+    with torch.no_grad():
+        mine.flow.raw.add_(1.0)
+    mine.flow.export_to(user)
+    assert torch.equal(torch.cat([p.detach().reshape(-1) for p in user.parameters()]), flat + 1.0)
+
+
+def test_rejects_zuko_flows_the_kernels_do_not_implement():
+    import zuko
+    with pytest.raises(ValueError, match="residual"):
+        Flow(4, zuko.flows.MAF(4, transforms=2, hidden_features=[32] * 3, residual=False))
+    with pytest.raises(ValueError, match="3 hidden layers"):
+        Flow(4, zuko.flows.MAF(4, transforms=2, hidden_features=[32] * 2, residual=True))
+    with pytest.raises(ValueError, match="orders must alternate"):
+        Flow(4, zuko.flows.MAF(4, transforms=2, hidden_features=[32] * 3, residual=True, randperm=True))
+    with pytest.raises(ValueError, match="bins = 8"):
+        Flow(4, zuko.flows.NSF(features=4, bins=4, transforms=2, hidden_features=[32] * 3, residual=True))
+    with pytest.raises(ValueError):
+        Flow(4, torch.nn.Linear(4, 4))

@@ -321,3 +321,35 @@ def test_tensor_core_block_triangular_sweep_matches_oracle(preset, d, n):
         config.inverse_path = old
     np.testing.assert_allclose(xi.numpy(), xs.numpy(), **tol)
     np.testing.assert_allclose(li.numpy(), ls.numpy(), **tol)
+
+
+@pytest.mark.parametrize("kind,d,h", [("maf", 12, 64), ("nsf", 6, 40)])
+def test_adopted_zuko_flow_matches_its_own_arithmetic(kind, d, h):
+    """pocomc/flow.py:87-88, the inner plugin seam: a user-built zuko flow handed to Flow runs on the kernels and returns
+    what the module itself computes (forward, inverse, log_prob); fit() writes the trained parameters back into it."""
+    import zuko
+    from pocomc_b200.flow import Flow
+    torch.manual_seed(21)
+    kw = dict(transforms=3, hidden_features=[h] * 3, residual=True)
+    user = zuko.flows.MAF(d, **kw) if kind == "maf" else zuko.flows.NSF(features=d, bins=8, **kw)
+    f = Flow(d, user)
+    x = torch.randn(300, d)
+    with torch.no_grad():
+        z_ref, l_ref = user().transform.call_and_ladj(x)
+        xi_ref, li_ref = user().transform.inv.call_and_ladj(z_ref)
+        lp_ref = user().log_prob(x)
+        z, l = f.forward(x)
+        xi, li = f.inverse(z_ref)
+        lp = f.log_prob(x)
+    base = 5e-5 if kind == "maf" else 5e-4
+    np.testing.assert_allclose(z.numpy(), z_ref.numpy(), **_bar(z_ref, base))
+    np.testing.assert_allclose(l.numpy(), l_ref.numpy(), **_bar(l_ref, base))
+    np.testing.assert_allclose(xi.numpy(), xi_ref.numpy(), **_bar(xi_ref, base))
+    np.testing.assert_allclose(li.numpy(), li_ref.numpy(), **_bar(li_ref, base))
+    np.testing.assert_allclose(lp.numpy(), lp_ref.numpy(), **_bar(lp_ref, base))
+    before = torch.cat([p.detach().reshape(-1) for p in user.parameters()]).clone()
+    f.fit(x, epochs=3, batch_size=100)
+    after = torch.cat([p.detach().reshape(-1) for p in user.parameters()])
+    assert torch.equal(after, f.flow.raw.detach().cpu()) and not torch.equal(after, before)
+    with torch.no_grad():
+        np.testing.assert_allclose(f.log_prob(x).numpy(), user().log_prob(x).numpy(), **_bar(lp_ref, 10 * base))
