@@ -232,6 +232,34 @@ int pmc_mh_accept_finalize(int32_t kind, double beta, double nu, float* pos32, d
                            double* ctl, uint32_t* ticket, int32_t mean_mode, int32_t n_steps,
                            int32_t n_max, int64_t n, int32_t d, pmc_stream_t stream);
 
+/* ---- peer-memory exchange of a particle-sharded run (one process per GPU, all on one NVLink / NVSwitch node) --------
+ * Replaces "all-gather the block partials, then pmc_mcmc_finalize" (mcmc.py:152-180 needs the mean acceptance, the mean
+ * of theta and the tracked mean log-density over ALL particles every step) by stores into peer memory from inside the
+ * accept kernel.  pmc_comm_create allocates this rank's exchange buffer (2 x capacity_doubles + flags) on the current
+ * device and returns its CUDA IPC handle (PMC_COMM_HANDLE_BYTES bytes) -- exchange the handles of all ranks with any
+ * host-side collective (torch.distributed.all_gather) -- pmc_comm_connect opens the peers' buffers; `block_off`
+ * [world + 1] = first 256-row block of every rank in global particle order (pmc_comm_set_blocks changes it later).
+ * pmc_comm_error: 1 after a peer failed to publish within 20 s (the kernel then sets the stop flag), -1 bad context. */
+#define PMC_COMM_MAX_RANKS 8
+#define PMC_COMM_HANDLE_BYTES 64
+int pmc_comm_create(int32_t rank, int32_t world, int64_t capacity_doubles, void** comm_out, unsigned char* handle64);
+int pmc_comm_connect(void* comm, const unsigned char* handles, const int32_t* block_off);
+int pmc_comm_set_blocks(void* comm, const int32_t* block_off, pmc_stream_t stream);
+int pmc_comm_error(void* comm);
+int pmc_comm_destroy(void* comm);
+/* pmc_mh_accept_finalize for a sharded run, ONE launch per MCMC step and rank: Metropolis update of this rank's n rows,
+ * block partials, and in the block that finishes last: push the partials into every peer's buffer over NVLink, publish
+ * an epoch flag, wait for all peers, adapt the controller from the rank-ordered partials of all n_global particles
+ * (mean_mode 0: the GPU-count independent f64 block sums).  Every rank must launch it for every step.               */
+int pmc_mh_accept_finalize_p2p(int32_t kind, double beta, double nu, float* pos32, double* u, double* x,
+                               double* logdetj, double* logl, double* logp, float* logdetj_flow,
+                               const double* prop64, const double* u_p, const double* x_p,
+                               const double* logdetj_p, const double* logl_p, const double* logp_p,
+                               const float* logdetj_flow_p, const double* m_cur, const double* m_prop,
+                               const double* r, const uint8_t* finite, double* alpha_out, double* partials,
+                               double* ctl, uint32_t* ticket, int32_t n_steps, int32_t n_max,
+                               int64_t n, int32_t d, void* comm, int64_t n_global, pmc_stream_t stream);
+
 /* Scalar adaptation + stop rule (mcmc.py:152-180 and the three siblings), on device:
  * reduces `partials` in fixed order, updates ctl (sigma, mu, step, best, cnt, stop, accept...).
  * mean_mode 1 reproduces np.mean(theta f32, axis=0)'s sequential f32 accumulation exactly

@@ -57,6 +57,12 @@ SIGNATURES = {
     "pmc_gather_rows_f64": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "pmc_trim_threshold": (C.c_int, [_P, _I64, _F64, _I32, _P, _P, _P]),
     "pmc_trim_scratch_size": (_I64, [_I64]),
+    "pmc_comm_create": (C.c_int, [_I32, _I32, _I64, _P, _P]),
+    "pmc_comm_connect": (C.c_int, [_P, _P, _P]),
+    "pmc_comm_set_blocks": (C.c_int, [_P, _P, _P]),
+    "pmc_comm_error": (C.c_int, [_P]),
+    "pmc_comm_destroy": (C.c_int, [_P]),
+    "pmc_mh_accept_finalize_p2p": (C.c_int, [_I32, _F64, _F64] + [_P] * 22 + [_I32, _I32, _I64, _I32, _P, _I64, _P]),
     "pmc_lse": (C.c_int, [_P, _I64, _P, _P, _P]),
     "pmc_lse_bootstrap": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
     "pmc_lse_bootstrap_rng": (C.c_int, [_P, _I64, _I64, _U64, _P, _P]),

@@ -35,6 +35,11 @@ fit_kernels
     ``"fused"`` (default): MAF flows with H <= 128 train on the hand-written forward/backward kernels of
     csrc/flow_train.cu (5 launches per optimiser step inside the graph); ``"autograd"``: torch autograd
     over the flat blob (always used for spline flows).
+p2p_exchange
+    True (default): under torch.distributed/NCCL with one GPU per rank the per-MCMC-step reduction of a particle-sharded
+    run (mean acceptance, mean theta, tracked log-density over ALL particles) is exchanged by the accept kernel itself
+    through peer memory over NVLink (csrc/mcmc_ops.cu: mh_accept_kernel<2>, pmc_comm_*); False: NCCL all-gather of the block
+    partials followed by pmc_mcmc_finalize (also what gloo test set-ups with two ranks on one GPU use).
 """
 import os
 
@@ -50,6 +55,7 @@ device_prior = os.environ.get("PMC_B200_DEVICE_PRIOR", "1") == "1"
 device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
 # experimental: under torch.distributed every rank stores only its block of the particle history (pocomc_b200.sharded)
 shard_history = os.environ.get("PMC_B200_SHARD_HISTORY", "0") == "1"
+p2p_exchange = os.environ.get("PMC_B200_P2P", "1") == "1"
 
 
 def set_rng_mode(mode: str):

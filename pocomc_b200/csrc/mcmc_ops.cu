@@ -4,6 +4,7 @@
 // HBM-bound: one warp per particle row, lanes stride the D columns so every
 // global access is a contiguous row segment.
 #include "common.cuh"
+#include <string.h>
 
 namespace pmc {
 
@@ -210,7 +211,35 @@ __device__ __forceinline__ void finalize_body(int kind, double* __restrict__ ctl
 // FUSED: the launch also runs the step's scalar adaptation (finalize_body) in the block that finishes last, and does
 // nothing at all once the controller's stop flag is set -- so a host that queues several steps without reading the
 // controller back cannot run past the reference's stopping point (mcmc.py:170-180).
-template <bool FUSED>
+// MODE 2 (particle-sharded runs, one process per GPU): the last block pushes this rank's block partials straight into
+// every peer's exchange buffer over NVLink (plain stores into peer memory opened through CUDA IPC), publishes an epoch
+// flag, waits for the flags of all peers and then adapts the controller from the rank-ordered partials of ALL ranks --
+// accept, exchange and adaptation are one launch and no collective library call sits between two MCMC steps.
+struct CommDev {
+  double* buf[PMC_COMM_MAX_RANKS];                  // exchange buffer of every rank (own entry: local pointer)
+  unsigned long long* flag[PMC_COMM_MAX_RANKS];     // epoch flags of every rank: flag[p][src] = last epoch src published to p
+  unsigned long long* epoch;                        // this rank's epoch counter (device memory)
+  int* error;                                       // set to 1 when a peer did not show up in time
+  long long capacity;                               // doubles per parity half of a buffer
+  int block_off[PMC_COMM_MAX_RANKS + 1];            // first global block of every rank
+  int rank, world;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
 mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, double* __restrict__ u,
                  double* __restrict__ x, double* __restrict__ logdetj, double* __restrict__ logl,
@@ -221,10 +250,13 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
                  const double* __restrict__ m_cur, const double* __restrict__ m_prop,
                  const double* __restrict__ r, const uint8_t* __restrict__ finite,
                  double* __restrict__ alpha_out, double* __restrict__ partials, long long n, int d,
-                 double* __restrict__ ctl, unsigned int* __restrict__ ticket, int mean_mode, int n_steps, int n_max) {
+                 double* __restrict__ ctl, unsigned int* __restrict__ ticket, int mean_mode, int n_steps, int n_max,
+                 const CommDev* __restrict__ comm, long long n_global) {
+  constexpr bool FUSED = MODE != 0;
   extern __shared__ double sh[];  // [8 warps][d] theta sums + [8][4] scalars
-  __shared__ float fin_tile[FUSED ? FIN_TILE_FLOATS + FIN_TILE_COLS : 1];
+  __shared__ float fin_tile[MODE == 1 ? FIN_TILE_FLOATS + FIN_TILE_COLS : 1];
   __shared__ unsigned int is_last;
+  __shared__ unsigned long long epoch_sh;
   if (FUSED && ctl[PMC_CTL_STOP] != 0.0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* th = sh + (size_t)warp * d;
@@ -316,7 +348,33 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    finalize_body(kind, ctl, partials, (int)gridDim.x, pos32, mean_mode, n_steps, n_max, n, d, sh, fin_tile);
+    if (MODE == 1) {
+      finalize_body(kind, ctl, partials, (int)gridDim.x, pos32, mean_mode, n_steps, n_max, n, d, sh, fin_tile);
+    } else {
+      const int world = comm->world, rank = comm->rank, w = d + 4;
+      if (threadIdx.x == 0) epoch_sh = *comm->epoch + 1ull;
+      __syncthreads();
+      const unsigned long long e = epoch_sh;
+      const size_t half = (size_t)(e & 1ull) * (size_t)comm->capacity;           // double buffer by epoch parity
+      const long long mine = (long long)gridDim.x * w;
+      for (int p = 0; p < world; ++p) {
+        double* dst = comm->buf[p] + half + (size_t)comm->block_off[rank] * w;
+        for (long long j = threadIdx.x; j < mine; j += blockDim.x) dst[j] = partials[j];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if ((int)threadIdx.x < world) {
+        st_release_sys(comm->flag[threadIdx.x] + rank, e);
+        const unsigned long long* f = comm->flag[rank] + threadIdx.x;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(f) < e) {
+          if (global_ns() - t0 > 20000000000ull) { *comm->error = 1; break; }   // 20 s: a peer is gone; the host raises
+        }
+      }
+      __syncthreads();
+      finalize_body(kind, ctl, comm->buf[rank] + half, comm->block_off[world], nullptr, 0, n_steps, n_max, n_global, d, sh, fin_tile);
+      if (threadIdx.x == 0) { *comm->epoch = e; if (*comm->error) ctl[PMC_CTL_STOP] = 1.0; }
+    }
     if (threadIdx.x == 0) *ticket = 0u;
   }
 }
@@ -652,9 +710,9 @@ extern "C" int pmc_mh_accept_update(int32_t kind, double beta, double nu, float*
   PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_update: tpCN kinds need the Mahalanobis distances");
   if (n == 0) return 0;
   const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
-  mh_accept_kernel<false><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
+  mh_accept_kernel<0><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
       kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
-      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, nullptr, nullptr, 0, 0, 0);
+      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, nullptr, nullptr, 0, 0, 0, nullptr, 0);
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -676,9 +734,133 @@ extern "C" int pmc_mh_accept_finalize(int32_t kind, double beta, double nu, floa
   PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_finalize: tpCN kinds need the Mahalanobis distances");
   PMC_REQUIRE(n > 0, "pmc_mh_accept_finalize: empty batch");
   const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
-  mh_accept_kernel<true><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
+  mh_accept_kernel<1><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
       kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
-      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, ctl, ticket, mean_mode, n_steps, n_max);
+      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, ctl, ticket, mean_mode, n_steps, n_max,
+      nullptr, 0);
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-memory exchange context (one per process = per GPU)
+// ------------------------------------------------------------------------------------------
+struct pmc_comm {
+  int rank, world, device;
+  long long capacity;                  // doubles per parity half
+  double* buf;                         // [2 * capacity] doubles, then [world] flags, epoch, error -- ONE cudaMalloc (one IPC handle)
+  void* peer_base[PMC_COMM_MAX_RANKS]; // opened peer allocations (nullptr for self / not connected)
+  CommDev host;                        // host image of the device descriptor
+  CommDev* dev;
+  bool connected;
+};
+
+static size_t comm_bytes(long long capacity, int world) { return (size_t)2 * capacity * sizeof(double) + ((size_t)world + 2) * sizeof(unsigned long long); }
+
+extern "C" int pmc_comm_create(int32_t rank, int32_t world, int64_t capacity_doubles, void** comm_out, unsigned char* handle64) {
+  PMC_REQUIRE(comm_out && handle64 && world >= 1 && world <= PMC_COMM_MAX_RANKS && rank >= 0 && rank < world && capacity_doubles > 0,
+              "pmc_comm_create: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == PMC_COMM_HANDLE_BYTES, "IPC handle size");
+  pmc_comm* c = new pmc_comm();
+  c->rank = rank; c->world = world; c->capacity = capacity_doubles; c->connected = false; c->dev = nullptr; c->buf = nullptr;
+  for (int p = 0; p < PMC_COMM_MAX_RANKS; ++p) c->peer_base[p] = nullptr;
+  PMC_TRY(cudaGetDevice(&c->device));
+  const size_t bytes = comm_bytes(capacity_doubles, world);
+  PMC_TRY(cudaMalloc(&c->buf, bytes));
+  PMC_TRY(cudaMemset(c->buf, 0, bytes));
+  PMC_TRY(cudaMalloc(&c->dev, sizeof(CommDev)));
+  PMC_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  PMC_TRY(cudaIpcGetMemHandle(&h, c->buf));
+  memcpy(handle64, &h, sizeof(h));
+  *comm_out = c;
+  return 0;
+}
+
+extern "C" int pmc_comm_connect(void* comm, const unsigned char* handles, const int32_t* block_off) {
+  pmc_comm* c = static_cast<pmc_comm*>(comm);
+  PMC_REQUIRE(c && handles && block_off && !c->connected, "pmc_comm_connect: bad arguments");
+  const size_t flags_off = (size_t)2 * c->capacity * sizeof(double);
+  for (int p = 0; p < c->world; ++p) {
+    unsigned char* base;
+    if (p == c->rank) base = reinterpret_cast<unsigned char*>(c->buf);
+    else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + (size_t)p * PMC_COMM_HANDLE_BYTES, sizeof(h));
+      void* ptr = nullptr;
+      PMC_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_base[p] = ptr;
+      base = static_cast<unsigned char*>(ptr);
+    }
+    c->host.buf[p] = reinterpret_cast<double*>(base);
+    c->host.flag[p] = reinterpret_cast<unsigned long long*>(base + flags_off);
+  }
+  unsigned char* mine = reinterpret_cast<unsigned char*>(c->buf);
+  c->host.epoch = reinterpret_cast<unsigned long long*>(mine + flags_off) + c->world;
+  c->host.error = reinterpret_cast<int*>(reinterpret_cast<unsigned long long*>(mine + flags_off) + c->world + 1);
+  c->host.capacity = c->capacity;
+  c->host.rank = c->rank; c->host.world = c->world;
+  for (int p = 0; p <= c->world; ++p) c->host.block_off[p] = block_off[p];
+  PMC_REQUIRE((long long)block_off[c->world] >= 0, "pmc_comm_connect: bad block offsets");
+  PMC_TRY(cudaMemcpy(c->dev, &c->host, sizeof(CommDev), cudaMemcpyHostToDevice));
+  c->connected = true;
+  return 0;
+}
+
+extern "C" int pmc_comm_set_blocks(void* comm, const int32_t* block_off, pmc_stream_t stream) {
+  pmc_comm* c = static_cast<pmc_comm*>(comm);
+  PMC_REQUIRE(c && c->connected && block_off, "pmc_comm_set_blocks: not connected");
+  for (int p = 0; p <= c->world; ++p) c->host.block_off[p] = block_off[p];
+  PMC_TRY(cudaMemcpyAsync(c->dev, &c->host, sizeof(CommDev), cudaMemcpyHostToDevice, as_stream(stream)));
+  PMC_TRY(cudaStreamSynchronize(as_stream(stream)));
+  return 0;
+}
+
+extern "C" int pmc_comm_error(void* comm) {
+  pmc_comm* c = static_cast<pmc_comm*>(comm);
+  if (!c || !c->connected) return -1;
+  int e = 0;
+  if (cudaMemcpy(&e, c->host.error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return e;
+}
+
+extern "C" int pmc_comm_destroy(void* comm) {
+  pmc_comm* c = static_cast<pmc_comm*>(comm);
+  if (!c) return 0;
+  cudaDeviceSynchronize();
+  for (int p = 0; p < c->world; ++p) if (c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+  if (c->dev) cudaFree(c->dev);
+  if (c->buf) cudaFree(c->buf);
+  delete c;
+  return 0;
+}
+
+extern "C" int pmc_mh_accept_finalize_p2p(int32_t kind, double beta, double nu, float* pos32, double* u, double* x,
+                                          double* logdetj, double* logl, double* logp, float* logdetj_flow,
+                                          const double* prop64, const double* u_p, const double* x_p,
+                                          const double* logdetj_p, const double* logl_p, const double* logp_p,
+                                          const float* logdetj_flow_p, const double* m_cur, const double* m_prop,
+                                          const double* r, const uint8_t* finite, double* alpha_out, double* partials,
+                                          double* ctl, uint32_t* ticket, int32_t n_steps, int32_t n_max,
+                                          int64_t n, int32_t d, void* comm, int64_t n_global, pmc_stream_t stream) {
+  pmc_comm* c = static_cast<pmc_comm*>(comm);
+  PMC_REQUIRE(kind >= 0 && kind <= 3, "pmc_mh_accept_finalize_p2p: bad kind");
+  PMC_REQUIRE(u && x && logdetj && logl && logp && u_p && x_p && logdetj_p && logl_p && logp_p && r && partials && ctl && ticket,
+              "pmc_mh_accept_finalize_p2p: null pointer");
+  PMC_REQUIRE(c && c->connected, "pmc_mh_accept_finalize_p2p: exchange context not connected (pmc_comm_create / pmc_comm_connect)");
+  const bool flow = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_RWM_FLOW);
+  const bool tp = (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_TPCN);
+  PMC_REQUIRE(!flow || (pos32 && prop64 && logdetj_flow && logdetj_flow_p), "pmc_mh_accept_finalize_p2p: flow kinds need theta + flow log-dets");
+  PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_finalize_p2p: tpCN kinds need the Mahalanobis distances");
+  PMC_REQUIRE(n > 0 && n_global >= n, "pmc_mh_accept_finalize_p2p: empty batch");
+  const int* bo = c->host.block_off;
+  PMC_REQUIRE(bo[c->rank + 1] - bo[c->rank] == (int)mh_blocks(n), "pmc_mh_accept_finalize_p2p: block table does not match this rank's batch");
+  PMC_REQUIRE((long long)bo[c->world] * (d + 4) <= c->capacity, "pmc_mh_accept_finalize_p2p: exchange buffer too small");
+  const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
+  mh_accept_kernel<2><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
+      kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
+      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, ctl, ticket, 0, n_steps, n_max,
+      c->dev, n_global);
   PMC_LAUNCH_CHECK();
   return 0;
 }

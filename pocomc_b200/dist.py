@@ -18,7 +18,7 @@ import torch.distributed as td
 
 __all__ = ["init_from_env", "is_active", "world", "shard_range", "shard_counts", "gather_blocks", "allreduce_sum_det",
            "allreduce_sum_int", "broadcast_from_rank0", "barrier", "merge_weight_stats", "combine_weight_stats",
-           "gather_history_scalars", "split_history_index"]
+           "gather_history_scalars", "split_history_index", "peer_exchange", "peer_exchange_error"]
 
 
 def init_from_env(backend: str = None):
@@ -193,3 +193,73 @@ def split_history_index(idx: np.ndarray, n_total: int, counts) -> tuple:
     owner = np.searchsorted(starts, j, side="right") - 1
     local = t * counts[owner] + (j - starts[owner])
     return owner, local
+
+
+# ---------------------------------------------------------------------------------------------
+# peer-memory exchange context (csrc/mcmc_ops.cu: pmc_comm_*): the per-MCMC-step reduction of a sharded run as stores into
+# peer memory over NVLink from inside the accept kernel instead of an NCCL all-gather between two launches
+# ---------------------------------------------------------------------------------------------
+_peer = dict(ptr=None, capacity=0, blocks=None, unavailable=False)
+
+
+def _all_ok(ok: bool) -> bool:
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+    td.all_reduce(t, op=td.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def peer_exchange(block_counts, width: int):
+    """The process-wide exchange context sized for ``sum(block_counts) * width`` doubles, or None when the ranks do not
+    own distinct GPUs of one NCCL job (the gloo test set-up: both ranks on one device) or peer memory cannot be opened --
+    the caller then takes the all-gather path.  Collective: every rank must call it with the same arguments."""
+    from . import _lib, config
+    if not (is_active() and td.get_backend() == "nccl" and config.p2p_exchange) or _peer["unavailable"]:
+        return None
+    rank, ws = world()
+    if ws > 8:
+        return None
+    off = np.concatenate([[0], np.cumsum(np.asarray(block_counts, dtype=np.int64))]).astype(np.int32)
+    need = int(off[-1]) * int(width)
+    lib, C = _lib.load(), _lib.C
+    if _peer["ptr"] is not None and _peer["capacity"] >= need:
+        if _peer["blocks"] != tuple(off.tolist()):
+            _lib.check(lib.pmc_comm_set_blocks(_peer["ptr"], off.ctypes.data_as(C.c_void_p), _lib.stream_ptr()), "pmc_comm_set_blocks")
+            _peer["blocks"] = tuple(off.tolist())
+            td.barrier()                              # nobody publishes into a table a peer has not switched yet
+        return _peer["ptr"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ids = torch.zeros(ws, dtype=torch.int64, device=dev)
+    ids[rank] = torch.cuda.current_device() + 1
+    td.all_reduce(ids)
+    if len(set(ids.tolist())) != ws:                  # two ranks share a GPU
+        _peer["unavailable"] = True
+        return None
+    if _peer["ptr"] is not None:
+        torch.cuda.synchronize()
+        td.barrier()
+        lib.pmc_comm_destroy(_peer["ptr"])
+        _peer.update(ptr=None, capacity=0, blocks=None)
+    capacity = max(need * 2, 1 << 16)
+    ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    ok = lib.pmc_comm_create(rank, ws, capacity, C.byref(ptr), handle) == 0
+    if not _all_ok(ok):
+        _peer["unavailable"] = True
+        return None
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    handles = torch.empty(ws * 64, dtype=torch.uint8, device=dev)
+    td.all_gather_into_tensor(handles, mine)
+    hbuf = (C.c_ubyte * (ws * 64))(*handles.cpu().tolist())
+    ok = lib.pmc_comm_connect(ptr, hbuf, off.ctypes.data_as(C.c_void_p)) == 0
+    if not _all_ok(ok):
+        lib.pmc_comm_destroy(ptr)
+        _peer["unavailable"] = True
+        return None
+    _peer.update(ptr=ptr, capacity=capacity, blocks=tuple(off.tolist()))
+    td.barrier()
+    return ptr
+
+
+def peer_exchange_error() -> bool:
+    """True when a kernel gave up waiting for a peer (the run is then stopped by the controller's stop flag)."""
+    from . import _lib
+    return _peer["ptr"] is not None and _lib.load().pmc_comm_error(_peer["ptr"]) == 1

@@ -145,8 +145,10 @@ class McmcEngine:
         # particle sharding: option_dict['shard'] = (global offset of row 0, global particle count, blocks per rank)
         self.sharded = shard is not None and dist.is_active()
         self.row_offset, self.n_global, self.shard_blocks = (shard if shard is not None else (0, n, None))
+        self._peer = None
         if self.sharded:
             self.mean_mode = 0
+            self._peer = dist.peer_exchange(self.shard_blocks, d + 4)      # None: all-gather path (gloo / shared GPU)
         self.seed = 0
         if self.rng_mode == "device":     # one draw from the host stream keys the Philox counters (same on every rank)
             self.seed = int(option_dict['seed']) if option_dict.get('seed') is not None else int(np.random.randint(0, 2 ** 62))
@@ -295,6 +297,19 @@ class McmcEngine:
                     self.n_steps, self.n_max, n, d)
             self._accept_fused[key]()
             return
+        if self._peer is not None:
+            # sharded, one GPU per rank: accept + exchange of the block partials through peer memory + adaptation, one launch
+            if key not in self._accept_fused:
+                self._accept_fused[key] = _lib.bind(
+                    "pmc_mh_accept_finalize_p2p", self.kind, self.beta, self.nu, _lib.ptr(self.theta), _lib.ptr(self.u),
+                    _lib.ptr(self.x), _lib.ptr(self.logdetj), _lib.ptr(self.logl), _lib.ptr(self.logp), _lib.ptr(self.ldjf),
+                    _lib.ptr(self.prop64), _lib.ptr(self.u_p), _lib.ptr(self.x_p), _lib.ptr(self.ldj_p),
+                    _lib.ptr(self.logl_p), _lib.ptr(self.logp_p), _lib.ptr(self.ldjf_p), _lib.ptr(self.m_cur),
+                    _lib.ptr(self.m_prop), _lib.ptr(self.r), _lib.ptr(self.finite) if calls is None else None,
+                    _lib.ptr(self.alpha), _lib.ptr(self.partials), _lib.ptr(self.ctl), _lib.ptr(self.ticket),
+                    self.n_steps, self.n_max, n, d, self._peer, self.n_global)
+            self._accept_fused[key]()
+            return
         key = calls is None
         if key not in self._accept:
             self._accept[key] = _lib.bind(
@@ -317,6 +332,8 @@ class McmcEngine:
         c = self.ctl_host.numpy()
         self.sigma, self.accept = float(c[CTL_SIGMA]), float(c[CTL_ACCEPT])
         self.step, self.stop = int(c[CTL_STEP]), bool(c[CTL_STOP] != 0.0)
+        if self.stop and self._peer is not None and dist.peer_exchange_error():
+            raise RuntimeError("pocomc_b200: a peer rank did not publish its block partials within 20 s (peer-memory exchange)")
         return c
 
     def reset_controller(self):
@@ -357,8 +374,9 @@ class McmcEngine:
     def loop(self):
         """MCMC steps until the plateau rule or n_max fires (mcmc.py:72-180); state stays on the GPU."""
         device_eval = self.loglike_device is not None and self.logprior_device is not None and not self.have_blobs
-        per_step = (1 if self.rng_mode == "device" else 0) + 1 + (1 if self.use_flow else 0) + 1 + (2 if self.sharded else 1)
-        if device_eval and self.rng_mode == "device" and not self.sharded:
+        fused = not self.sharded or self._peer is not None       # accept + (exchange +) adaptation in one stop-guarded launch
+        per_step = (1 if self.rng_mode == "device" else 0) + 1 + (1 if self.use_flow else 0) + 1 + (1 if fused else 2)
+        if device_eval and self.rng_mode == "device" and fused:
             # nothing of a step needs the host: queue several steps per controller read-back.  Every kernel of a step
             # reads its scalars (sigma, mu, step) from the device controller block; the fused accept + adapt launch is
             # a no-op after the stop flag is set, so the state stops changing exactly where the reference stops.

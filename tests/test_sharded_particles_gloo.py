@@ -147,3 +147,65 @@ def test_sharded_particles_single_process_is_the_plain_history(monkeypatch):
         one.probe(1.0, uss_k=10)
     with pytest.raises(ValueError):
         ShardedParticles(N, D, [N - 1], 0)
+
+
+def _ckpt_worker(rank, world, port, tmp, out):
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import fake_lib
+    from pocomc_b200 import dist
+    from pocomc_b200.particles import Particles
+    from pocomc_b200.sampler import Sampler
+    from pocomc_b200.sharded import ShardedParticles
+    fake_lib.install(_Patch())
+    dist.init_from_env("gloo")
+    logl, u, beta, logz = _history(11)
+    counts = dist.shard_counts(N, world, 256)
+    lo, hi = dist.shard_range(N, rank, world, 256)
+    ok = True
+
+    class _Bare:                                    # carries only what save_state / load_state touch
+        pass
+
+    def sampler_like(store):
+        ns = _Bare()
+        ns.__dict__.update(particles=store, t=T_ITERS, pbar=None, pool=None, distribute=None, calls=123)
+        ns._state_path = types.MethodType(Sampler._state_path, ns)
+        return ns
+
+    # sharded history: every rank writes its own slice (<path>, <path>.rank1) and reads it back
+    mine = ShardedParticles(N, D, counts, rank)
+    _fill(mine, logl, u, beta, logz, slice(lo, hi))
+    path = os.path.join(tmp, "sharded.state")
+    Sampler.save_state(sampler_like(mine), path)
+    ok &= os.path.exists(path) and os.path.exists(path + ".rank1") and not os.path.exists(path + ".temp")
+    fresh = sampler_like(ShardedParticles(N, D, counts, rank))
+    Sampler.load_state(fresh, path)
+    ok &= fresh.t == T_ITERS and len(fresh.particles.past["logl"]) == T_ITERS
+    ok &= all(np.array_equal(a, b) for a, b in zip(fresh.particles.past["u"], mine.past["u"]))
+    ok &= np.array_equal(fresh.particles.get("logl", flat=True), logl.reshape(-1))          # the collective read sees the whole history
+    ok &= bool(np.isclose(fresh.particles.probe(0.4)["ess"], mine.probe(0.4)["ess"], rtol=1e-12))
+    # replicated history: rank 0 alone writes, everybody reads the same file
+    full = Particles(N, D)
+    _fill(full, logl, u, beta, logz)
+    path2 = os.path.join(tmp, "replicated.state")
+    Sampler.save_state(sampler_like(full), path2)
+    ok &= os.path.exists(path2) and not os.path.exists(path2 + ".rank1")
+    again = sampler_like(Particles(N, D))
+    Sampler.load_state(again, path2)
+    ok &= np.array_equal(again.particles.get("u"), full.get("u")) and again.calls == 123
+    out[rank] = bool(ok)
+    td.barrier()
+    td.destroy_process_group()
+
+
+def test_checkpoint_of_sharded_and_replicated_history_world2(tmp_path):
+    """SURVEY 8(f4), sampler.py:1023-1061 under torch.distributed: a sharded history is saved as one file per rank and
+    resumes on the same sharding; a replicated state is written once, by rank 0."""
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_ckpt_worker, args=(world, _free_port(), str(tmp_path), out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)), dict(out)
