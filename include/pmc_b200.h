@@ -232,6 +232,24 @@ int pmc_mh_accept_finalize(int32_t kind, double beta, double nu, float* pos32, d
                            double* ctl, uint32_t* ticket, int32_t mean_mode, int32_t n_steps,
                            int32_t n_max, int64_t n, int32_t d, pmc_stream_t stream);
 
+/* ---- proposal geometry (geometry.py:31-59, student.py:5-85) ------------------------------------------------
+ * The O(n D^2) reductions of Geometry.fit / fit_mvstud over a cloud x [n, d] f64 (row-major), f64, fixed-order two-stage sums
+ * (independent of the SM count).  scratch: pmc_geometry_scratch_size(n, d) doubles.
+ *   pmc_weighted_colsums : out[0..d) = sum_i w_i x_i, out[d] = sum w, out[d+1] = sum w^2, out[d+2] = max_i |x_i - center|^2
+ *                          (np.average / np.mean numerators; w == NULL: unit weights; center == NULL: no max)
+ *   pmc_weighted_scatter : C [d,d] = sum_i w_i (x_i - center)(x_i - center)^T  (np.cov numerators, the EM scatter update)
+ *   pmc_mahalanobis      : delta [n] = (x_i - center)^T P (x_i - center), P = Sigma^-1 [d,d]        (student.py:40)
+ *   pmc_student_weights  : w_i = (nu + dim) / (nu + delta_i); out2 = (sum log w_i, sum w_i); w_out may be NULL (student.py:42-56) */
+int64_t pmc_geometry_scratch_size(int64_t n, int32_t d);
+int pmc_weighted_colsums(const double* x, const double* w, const double* center, int64_t n, int32_t d, double* scratch,
+                         double* out, pmc_stream_t stream);
+int pmc_weighted_scatter(const double* x, const double* w, const double* center, int64_t n, int32_t d, double* scratch,
+                         double* C, pmc_stream_t stream);
+int pmc_mahalanobis(const double* x, const double* center, const double* P, int64_t n, int32_t d, double* delta,
+                    pmc_stream_t stream);
+int pmc_student_weights(const double* delta, int64_t n, double nu, double dim, double* w_out, double* scratch, double* out2,
+                        pmc_stream_t stream);
+
 /* ---- peer-memory exchange of a particle-sharded run (one process per GPU, all on one NVLink / NVSwitch node) --------
  * Replaces "all-gather the block partials, then pmc_mcmc_finalize" (mcmc.py:152-180 needs the mean acceptance, the mean
  * of theta and the tracked mean log-density over ALL particles every step) by stores into peer memory from inside the

@@ -57,6 +57,11 @@ SIGNATURES = {
     "pmc_gather_rows_f64": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "pmc_trim_threshold": (C.c_int, [_P, _I64, _F64, _I32, _P, _P, _P]),
     "pmc_trim_scratch_size": (_I64, [_I64]),
+    "pmc_geometry_scratch_size": (_I64, [_I64, _I32]),
+    "pmc_weighted_colsums": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "pmc_weighted_scatter": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "pmc_mahalanobis": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
+    "pmc_student_weights": (C.c_int, [_P, _I64, _F64, _F64, _P, _P, _P, _P]),
     "pmc_comm_create": (C.c_int, [_I32, _I32, _I64, _P, _P]),
     "pmc_comm_connect": (C.c_int, [_P, _P, _P]),
     "pmc_comm_set_blocks": (C.c_int, [_P, _P, _P]),

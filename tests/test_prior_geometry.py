@@ -60,7 +60,7 @@ def test_device_spec_only_for_norm_and_uniform_factors():
 # ---- geometry -----------------------------------------------------------------------------------
 def test_unweighted_geometry_matches_reference(golden):
     g = golden("geometry")
-    geo = pc.geometry.Geometry()
+    geo = pc.geometry.Geometry(host=True)
     geo.fit(g["theta"])
     for k in KEYS:
         np.testing.assert_allclose(getattr(geo, k), g["nw_" + k], err_msg=k, **F64)
@@ -72,32 +72,87 @@ def test_fit_mvstud_keeps_the_reference_nu_quirk():
     Geometry.fit then pins nu to 1e6 (geometry.py:57-58).  Parity mode keeps that behaviour."""
     rng = np.random.default_rng(4)                       # multivariate t_3: normal / sqrt(chi2_3 / 3)
     heavy = rng.normal(size=(4000, 5)) / np.sqrt(rng.chisquare(3.0, size=(4000, 1)) / 3.0)
-    mu, cov, nu = pc.geometry.fit_mvstud(heavy)
+    mu, cov, nu = pc.geometry.fit_mvstud_host(heavy)
     assert mu.shape == (5,) and cov.shape == (5, 5)
     assert nu == np.inf
     np.testing.assert_allclose(mu, np.median(heavy, axis=0), rtol=1e-14)          # first-iteration exit: the initial guess
-    geo = pc.geometry.Geometry()
+    geo = pc.geometry.Geometry(host=True)
     geo.fit(heavy)
     assert geo.t_nu == 1e6
 
 
 @pytest.mark.gpu
-def test_weighted_geometry_matches_reference(golden):
-    """Weighted fit: np.average / np.cov on the host, the systematic resample (one uniform from the
-    global stream, tools.py:136-186) on the GPU -- indices must be bit-exact for the t fit to agree."""
+@pytest.mark.parametrize("host", [True, False])
+def test_weighted_geometry_matches_reference(golden, host):
+    """Weighted fit against the reference's recorded vectors: the systematic resample (one uniform from the global stream,
+    tools.py:136-186) runs on the GPU -- indices must be bit-exact for the t fit to agree -- and with host=False so does
+    every pass over the cloud (csrc/geom_ops.cu): moments, medians, scatter; f64 bar 1e-12."""
     g = golden("geometry")
-    geo = pc.geometry.Geometry()
+    geo = pc.geometry.Geometry(host=host)
     np.random.seed(77)
     geo.fit(g["theta"], weights=g["w"])
     for k in KEYS:
         np.testing.assert_allclose(getattr(geo, k), g[k], err_msg=k, **F64)
 
 
+@pytest.mark.gpu
+def test_device_geometry_matches_reference_unweighted_and_mvstud(golden):
+    g = golden("geometry")
+    geo = pc.geometry.Geometry()
+    geo.fit(g["theta"])
+    for k in KEYS:
+        np.testing.assert_allclose(getattr(geo, k), g["nw_" + k], err_msg=k, **F64)
+    mu, sigma, nu = pc.geometry.fit_mvstud(g["theta"])
+    np.testing.assert_allclose(mu, g["mvstud_mu"], **F64)
+    np.testing.assert_allclose(sigma, g["mvstud_sigma"], **F64)
+    assert nu == g["mvstud_nu"] or (np.isinf(nu) and np.isinf(g["mvstud_nu"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,d", [(777, 3), (5000, 32), (20011, 200), (300, 70)])
+def test_device_geometry_reductions_against_numpy(n, d):
+    """every reduction of csrc/geom_ops.cu against its numpy formula (student.py:38-58, geometry.py:44-49): odd sizes, several
+    row chunks, several 64 x 64 output tiles, weights with a large dynamic range; f64 bar 1e-12 relative to the result's scale."""
+    import torch
+    from pocomc_b200.geometry import _Cloud, fit_mvstud_device, fit_mvstud_host
+    rng = np.random.default_rng(n + d)
+    a = rng.normal(size=(d, d)) / np.sqrt(d)
+    x = rng.normal(size=(n, d)) @ a + rng.normal(size=d)
+    w = np.exp(rng.normal(size=n) * 3.0)
+    cloud = _Cloud(x)
+    wd = torch.from_numpy(w).cuda()
+    mu = np.median(x, axis=0)
+    np.testing.assert_array_equal(cloud.medians(), mu)
+    sums, sw, sw2, r2 = cloud.colsums(wd, center=mu)
+    np.testing.assert_allclose(sums, w @ x, rtol=1e-12, atol=1e-12 * np.abs(w @ x).max())
+    np.testing.assert_allclose([sw, sw2, r2], [w.sum(), (w * w).sum(), ((x - mu) ** 2).sum(1).max()], rtol=1e-12)
+    ref_cov = np.cov(x.T, aweights=w)
+    got_cov = cloud.scatter(np.average(x, axis=0, weights=w), wd) / (sw - sw2 / sw)
+    np.testing.assert_allclose(got_cov, ref_cov, rtol=1e-11, atol=1e-12 * np.abs(ref_cov).max())
+    assert np.array_equal(got_cov, got_cov.T)
+    sigma = np.cov(x.T)
+    diffs = (x - mu).T
+    ref_delta = np.sum(diffs * np.linalg.solve(sigma, diffs), 0)
+    delta = cloud.mahalanobis(mu, np.linalg.inv(sigma))
+    np.testing.assert_allclose(delta.cpu().numpy(), ref_delta, rtol=1e-9)
+    for nu in (0.7, 20.0, 1e300):
+        sl, s1, wt = cloud.student_weights(delta, nu, store=True)
+        wr = (nu + d) / (nu + delta.cpu().numpy())
+        np.testing.assert_allclose([sl, s1], [np.log(wr).sum(), wr.sum()], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(wt.cpu().numpy(), wr, rtol=1e-14)
+    # the whole fit: same exit, same values as the reference's numpy formulation
+    md, sd, nd = fit_mvstud_device(x)
+    mh, sh_, nh = fit_mvstud_host(x)
+    np.testing.assert_allclose(md, mh, rtol=1e-12)
+    np.testing.assert_allclose(sd, sh_, rtol=1e-11, atol=1e-12 * np.abs(sh_).max())
+    assert nd == nh or (np.isinf(nd) and np.isinf(nh))
+
+
 def test_fit_mvstud_matches_reference_vectors_and_takes_the_full_path_when_it_must(golden):
     """student.py:5-85 on the recorded cloud (bit-for-bit: the shortcut past the unused Mahalanobis solve must not
     change a single value), and the guard that sends degenerate clouds down the reference's own path."""
     g = golden("geometry")
-    mu, sigma, nu = pc.geometry.fit_mvstud(g["theta"])
+    mu, sigma, nu = pc.geometry.fit_mvstud_host(g["theta"])
     np.testing.assert_array_equal(mu, g["mvstud_mu"])
     np.testing.assert_array_equal(sigma, g["mvstud_sigma"])
     assert nu == g["mvstud_nu"] or (np.isinf(nu) and np.isinf(g["mvstud_nu"]))
