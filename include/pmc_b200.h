@@ -232,6 +232,19 @@ int pmc_mh_accept_finalize(int32_t kind, double beta, double nu, float* pos32, d
                            double* ctl, uint32_t* ticket, int32_t mean_mode, int32_t n_steps,
                            int32_t n_max, int64_t n, int32_t d, pmc_stream_t stream);
 
+/* ---- layer-wise training step of Flow.fit (flow.py:301-319) for every flow shape: spline (NSF, the reference's default
+ * presets) and affine heads, any width.  raw / mask / grad: flat parameter blob in module order (per transform W0 [H,D], b0,
+ * W1 [H,H], b1, W2, b2, W3 [D*total,H], b3), its MADE mask laid out alike (1 for biases), its gradient.  x [*, D] f32 training
+ * matrix, w (NULL: unweighted), idx_all / mask_all [*, B] batch tables, cursor: device int64 selecting the batch.  kind 0 =
+ * affine heads (2 parameters per feature), 1 = spline heads (23 = 3 * 8 bins - 1).  partials:
+ * pmc_flow_train_lw_partials(B) doubles whose sum is the batch loss (flow.py:305-310).  train = 0: loss only.  scratch:
+ * pmc_flow_train_lw_scratch_size(D, H, T, total, numel, B) floats.  A fixed sequence of launches on `stream` (graph-capturable). */
+int64_t pmc_flow_train_lw_scratch_size(int32_t D, int32_t H, int32_t T, int32_t total, int64_t numel, int64_t B);
+int32_t pmc_flow_train_lw_partials(int64_t B);
+int pmc_flow_train_step_lw(const float* raw, const float* mask, int32_t D, int32_t H, int32_t T, int32_t kind, int64_t numel,
+                           const float* x, const float* w, const int64_t* idx_all, const float* mask_all, const int64_t* cursor,
+                           int64_t B, float* scratch, double* partials, float* grad, int32_t train, pmc_stream_t stream);
+
 /* ---- proposal geometry (geometry.py:31-59, student.py:5-85) ------------------------------------------------
  * The O(n D^2) reductions of Geometry.fit / fit_mvstud over a cloud x [n, d] f64 (row-major), f64, fixed-order two-stage sums
  * (independent of the SM count).  scratch: pmc_geometry_scratch_size(n, d) doubles.

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libpmc_b200.so")
-SOURCES = ["lib.cu", "flow_sweep.cu", "mcmc_ops.cu", "smc_ops.cu", "train_ops.cu", "flow_tc.cu", "flow_train.cu", "flow_tri.cu", "geom_ops.cu"]
+SOURCES = ["lib.cu", "flow_sweep.cu", "mcmc_ops.cu", "smc_ops.cu", "train_ops.cu", "flow_tc.cu", "flow_train.cu", "flow_tri.cu", "geom_ops.cu", "flow_train_lw.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 

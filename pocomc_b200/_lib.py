@@ -57,6 +57,9 @@ SIGNATURES = {
     "pmc_gather_rows_f64": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "pmc_trim_threshold": (C.c_int, [_P, _I64, _F64, _I32, _P, _P, _P]),
     "pmc_trim_scratch_size": (_I64, [_I64]),
+    "pmc_flow_train_lw_scratch_size": (_I64, [_I32, _I32, _I32, _I32, _I64, _I64]),
+    "pmc_flow_train_lw_partials": (_I32, [_I64]),
+    "pmc_flow_train_step_lw": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _I32, _P]),
     "pmc_geometry_scratch_size": (_I64, [_I64, _I32]),
     "pmc_weighted_colsums": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P]),
     "pmc_weighted_scatter": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P]),

@@ -32,9 +32,10 @@ fit_path
     consumption as ``"eager"``, which issues the ops one by one.  Noise / L1 / L2 regularised fits
     always take the eager path.
 fit_kernels
-    ``"fused"`` (default): MAF flows with H <= 128 train on the hand-written forward/backward kernels of
-    csrc/flow_train.cu (5 launches per optimiser step inside the graph); ``"autograd"``: torch autograd
-    over the flat blob (always used for spline flows).
+    ``"fused"`` (default): MAF flows with H <= 256, D <= 64 train on the fused forward/backward kernels of
+    csrc/flow_train.cu (4 launches per optimiser step inside the graph), every other flow -- spline heads (the reference's
+    default presets), H >= 512 -- on the layer-wise kernels of csrc/flow_train_lw.cu; ``"autograd"``: torch autograd
+    over the flat blob (what noise / L1 / L2 regularised fits always use).
 p2p_exchange
     True (default): under torch.distributed/NCCL with one GPU per rank the per-MCMC-step reduction of a particle-sharded
     run (mean acceptance, mean theta, tracked log-density over ALL particles) is exchanged by the accept kernel itself

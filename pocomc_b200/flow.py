@@ -587,6 +587,12 @@ class _FitEngine:
             self.grad = torch.zeros(n, dtype=torch.float32, device=dev)      # masked entries stay 0
             self.fscratch = {}      # Bp -> (scratch floats, loss partials)
             self.eval_partials = {} # Bp -> loss partials of a whole validation epoch
+        # every other flow (spline heads = the reference's default presets, H >= 512, D > 64): the layer-wise kernels of
+        # csrc/flow_train_lw.cu -- masked-linear GEMMs + univariate-head kernels, forward and backward, one C call per batch
+        self.layerwise = (not self.fused) and config.fit_kernels != "autograd"
+        if self.layerwise:
+            self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.fscratch = {}
 
     def load(self, x: torch.Tensor, w):
         """copy the training matrix (already shuffled like flow.py:229-234) into the static buffers"""
@@ -641,9 +647,48 @@ class _FitEngine:
             self.acc += partials.sum()
             self.cursor += 1
 
+    def _lw_buffers(self, B):
+        if B not in self.fscratch:
+            lay, lib = self.module.layout, _lib.load()
+            nfl = int(lib.pmc_flow_train_lw_scratch_size(lay.n_dim, lay.n_hidden, lay.n_transforms, lay.total, self.module.raw.numel(), B))
+            self.fscratch[B] = (torch.empty(nfl, dtype=torch.float32, device=self.module.raw.device),
+                                torch.zeros(int(lib.pmc_flow_train_lw_partials(B)), dtype=torch.float64, device=self.module.raw.device))
+        return self.fscratch[B]
+
+    def _body_lw(self, B, weighted, train):
+        """layer-wise forward + backward (csrc/flow_train_lw.cu) -> clip + AdamW with the loss / cursor bookkeeping folded in"""
+        mod, lay = self.module, self.module.layout
+        idx_all, mask_all = self._tables(B)
+        scratch, partials = self._lw_buffers(B)
+        _lib.call("pmc_flow_train_step_lw", _lib.ptr(mod.raw), _lib.ptr(mod._flat_mask()), lay.n_dim, lay.n_hidden, lay.n_transforms,
+                  0 if lay.kind == ML.KIND_AFFINE else 1, mod.raw.numel(), _lib.ptr(self.x), _lib.ptr(self.w) if weighted else None,
+                  _lib.ptr(idx_all), _lib.ptr(mask_all), _lib.ptr(self.cursor), B, _lib.ptr(scratch), _lib.ptr(partials),
+                  _lib.ptr(self.grad), 1 if train else 0)
+        if train:
+            _lib.call("pmc_adamw_clip_step_ex", _lib.ptr(mod.raw), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
+                      mod.raw.numel(), _lib.ptr(self.hyper), _lib.ptr(self.step), _lib.ptr(self.scratch), _lib.ptr(self.gnorm),
+                      _lib.ptr(partials), partials.numel(), _lib.ptr(self.acc), _lib.ptr(self.cursor), None, None, None)
+        else:
+            self.acc += partials.sum()
+            self.cursor += 1
+
     def loss_and_grad(self, rows: torch.Tensor, weighted: bool):
-        """(loss, gradient blob) of one batch on the fused kernels, no parameter update (tests / diagnostics)."""
-        assert self.fused
+        """(loss, gradient blob) of one batch on the hand-written kernels, no parameter update (tests / diagnostics)."""
+        assert self.fused or self.layerwise
+        if self.layerwise:
+            B = (len(rows) + 31) // 32 * 32
+            idx_all, mask_all = self._tables(B)
+            idx_all[0].zero_(); mask_all[0].zero_()
+            idx_all[0, :len(rows)] = rows.to(idx_all.device)
+            mask_all[0, :len(rows)] = 1.0
+            self.cursor.zero_(); self.acc.zero_(); self.grad.zero_()
+            scratch, partials = self._lw_buffers(B)
+            mod, lay = self.module, self.module.layout
+            _lib.call("pmc_flow_train_step_lw", _lib.ptr(mod.raw), _lib.ptr(mod._flat_mask()), lay.n_dim, lay.n_hidden, lay.n_transforms,
+                      0 if lay.kind == ML.KIND_AFFINE else 1, mod.raw.numel(), _lib.ptr(self.x), _lib.ptr(self.w) if weighted else None,
+                      _lib.ptr(idx_all), _lib.ptr(mask_all), _lib.ptr(self.cursor), B, _lib.ptr(scratch), _lib.ptr(partials),
+                      _lib.ptr(self.grad), 1)
+            return float(partials.sum().item()), self.grad.clone()
         B = (len(rows) + 31) // 32 * 32
         idx_all, mask_all = self._tables(B)
         idx_all[0].zero_(); mask_all[0].zero_()
@@ -697,7 +742,10 @@ class _FitEngine:
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                if not self.fused:
+                if self.layerwise:
+                    self.module._flat_mask()
+                    self._lw_buffers(B)                          # allocate outside the capture
+                elif not self.fused:
                     for _ in range(2):                           # warm-up without touching any state
                         self._body(B, weighted, optimise=False)
                 else:
@@ -710,6 +758,8 @@ class _FitEngine:
                 for _ in range(int(steps)):
                     if self.fused:
                         self._body_fused(B, weighted, train)
+                    elif self.layerwise:
+                        self._body_lw(B, weighted, train)
                     else:
                         self._body(B, weighted, optimise=True)
             self.graphs[key] = g
@@ -760,7 +810,7 @@ class _FitEngine:
             return self.acc
         if self.fused and train:       # the training image follows raw inside the step; bring it up to date once per epoch
             _lib.call("pmc_flow_pack", _lib.ptr(self.module.raw), _lib.ptr(self.tl_gather), _lib.ptr(self.tl_packed), self.tl.numel)
-        k = self.STEPS_PER_GRAPH if self.fused else 1
+        k = self.STEPS_PER_GRAPH if (self.fused or self.layerwise) else 1
         if nb >= k > 1:
             gk = self.graph(B, weighted, train, steps=k)
             for _ in range(nb // k):
