@@ -457,6 +457,17 @@ def run_b200(args):
                     flop_per_launch=issued, useful_flop_per_launch=useful, useful_tflops=useful / (sweep_ms * 1e-3) / 1e12,
                     avg_launch_ms=sweep_ms, share_of_step=sweep_ms * MCMC_STEPS * args.steps / (t_dev * 1e3), note=note)
 
+    # the rest of the device-resident step (rng, proposal, scaler, prior, synthetic likelihood, accept + adapt [+ exchange]): HBM-bound
+    hbm_peak = float(peaks.get("hbm_gbs", 6551.0))
+    step_ms = 1e3 * t_dev / (args.steps * MCMC_STEPS)
+    chain_ms = max(step_ms - sweep_ms, 1e-6)
+    chain_bytes = (44.0 * D + 56.0) * n_local                      # algorithmic bytes per particle-step of the non-flow part
+    roofline_chain = dict(bound="hbm", kernel="non-flow chain of one MCMC step (rng_fill, tpcn_propose, scaler_inverse, logprior, loglike, mh_accept + adapt)",
+                          achieved=chain_bytes / (chain_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                          frac=chain_bytes / (chain_ms * 1e-3) / 1e9 / hbm_peak, bytes_per_step=chain_bytes, ms_per_step=chain_ms,
+                          note="step time minus the flow-inverse launch (CUDA events); (44 D + 56) B per particle-step; the state of one shard "
+                               "is L2-resident, the chain is launch-latency bound at this size (6 launches)")
+
     value = n_global * MCMC_STEPS * args.steps / t_dev
     e2e_value = n_global * MCMC_STEPS * e2e_steps / t_e2e
     line = dict(metric="particle-steps/sec", value=value, unit="particle-steps/s", n_gpus=world, steps=args.steps,
@@ -466,7 +477,7 @@ def run_b200(args):
                 e2e=dict(value=e2e_value, unit="particle-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=1e3 * t_e2e / e2e_steps, steps=e2e_steps, rng="device Philox",
                          callbacks="host numpy likelihood (black box); pc.Prior of scipy norm / uniform factors evaluated on the GPU"),
-                gpu_launches=launches, roofline=roofline, accept_rate=accept_dev)
+                gpu_launches=launches, roofline=roofline, roofline_other=[roofline_chain], accept_rate=accept_dev)
     if rank == 0 and world == 1 and not args.no_aux and args.config == 1:
         line["aux"] = aux_measurements(flow, peaks, D)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -561,11 +572,52 @@ def aux_measurements(flow, peaks, n_dim):
         for _ in range(5):
             eng.run_epoch(batches, 512, True)
         torch.cuda.synchronize()
-        out["fit_step"] = dict(batch=512, flow=FLOW, n_dim=n_dim, us_per_optimizer_step=(time.perf_counter() - t0) / 80 * 1e6,
+        us = (time.perf_counter() - t0) / 80 * 1e6
+        lay2 = f2.flow.layout
+        dense = lay2.n_transforms * (lay2.n_dim * lay2.n_hidden + (lay2.n_layers - 1) * lay2.n_hidden ** 2 + lay2.n_hidden * lay2.n_dim * lay2.total)
+        gflop = 6.0 * dense * 512 / 1e9                         # forward + input gradients + weight gradients, dense
+        out["fit_step"] = dict(batch=512, flow=FLOW, n_dim=n_dim, us_per_optimizer_step=us, gflop_per_step=gflop,
+                               tflops=gflop / us * 1e-3, frac_of_fp32_fma_peak=gflop / us * 1e-3 / 74.45,
                                path="fused forward/backward + grouped weight-gradient GEMM + clip/AdamW, one CUDA graph launch"
-                               if eng.fused else "autograd in a CUDA graph")
+                               if eng.fused else ("layer-wise kernels in a CUDA graph" if eng.layerwise else "autograd in a CUDA graph"))
     except Exception as e:      # diagnostics only
         out["fit_step"] = dict(error=repr(e))
+    # (2b) the same for the reference's default flow family (nsf6, 10-D): layer-wise kernels (csrc/flow_train_lw.cu)
+    try:
+        f3 = pc.Flow(10, "nsf6")
+        eng3 = _FitEngine(f3.flow)
+        xt = torch.randn(8192, 10, device="cuda")
+        wt = torch.rand(8192, device="cuda") + 0.1
+        eng3.load(xt, wt)
+        eng3.reset_optimizer(1e-3, 0.0, 1.0)
+        batches = [torch.arange(i, i + 512) for i in range(0, 8192, 512)]
+        eng3.run_epoch(batches, 512, True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            eng3.run_epoch(batches, 512, True)
+        torch.cuda.synchronize()
+        out["fit_step_nsf6_10d"] = dict(batch=512, us_per_optimizer_step=(time.perf_counter() - t0) / 80 * 1e6,
+                                        path="layer-wise kernels in a CUDA graph" if eng3.layerwise else "autograd in a CUDA graph")
+    except Exception as e:
+        out["fit_step_nsf6_10d"] = dict(error=repr(e))
+    # (2c) proposal geometry on the device: weighted fit of a 40 000 x n_dim cloud (what Sampler._train hands over at this config)
+    try:
+        rng = np.random.default_rng(0)
+        cloud = rng.normal(size=(40000, n_dim))
+        wts = np.exp(rng.normal(size=40000)); wts /= wts.sum()
+        geo = pc.geometry.Geometry()
+        best = 1e9
+        for _ in range(3):
+            np.random.seed(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            geo.fit(cloud, weights=wts)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        out["geometry_fit"] = dict(rows=40000, n_dim=n_dim, ms=best * 1e3, path="csrc/geom_ops.cu (f64, fixed-order reductions) + device sort / resample / gather")
+    except Exception as e:
+        out["geometry_fit"] = dict(error=repr(e))
     # (3) full Sampler.run() of BASELINE configs[0]; logZ against the unmodified reference
     try:
         from scipy.stats import uniform

@@ -363,7 +363,9 @@ __device__ __forceinline__ void run_block(const TriParams& p, const int bi, cons
       *reinterpret_cast<float4*>(xt + 2048 + row_in_tile * 16) = z;              // K = 8: order positions 4..7 do not exist
       *reinterpret_cast<float4*>(xt + 4096 + 2048 + row_in_tile * 16) = z;
     }
-    fence_proxy_async_all();
+    // generic-proxy stores -> async proxy (tcgen05.mma operand reads, bulk copies of the scratch area): the global half of the
+    // fence only when this block wrote scratch
+    if (p.NW > 1 && win + 1 < p.NW) fence_proxy_async_all(); else fence_proxy_async();
     tc_fence_before();
     mbar_arrive(&sh.a_ready);
     if (flags & TBF_LAST_IN_WIN) mbar_arrive(&sh.s_ready);

@@ -767,7 +767,7 @@ class _FitEngine:
 
     def run_epoch(self, batches, B, weighted, train=True, offset=0):
         """batches: list of host index tensors (each <= B rows) into the training matrix (shifted by
-        ``offset``); returns the device scalar holding the summed batch losses.  ``train=False`` (fused
+        ``offset``); returns the device scalar holding the summed batch losses.  ``train=False`` (hand-written
         kernels only) evaluates the loss without touching the parameters."""
         nb = len(batches)
         if nb > self.MAX_BATCHES:
@@ -962,11 +962,11 @@ class Flow:
                     optimizer.step()
                     train_loss += loss.detach().double()
             val_loss = None
-            if engine is not None and engine.fused:
+            if engine is not None and (engine.fused or engine.layerwise):
                 train_loss = train_loss.clone()                  # engine.acc is reused by the validation pass
             if validation:
                 module.eval()
-                if engine is not None and engine.fused:
+                if engine is not None and (engine.fused or engine.layerwise):
                     val_loss = engine.run_epoch(epoch_batches(n_valid, batch_size, shuffle), int(batch_size), weights is not None,
                                                 train=False, offset=n_train)
                 else:
