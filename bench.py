@@ -14,7 +14,8 @@ steps / time.  `--config` selects the workload (default 1 = the configuration BA
 
 all with flow 'maf6' trained for 200 optimiser steps on the initial cloud, Student-t geometry fitted on the latent
 cloud, beta = 1.  At N GPUs every rank holds the per-GPU particle count (weak scaling); `--scaling strong` keeps the
-TOTAL fixed at 8x the per-GPU count and gives every rank total / N.
+TOTAL fixed (the config's own multi-GPU total, else 64 x its particle count, rounded to whole tile waves: 606 208 particles
+at config 1) and gives every rank total / N.
 
   value : device-resident arm -- state in HBM, Philox noise and the synthetic prior/likelihood evaluated on the GPU, no
           host traffic inside the timed region.
@@ -321,6 +322,11 @@ def run_b200(args):
         # fixed TOTAL: the config's own total where it is defined on several GPUs, else 64 x the per-GPU count (a total
         # small enough for one tile wave per GPU would only measure the latency floor of one sweep)
         total = cfg["n"] * cfg["gpus"] if cfg["gpus"] > 1 else 64 * cfg["n"]
+        # ... rounded down to whole waves of the flow inverse's 128-particle tiles on 148 SMs x 8 GPUs, so that every rank
+        # runs full waves at every N in {1, 2, 4, 8} (config 1: 606 208 particles = 4 x 148 tiles per GPU at N = 8; an
+        # unrounded 640 000 costs every rank a fifth, 23 %-full wave there)
+        wave = 128 * 148 * 8
+        total = max(wave, total // wave * wave)
         n_local = (total // world + 255) // 256 * 256
     else:
         n_local = cfg["n"]
@@ -577,7 +583,7 @@ def aux_measurements(flow, peaks, n_dim):
         dense = lay2.n_transforms * (lay2.n_dim * lay2.n_hidden + (lay2.n_layers - 1) * lay2.n_hidden ** 2 + lay2.n_hidden * lay2.n_dim * lay2.total)
         gflop = 6.0 * dense * 512 / 1e9                         # forward + input gradients + weight gradients, dense
         out["fit_step"] = dict(batch=512, flow=FLOW, n_dim=n_dim, us_per_optimizer_step=us, gflop_per_step=gflop,
-                               tflops=gflop / us * 1e-3, frac_of_fp32_fma_peak=gflop / us * 1e-3 / 74.45,
+                               tflops=gflop / us * 1e3, frac_of_fp32_fma_peak=gflop / us * 1e3 / 74.45,
                                path="fused forward/backward + grouped weight-gradient GEMM + clip/AdamW, one CUDA graph launch"
                                if eng.fused else ("layer-wise kernels in a CUDA graph" if eng.layerwise else "autograd in a CUDA graph"))
     except Exception as e:      # diagnostics only
