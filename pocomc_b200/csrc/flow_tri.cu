@@ -43,6 +43,7 @@ enum { TBF_LAST_IN_WIN = 1, TBF_LAST = 2 };
 
 constexpr int TRI_LAYOUT_VERSION = 300;
 constexpr int TRI_MAX_STAGES = 8;          // ring depth: as many slots as fit, decided by tri_layout.build_tri
+constexpr int TRI_MAX_SLOTS = 12;          // + the slots a window initialisation borrows from the (then idle) A-tile area
 constexpr int TRI_MAX_BLOCKS = 64;
 constexpr int TRI_MAX_WINDOWS = 16;
 constexpr int TRI_THREADS = 224;           // warps 0-3 particles, 4 ring producer, 5 MMA issuer, 6 in-block slab producer
@@ -58,7 +59,7 @@ struct TriParams {
   float* ws;               // scratch: gridDim.x * ws_floats
   long long n;
   long long ws_floats;
-  int D, T, NB, NW, tstride, chunk_off, passes, stages, kc, kh_total, kx_total;
+  int D, T, NB, NW, tstride, chunk_off, passes, stages, extra, kc, kh_total, kx_total;
   uint32_t slot_bytes, dslot_bytes, tile_bytes;
 };
 
@@ -267,7 +268,7 @@ __device__ __forceinline__ void tri_stages(const float4* __restrict__ q, int& of
 }
 
 struct TriShared {
-  uint64_t bfull[TRI_MAX_STAGES], bempty[TRI_MAX_STAGES], asplit[TRI_MAX_STAGES], dfull[2], dempty[2], a_ready, acc_ready, s_ready;
+  uint64_t bfull[TRI_MAX_SLOTS], bempty[TRI_MAX_SLOTS], asplit[TRI_MAX_SLOTS], dfull[2], dempty[2], a_ready, acc_ready, s_ready;
   uint32_t tmem_slot;
   int blocks[TRI_MAX_BLOCKS][TB_FIELDS];
   int wins[TRI_MAX_WINDOWS][TW_FIELDS];
@@ -373,11 +374,21 @@ __device__ __forceinline__ void run_block(const TriParams& p, const int bi, cons
   }
 }
 
-struct RingPos {
-  uint32_t slot = 0, round = 0;
-  __device__ __forceinline__ void advance(const uint32_t stages, const uint32_t k = 1) {
-    slot += k;
-    while (slot >= stages) { slot -= stages; ++round; }
+// The operand ring as every role walks it.  Update slabs cycle through the `stages` slots behind the tiles; the chunks of a
+// window initialisation cycle through stages + extra slots -- the extra ones lie in the A-tile area, which nothing reads
+// between the last update of a window and the first block of the next.  A slot's mbarriers complete once per use whichever
+// sequence used it, so every role keeps ONE parity bit per slot for the barrier it waits on.
+struct Ring {
+  uint32_t su = 0, si = 0;        // next slot of the update / initialisation sequence
+  uint32_t par = 0;               // per slot: parity of the next completion this role waits for
+  uint32_t used = 0;              // producer: slots filled at least once (their `empty` barrier has something to wait for)
+  __device__ __forceinline__ uint32_t next_update(const uint32_t stages) { const uint32_t s = su; su = (su + 1 == stages) ? 0 : su + 1; return s; }
+  __device__ __forceinline__ uint32_t next_init(const uint32_t slots) { const uint32_t s = si; si = (si + 1 == slots) ? 0 : si + 1; return s; }
+  __device__ __forceinline__ void wait(uint64_t* bars, const uint32_t s) { mbar_wait(bars + s, (par >> s) & 1u); par ^= 1u << s; }
+  __device__ __forceinline__ void pass(const uint32_t s) { par ^= 1u << s; }                  // a use this role does not wait for
+  __device__ __forceinline__ void acquire(uint64_t* empty, const uint32_t s) {               // producer: the slot's previous use is over
+    if ((used >> s) & 1u) wait(empty, s);
+    used |= 1u << s;
   }
 };
 
@@ -418,7 +429,7 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
     w[7] = (uint32_t)nks | ((uint32_t)(bi == 0 ? 1 : 0) << 8);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TRI_MAX_STAGES; ++i) { mbar_init(sh.bfull + i, 1); mbar_init(sh.bempty + i, 1); mbar_init(sh.asplit + i, 128); }
+    for (int i = 0; i < TRI_MAX_SLOTS; ++i) { mbar_init(sh.bfull + i, 1); mbar_init(sh.bempty + i, 1); mbar_init(sh.asplit + i, 128); }
     for (int i = 0; i < 2; ++i) { mbar_init(sh.dfull + i, 1); mbar_init(sh.dempty + i, 128); }
     mbar_init(&sh.a_ready, 128);
     mbar_init(&sh.acc_ready, 1);
@@ -432,12 +443,13 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
   const uint32_t tm = sh.tmem_slot;
   const long long n_tiles = (p.n + 127) / 128;
   float* ws = p.ws + (size_t)blockIdx.x * (size_t)p.ws_floats;
-  const uint32_t stages = (uint32_t)p.stages;
+  const uint32_t stages = (uint32_t)p.stages, init_slots = (uint32_t)(p.stages + p.extra);
+  auto slot_ptr = [&](const uint32_t sl) -> unsigned char* { return sl < stages ? ring + (size_t)sl * p.slot_bytes : smem + (size_t)(sl - stages) * p.slot_bytes; };
 
   if (warp == 4) {
     // ---------------- producer 1: update slabs (B operands) and window-initialisation chunks (A from scratch + B) ----------------
     if (lane == 0) {
-      RingPos rp;
+      Ring rg;
       uint32_t n_tr = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int tt = 0; tt < p.T; ++tt) {
@@ -450,11 +462,11 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
               for (int op = 0; op < 4; ++op) {
                 const uint32_t N = (uint32_t)(op < 3 ? B[TB_UPD_N] : B[TB_OUT_N]), K = (uint32_t)(op == 0 ? 8 : B[TB_KP]);
                 const uint32_t bytes = N * K * 8u;
-                if (rp.round > 0) mbar_wait(sh.bempty + rp.slot, (rp.round - 1) & 1);
-                mbar_expect_tx(sh.bfull + rp.slot, bytes);
-                bulk_g2s(ring + (size_t)rp.slot * p.slot_bytes, src, bytes, sh.bfull + rp.slot);
+                const uint32_t sl = rg.next_update(stages);
+                rg.acquire(sh.bempty, sl);
+                mbar_expect_tx(sh.bfull + sl, bytes);
+                bulk_g2s(slot_ptr(sl), src, bytes, sh.bfull + sl);
                 src += N * K * 2u;
-                rp.advance(stages);
               }
             } else if (!(flags & TBF_LAST)) {
               const int* Wn = sh.wins[B[TB_WIN] + 1];
@@ -468,13 +480,13 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
                 for (int k = 0; k < ktot; k += p.kc) {
                   const uint32_t ke = (uint32_t)min(p.kc, ktot - k);
                   const uint32_t a_bytes = ke * 512u, b_bytes = N * ke * 8u;
-                  if (rp.round > 0) mbar_wait(sh.bempty + rp.slot, (rp.round - 1) & 1);
-                  unsigned char* dst = ring + (size_t)rp.slot * p.slot_bytes;
-                  mbar_expect_tx(sh.bfull + rp.slot, a_bytes + b_bytes);
-                  bulk_g2s(dst, a_src + (size_t)k * 128, a_bytes, sh.bfull + rp.slot);
-                  bulk_g2s(dst + 2 * a_bytes, src, b_bytes, sh.bfull + rp.slot);
+                  const uint32_t sl = rg.next_init(init_slots);
+                  rg.acquire(sh.bempty, sl);
+                  unsigned char* dst = slot_ptr(sl);
+                  mbar_expect_tx(sh.bfull + sl, a_bytes + b_bytes);
+                  bulk_g2s(dst, a_src + (size_t)k * 128, a_bytes, sh.bfull + sl);
+                  bulk_g2s(dst + 2 * a_bytes, src, b_bytes, sh.bfull + sl);
                   src += N * ke * 2u;
-                  rp.advance(stages);
                 }
               }
             }
@@ -504,9 +516,9 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
   } else if (warp == 5) {
     // ---------------- issuer: one thread drives the tensor core ----------------
     if (lane == 0) {
-      RingPos rp;
+      Ring rg;
       uint32_t n_blk = 0, split_phase = 0;              // split_phase: one parity bit per ring slot (asplit completes only on init chunks)
-      const uint32_t ring16 = (smem_u32(ring) & 0x3FFFF) >> 4, slot16 = p.slot_bytes >> 4;
+      const uint32_t ring16 = (smem_u32(ring) & 0x3FFFF) >> 4, slot16 = p.slot_bytes >> 4, tiles16 = (smem_u32(smem) & 0x3FFFF) >> 4;
       const uint32_t desc_top = (128u >> 4) | (1u << 14);              // high word: SBO = 128 bytes, descriptor version 1
       const bool split = p.passes > 1;
       auto mma_group = [&](const uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, const uint32_t b_lo_off, const uint32_t b_step,
@@ -534,11 +546,11 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
               for (int op = 0; op < 4; ++op) {
                 const uint4 r0 = *reinterpret_cast<const uint4*>(sh.issue[bi][op]);
                 const uint4 r1 = *reinterpret_cast<const uint4*>(sh.issue[bi][op] + 4);
-                mbar_wait(sh.bfull + rp.slot, rp.round & 1);
+                const uint32_t sl = rg.next_update(stages);
+                rg.wait(sh.bfull, sl);
                 tc_fence_after();
-                mma_group(tm + r1.z, r0.x, r0.y, r0.z + ring16 + rp.slot * slot16, r0.w, r1.x, r1.y, r1.w & 0xffu, (r1.w & 0x100u) ? 0u : 1u);
-                mma_commit(sh.bempty + rp.slot);
-                rp.advance(stages);
+                mma_group(tm + r1.z, r0.x, r0.y, r0.z + ring16 + sl * slot16, r0.w, r1.x, r1.y, r1.w & 0xffu, (r1.w & 0x100u) ? 0u : 1u);
+                mma_commit(sh.bempty + sl);
               }
             } else {
               const int* Wn = sh.wins[B[TB_WIN] + 1];
@@ -549,14 +561,15 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
                 const uint32_t idesc = idesc_tf32(128, (int)N);
                 for (int k = 0; k < ktot; k += p.kc) {
                   const uint32_t ke = (uint32_t)min(p.kc, ktot - k);
-                  const uint32_t base16 = ring16 + rp.slot * slot16;
-                  mbar_wait(sh.asplit + rp.slot, (split_phase >> rp.slot) & 1u);
-                  split_phase ^= 1u << rp.slot;
+                  const uint32_t sl = rg.next_init(init_slots);
+                  rg.pass(sl);                                   // the chunk's arrival is observed by the splitting threads
+                  const uint32_t base16 = sl < stages ? ring16 + sl * slot16 : tiles16 + (sl - stages) * slot16;
+                  mbar_wait(sh.asplit + sl, (split_phase >> sl) & 1u);
+                  split_phase ^= 1u << sl;
                   tc_fence_after();
                   const uint32_t a_hi = base16 | ((2048u >> 4) << 16);
                   mma_group(d, a_hi, a_hi + ke * 32u, (base16 + ke * 64u) | (N << 16), (N * ke * 4u) >> 4, N * 2u, idesc, ke >> 3, k == 0 ? 0u : 1u);
-                  mma_commit(sh.bempty + rp.slot);
-                  rp.advance(stages);
+                  mma_commit(sh.bempty + sl);
                 }
               }
             }
@@ -570,7 +583,7 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
     const int row_in_tile = threadIdx.x;
     const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16);
     uint32_t n_groups = 0, dit = 0;
-    RingPos rp;
+    Ring rg;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long row = tile * 128 + row_in_tile;
       const bool valid = row < p.n;
@@ -612,7 +625,7 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
           if (bi + 1 < p.NB) load_y(t, bi + 1, y);
           else if (tt + 1 < p.T) load_y(INV ? t - 1 : t + 1, 0, y);
           if (!(flags & TBF_LAST_IN_WIN)) {
-            rp.advance(stages, 4);                       // the four update slabs of this block pass through the ring untouched
+            for (int op = 0; op < 4; ++op) rg.pass(rg.next_update(stages));      // the four update slabs of this block go by untouched
           } else if (!(flags & TBF_LAST)) {
             // window initialisation: split this row of every A chunk into its TF32 hi / lo images
             const int* Wn = sh.wins[sh.blocks[bi][TB_WIN] + 1];
@@ -620,8 +633,9 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
               const int ktot = op == 0 ? Wn[TW_KX] : Wn[TW_KH];
               for (int k = 0; k < ktot; k += p.kc) {
                 const int ke = min(p.kc, ktot - k);
-                mbar_wait(sh.bfull + rp.slot, rp.round & 1);
-                float4* a = reinterpret_cast<float4*>(ring + (size_t)rp.slot * p.slot_bytes) + row_in_tile;
+                const uint32_t sl = rg.next_init(init_slots);
+                rg.wait(sh.bfull, sl);
+                float4* a = reinterpret_cast<float4*>(slot_ptr(sl)) + row_in_tile;
                 for (int c = 0; c < (ke >> 2); ++c) {
                   const float4 v = a[c * 128];
                   float4 h, l;
@@ -630,8 +644,7 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
                   a[(ke >> 2) * 128 + c * 128] = l;
                 }
                 fence_proxy_async();
-                mbar_arrive(sh.asplit + rp.slot);
-                rp.advance(stages);
+                mbar_arrive(sh.asplit + sl);
               }
             }
           }
@@ -711,6 +724,14 @@ extern "C" int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host,
     if (w > 0) PMC_REQUIRE((uint32_t)q.kc * (1024u + (uint32_t)std::max(Wn[TW_WP], Wn[TW_OP]) * 8u) <= q.slot_bytes, "pmc_flow_sweep_tri: init chunk exceeds a ring slot");
   }
   PMC_REQUIRE(q.stages >= 2 && q.stages <= TRI_MAX_STAGES, "pmc_flow_sweep_tri: bad ring depth");
+  // a window initialisation borrows the A-tile area (3 layers x hi / lo + the x tile: idle between the last update of a
+  // window and the first block of the next) as extra ring slots: more bytes in flight for the phase bound by the latency
+  // of its operand stream
+  q.extra = q.NW > 1 ? (int)std::min<size_t>((size_t)(TRI_MAX_SLOTS - q.stages), ((size_t)6 * q.tile_bytes + 8192) / q.slot_bytes) : 0;
+  {
+    const char* ex = getenv("PMC_TRI_EXTRA");
+    if (ex && atoi(ex) >= 0 && atoi(ex) < q.extra) q.extra = atoi(ex);
+  }
   const size_t smem = (size_t)6 * q.tile_bytes + 8192 + (size_t)q.stages * q.slot_bytes + 2 * (size_t)q.dslot_bytes;
   PMC_REQUIRE(smem + sizeof(TriShared) <= 227 * 1024, "pmc_flow_sweep_tri: shared memory budget exceeded");
   PMC_REQUIRE(q.slot_bytes % 1024 == 0 && q.dslot_bytes % 1024 == 0 && q.tile_bytes % 1024 == 0, "pmc_flow_sweep_tri: unaligned slot sizes");

@@ -6,18 +6,20 @@ import bench as B
 import pocomc_b200 as pc
 from pocomc_b200 import config, mcmc as M
 
-wl = B.Workload(B.N_PER_GPU, B.N_DIM)
+cfg = B.CONFIGS[int(os.environ.get("CFG", "1"))]
+N_DIM = cfg["d"]
+wl = B.Workload(cfg, cfg["n"])
 np.random.seed(0); torch.manual_seed(0)
-scaler = pc.scaler.Reparameterize(B.N_DIM, bounds=wl.bounds); scaler.fit(wl.prior_samples)
+scaler = pc.scaler.Reparameterize(N_DIM, bounds=wl.bounds); scaler.fit(wl.prior_samples)
 u0 = scaler.forward(wl.x0)
-flow = pc.Flow(B.N_DIM, B.FLOW)
+flow = pc.Flow(N_DIM, B.FLOW)
 flow.fit(torch.tensor(u0, dtype=torch.float32), validation_split=0.5, epochs=3, batch_size=512, patience=10**6, annealing=False)
 theta = pc.tools.flow_numpy_wrapper(flow).forward(u0)[0]
 geo = pc.geometry.Geometry(); geo.fit(theta.astype(np.float64))
 state = dict(u=u0, x=wl.x0, logdetj=scaler.inverse(u0)[1], logl=wl.loglike(wl.x0), logp=wl.logprior(wl.x0), beta=1.0, blobs=None)
 prior = pc.Prior(wl.dists)
 fd = dict(loglike=lambda x: (wl.loglike(x), None), logprior=prior.logpdf, scaler=scaler, flow=flow, theta_geometry=geo, u_geometry=geo)
-od = dict(n_max=50, n_steps=10**9, progress_bar=None, proposal_scale=2.38 / B.N_DIM ** 0.5, seed=1)
+od = dict(n_max=50, n_steps=10**9, progress_bar=None, proposal_scale=2.38 / N_DIM ** 0.5, seed=1)
 config.set_rng_mode("device")
 M.preconditioned_pcn(dict(state), fd, od)
 pr = cProfile.Profile(); pr.enable()
