@@ -32,9 +32,9 @@ struct LwGemm {
 // C[M,N] = epilogue(op(A)[M,K] . op(B)[K,N]);  TA: A[m][k] stored at A[k*lda + m], else A[m*lda + k];
 // TB: B[k][n] stored at B[n*ldb + k], else B[k*ldb + n]
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256) lw_gemm_kernel(const LwGemm g) {
-  __shared__ float As[LW_TK][LW_TM + 4], Bs[LW_TK][LW_TN + 4];
+__device__ __forceinline__ void lw_gemm_body(const LwGemm& g, float (&As)[LW_TK][LW_TM + 4], float (&Bs)[LW_TK][LW_TN + 4]) {
   const int m0 = blockIdx.y * LW_TM, n0 = blockIdx.x * LW_TN;
+  if (m0 >= g.M || n0 >= g.N) return;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   float acc[4][4] = {};
   // 16-byte loads when every row of the operand starts on a 16-byte boundary and the tile is interior
@@ -128,29 +128,10 @@ __global__ void __launch_bounds__(256) lw_gemm_kernel(const LwGemm g) {
     }
   }
 }
-
-// out[n] = sum_m Y[m][n] (bias gradients): 32 columns x 8 row groups per block, four independent partial sums per thread,
-// combined in a fixed order
-__global__ void __launch_bounds__(256) lw_colsum_kernel(const float* __restrict__ Y, int M, int N, int ld, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + c;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if (n < N) {
-    int m = rg;
-    for (; m + 24 < M; m += 32) {
-      s0 += Y[(size_t)m * ld + n]; s1 += Y[(size_t)(m + 8) * ld + n]; s2 += Y[(size_t)(m + 16) * ld + n]; s3 += Y[(size_t)(m + 24) * ld + n];
-    }
-    for (; m < M; m += 8) s0 += Y[(size_t)m * ld + n];
-  }
-  red[rg][c] = (s0 + s1) + (s2 + s3);
-  __syncthreads();
-  if (rg == 0 && n < N) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][c];
-    out[n] = s;
-  }
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) lw_gemm_kernel(const LwGemm g) {
+  __shared__ float As[LW_TK][LW_TM + 4], Bs[LW_TK][LW_TN + 4];
+  lw_gemm_body<TA, TB>(g, As, Bs);
 }
 
 __global__ void lw_mask_kernel(const float* __restrict__ raw, const float* __restrict__ mask, float* __restrict__ out, long long n) {
@@ -358,6 +339,40 @@ lw_loss_kernel(const float* __restrict__ z, const float* __restrict__ ladj, cons
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
+// the four weight-gradient GEMMs of one transform in one launch (blockIdx.z = layer), and their four bias gradients
+// (out[n] = sum_m Y[m][n]: 32 columns x 8 row groups per block, four independent partial sums per thread, fixed order)
+struct LwGemm4 { LwGemm g[4]; };
+__global__ void __launch_bounds__(256) lw_wgrad4_kernel(const LwGemm4 q) {
+  __shared__ float As[LW_TK][LW_TM + 4], Bs[LW_TK][LW_TN + 4];
+  lw_gemm_body<true, false>(q.g[blockIdx.z], As, Bs);
+}
+struct LwColsum4 { const float* Y[4]; float* out[4]; int N[4]; int M; };
+__global__ void __launch_bounds__(256) lw_colsum4_kernel(const LwColsum4 q) {
+  __shared__ float red[8][33];
+  const int l = blockIdx.y;
+  const float* __restrict__ Y = q.Y[l];
+  const int N = q.N[l], M = q.M, ld = N;
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  if (blockIdx.x * 32 >= N) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    int m = rg;
+    for (; m + 24 < M; m += 32) {
+      s0 += Y[(size_t)m * ld + n]; s1 += Y[(size_t)(m + 8) * ld + n]; s2 += Y[(size_t)(m + 16) * ld + n]; s3 += Y[(size_t)(m + 24) * ld + n];
+    }
+    for (; m < M; m += 8) s0 += Y[(size_t)m * ld + n];
+  }
+  red[rg][c] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rg == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][c];
+    q.out[l][n] = s;
+  }
+}
+
 static void lw_launch_gemm(bool ta, bool tb, const LwGemm& g, cudaStream_t st) {
   dim3 grid((g.N + LW_TN - 1) / LW_TN, (g.M + LW_TM - 1) / LW_TM);
   if (!ta && tb) lw_gemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
@@ -370,10 +385,10 @@ static void lw_launch_gemm(bool ta, bool tb, const LwGemm& g, cudaStream_t st) {
 using namespace pmc;
 
 /* floats of scratch for a (padded) batch of B rows: masked weights | xb | coef | ladj | lrow | per transform (v, h0, h1, h2, phi) |
- * z | g (D) x 2 | dphi | dh x 2 */
+ * z | g (D) x 2 | dphi | dh x 3 */
 extern "C" int64_t pmc_flow_train_lw_scratch_size(int32_t D, int32_t H, int32_t T, int32_t total, int64_t numel, int64_t B) {
   const int64_t P = (int64_t)D * total;
-  return numel + B * D + 2 * B + B * D + (int64_t)T * B * (D + 3 * (int64_t)H + P) + B * D + 2 * B * D + B * P + 2 * B * H + 64;
+  return numel + B * D + 2 * B + B * D + (int64_t)T * B * (D + 3 * (int64_t)H + P) + B * D + 2 * B * D + B * P + 3 * B * H + 64;
 }
 extern "C" int32_t pmc_flow_train_lw_partials(int64_t B) { return (int32_t)((B + 127) / 128); }
 
@@ -402,8 +417,7 @@ extern "C" int pmc_flow_train_step_lw(const float* raw, const float* mask, int32
   float* gA = take((size_t)B * D);
   float* gB = take((size_t)B * D);
   float* dphi = take((size_t)B * P);
-  float* dhA = take((size_t)B * H);
-  float* dhB = take((size_t)B * H);
+  float* dh[3] = {take((size_t)B * H), take((size_t)B * H), take((size_t)B * H)};     // d loss / d pre-activation of layers 2, 1, 0
   const size_t per_t = (size_t)B * (D + 3 * (size_t)H + P);
   auto act = [&](int t, int which) -> float* {      // 0: v (input), 1..3: h0..h2, 4: phi
     float* base = acts + (size_t)t * per_t;
@@ -452,21 +466,11 @@ extern "C" int pmc_flow_train_step_lw(const float* raw, const float* mask, int32
     // head: dphi and the direct part of d loss / d v (into gnext)
     if (kind == 0) lw_head_bwd_kernel<false><<<head_blocks, 128, 0, st>>>(act(t, 0), act(t, 4), gy, coef, B, D, total, dphi, gnext);
     else lw_head_bwd_kernel<true><<<head_blocks, 128, 0, st>>>(act(t, 0), act(t, 4), gy, coef, B, D, total, dphi, gnext);
-    const float* dpre = dphi;     // gradient with respect to the pre-activation of layer l
-    float* dh_cur = dhA;
-    float* dh_other = dhB;
+    // input-gradient chain: d input_l = dpre_l . Wm_l (+ dpre_l for the residual layers 1, 2), gated by the ReLU of the layer
+    // below; at l = 0 the input is v: add the head's direct part, no gate.  dpre_3 = dphi, dpre_2..0 = dh[0..2]
+    const float* dpre_of[4] = {dh[2], dh[1], dh[0], dphi};
     for (int l = 3; l >= 0; --l) {
-      // weight gradient dW_l [Nout, Kin] = dpre^T . input_l, masked; bias gradient = column sums
-      LwGemm gw{};
-      gw.A = dpre; gw.lda = Nout[l];
-      gw.B = act(t, l); gw.ldb = Kin[l];
-      gw.C = Gt + oW[l]; gw.ldc = Kin[l];
-      gw.M = Nout[l]; gw.N = Kin[l]; gw.K = B;
-      gw.epi = LW_EPI_WGRAD; gw.gate = Mt + oW[l]; gw.ldg = Kin[l];
-      lw_launch_gemm(true, false, gw, st);
-      lw_colsum_kernel<<<(Nout[l] + 31) / 32, 256, 0, st>>>(dpre, B, Nout[l], Nout[l], Gt + oB[l]);
-      // input gradient: d input_l = dpre . Wm_l (+ dpre for the residual layers 1, 2), gated by the ReLU of the layer below;
-      // at l = 0 the input is v: add the head's direct part, no gate
+      const float* dpre = dpre_of[l];
       LwGemm gd{};
       gd.A = dpre; gd.lda = Nout[l];
       gd.B = Wt + oW[l]; gd.ldb = Kin[l];
@@ -474,13 +478,32 @@ extern "C" int pmc_flow_train_step_lw(const float* raw, const float* mask, int32
       gd.epi = LW_EPI_BWD;
       if (l == 0) { gd.C = gnext; gd.ldc = D; gd.res = gnext; gd.ldr = D; gd.gate = nullptr; }
       else {
-        gd.C = dh_cur; gd.ldc = H;
+        gd.C = const_cast<float*>(dpre_of[l - 1]); gd.ldc = H;
         gd.res = (l == 1 || l == 2) ? dpre : nullptr; gd.ldr = H;
         gd.gate = act(t, l); gd.ldg = H;               // h_{l-1} > 0  <=>  its pre-activation passed the ReLU
       }
       lw_launch_gemm(false, false, gd, st);
-      if (l > 0) { dpre = dh_cur; std::swap(dh_cur, dh_other); }
     }
+    // the four weight gradients dW_l [Nout, Kin] = dpre_l^T . input_l (masked, straight into the gradient blob) in ONE
+    // launch, the four bias gradients (column sums of dpre_l) in another
+    LwGemm4 gw4{};
+    LwColsum4 cs4{};
+    int max_m = 0, max_n = 0, max_c = 0;
+    for (int l = 0; l < 4; ++l) {
+      LwGemm& gw = gw4.g[l];
+      gw.A = dpre_of[l]; gw.lda = Nout[l];
+      gw.B = act(t, l); gw.ldb = Kin[l];
+      gw.C = Gt + oW[l]; gw.ldc = Kin[l];
+      gw.M = Nout[l]; gw.N = Kin[l]; gw.K = B;
+      gw.epi = LW_EPI_WGRAD; gw.gate = Mt + oW[l]; gw.ldg = Kin[l];
+      max_m = std::max(max_m, (Nout[l] + LW_TM - 1) / LW_TM);
+      max_n = std::max(max_n, (Kin[l] + LW_TN - 1) / LW_TN);
+      cs4.Y[l] = dpre_of[l]; cs4.out[l] = Gt + oB[l]; cs4.N[l] = Nout[l];
+      max_c = std::max(max_c, (Nout[l] + 31) / 32);
+    }
+    cs4.M = B;
+    lw_wgrad4_kernel<<<dim3(max_n, max_m, 4), 256, 0, st>>>(gw4);
+    lw_colsum4_kernel<<<dim3(max_c, 4), 256, 0, st>>>(cs4);
     std::swap(gy, gnext);
   }
   PMC_LAUNCH_CHECK();
