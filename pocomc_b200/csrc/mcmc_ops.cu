@@ -5,6 +5,7 @@
 // global access is a contiguous row segment.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace pmc {
 
@@ -69,6 +70,116 @@ tpcn_propose_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl
     const double mp = warp_sum(part);
     if (lane == 0) { m_cur[row] = m; m_prop[row] = mp; }
     __syncwarp();
+  }
+}
+
+// The same proposal for wide problems (D >= 64): a block owns 32 rows, so that every element of the two D x D matrices is
+// read four times per 32 rows instead of once per row (at D = 200 the warp-per-row kernel pulls 960 KB through L1/L2 per
+// particle: 120 GB per step at 125 000 particles).  Thread (rg, c): 8 rows x two columns per 128-column pass; every output
+// keeps the row kernel's arithmetic -- an ascending-j fma chain per element, the lane-strided partial sums and the xor
+// tree of the Mahalanobis reductions -- so both kernels return bit-identical results.
+constexpr int PROP_ROWS = 32;
+template <typename PosT>
+__global__ void __launch_bounds__(256)
+tpcn_propose_tiled_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl,
+                          const double* __restrict__ inv_t, const double* __restrict__ chol_t, double nu,
+                          const double* __restrict__ g, const double* __restrict__ z,
+                          double* __restrict__ prop64, float* __restrict__ prop32,
+                          double* __restrict__ m_cur, double* __restrict__ m_prop, long long n, int d) {
+  extern __shared__ double sh[];
+  const int ld = d + 1;
+  double* diff = sh;                          // [32][ld]  theta - mu
+  double* zz = diff + PROP_ROWS * ld;         // [32][ld]  z, later the proposal's offset from mu
+  double* vv = zz + PROP_ROWS * ld;           // [32][ld]  Sigma^-1 (.)
+  double* lz = vv + PROP_ROWS * ld;           // [32][ld]  L z
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = threadIdx.x >> 6, c = threadIdx.x & 63;        // 4 row groups of 8 rows, 64 columns per pass
+  const double sigma = ctl[PMC_CTL_SIGMA];
+  const double* mu = ctl + PMC_CTL_MU;
+  const double keep = sqrt(1.0 - sigma * sigma);
+  for (long long r0 = (long long)blockIdx.x * PROP_ROWS; r0 < n; r0 += (long long)gridDim.x * PROP_ROWS) {
+    for (int e = threadIdx.x; e < PROP_ROWS * d; e += blockDim.x) {
+      const int r = e / d, j = e - r * d;
+      const bool ok = r0 + r < n;
+      diff[r * ld + j] = ok ? (double)pos[(r0 + r) * d + j] - mu[j] : 0.0;
+      zz[r * ld + j] = ok ? z[(r0 + r) * d + j] : 0.0;
+    }
+    __syncthreads();
+    for (int i = c; i < d; i += 128) {                        // columns i and i + 64: 8 rows x 2 columns per thread
+      const int i2 = i + 64;
+      const bool two = i2 < d;
+      double v[8], l[8], v2[8], l2[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { v[q] = 0.0; l[q] = 0.0; v2[q] = 0.0; l2[q] = 0.0; }
+      for (int j = 0; j < d; ++j) {
+        const double a = inv_t[(size_t)j * d + i], b = chol_t[(size_t)j * d + i];
+        const double a2 = two ? inv_t[(size_t)j * d + i2] : 0.0, b2 = two ? chol_t[(size_t)j * d + i2] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double dq = diff[(rg * 8 + q) * ld + j], zq = zz[(rg * 8 + q) * ld + j];
+          v[q] = fma(a, dq, v[q]);
+          l[q] = fma(b, zq, l[q]);
+          v2[q] = fma(a2, dq, v2[q]);
+          l2[q] = fma(b2, zq, l2[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        vv[(rg * 8 + q) * ld + i] = v[q]; lz[(rg * 8 + q) * ld + i] = l[q];
+        if (two) { vv[(rg * 8 + q) * ld + i2] = v2[q]; lz[(rg * 8 + q) * ld + i2] = l2[q]; }
+      }
+    }
+    __syncthreads();
+    // m = (theta - mu)^T Sigma^-1 (theta - mu): one warp per row, lanes stride the columns, xor tree (as the row kernel)
+    for (int r = warp; r < PROP_ROWS; r += 8) {
+      double part = 0.0;
+      for (int i = lane; i < d; i += 32) part = fma(diff[r * ld + i], vv[r * ld + i], part);
+      const double m = warp_sum(part);
+      const long long row = r0 + r;
+      if (row < n) {
+        const double s = 1.0 / (g[row] * (2.0 / (nu + m)));
+        const double amp = sigma * sqrt(s);
+        if (lane == 0) m_cur[row] = m;
+        for (int i = lane; i < d; i += 32) {
+          const double pr = (mu[i] + keep * diff[r * ld + i]) + amp * lz[r * ld + i];
+          prop64[row * d + i] = pr;
+          if (prop32) prop32[row * d + i] = (float)pr;
+          zz[r * ld + i] = pr - mu[i];
+        }
+      } else {
+        for (int i = lane; i < d; i += 32) zz[r * ld + i] = 0.0;
+      }
+    }
+    __syncthreads();
+    for (int i = c; i < d; i += 128) {
+      const int i2 = i + 64;
+      const bool two = i2 < d;
+      double v[8], v2[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { v[q] = 0.0; v2[q] = 0.0; }
+      for (int j = 0; j < d; ++j) {
+        const double a = inv_t[(size_t)j * d + i], a2 = two ? inv_t[(size_t)j * d + i2] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double dq = zz[(rg * 8 + q) * ld + j];
+          v[q] = fma(a, dq, v[q]);
+          v2[q] = fma(a2, dq, v2[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        vv[(rg * 8 + q) * ld + i] = v[q];
+        if (two) vv[(rg * 8 + q) * ld + i2] = v2[q];
+      }
+    }
+    __syncthreads();
+    for (int r = warp; r < PROP_ROWS; r += 8) {
+      double part = 0.0;
+      for (int i = lane; i < d; i += 32) part = fma(zz[r * ld + i], vv[r * ld + i], part);
+      const double mp = warp_sum(part);
+      if (lane == 0 && r0 + r < n) m_prop[r0 + r] = mp;
+    }
+    __syncthreads();
   }
 }
 
@@ -630,6 +741,20 @@ extern "C" int pmc_tpcn_propose(int32_t pos_is_f32, const void* pos, const doubl
   PMC_REQUIRE(pos && ctl && inv_cov_t && chol_t && g && z && prop64 && m_cur && m_prop, "pmc_tpcn_propose: null pointer");
   PMC_REQUIRE(d >= 1 && d <= 1024, "pmc_tpcn_propose: unsupported dimension");
   if (n == 0) return 0;
+  const size_t tiled_smem = (size_t)4 * PROP_ROWS * (d + 1) * sizeof(double);
+  const char* force_rows = getenv("PMC_TPCN_ROW_KERNEL");          // tests: compare the two kernels bit for bit
+  if (d >= 64 && tiled_smem <= 220 * 1024 && !(force_rows && force_rows[0] == '1')) {
+    const int tblocks = grid_for(n, PROP_ROWS, 1);
+    if (pos_is_f32) {
+      PMC_TRY(cudaFuncSetAttribute(tpcn_propose_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+      tpcn_propose_tiled_kernel<float><<<tblocks, 256, tiled_smem, as_stream(stream)>>>((const float*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+    } else {
+      PMC_TRY(cudaFuncSetAttribute(tpcn_propose_tiled_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+      tpcn_propose_tiled_kernel<double><<<tblocks, 256, tiled_smem, as_stream(stream)>>>((const double*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+    }
+    PMC_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)4 * 3 * d * sizeof(double);
   const int blocks = grid_for(n, 4, 16);
   if (pos_is_f32)
