@@ -312,6 +312,20 @@ def run_b200(args):
         share = max(1, (os.cpu_count() or 1) // world)
         torch.set_num_threads(share)
         try:
+            # ... and on its own block of cores: the ranks meet at every MCMC step (peer-memory exchange of the block partials),
+            # so a host likelihood that migrates between cores or shares one with another rank stalls all of them
+            cores = sorted(os.sched_getaffinity(0))
+            if len(cores) >= world:
+                per = len(cores) // world
+                mine = set(cores[rank * per:(rank + 1) * per])
+                for tid in os.listdir("/proc/self/task"):          # the BLAS / torch worker threads that already exist, too
+                    try:
+                        os.sched_setaffinity(int(tid), mine)
+                    except (OSError, ValueError):
+                        pass
+        except (AttributeError, OSError):
+            pass
+        try:
             from threadpoolctl import threadpool_limits
             threadpool_limits(limits=share)
         except ImportError:
