@@ -312,10 +312,11 @@ def run_b200(args):
         share = max(1, (os.cpu_count() or 1) // world)
         torch.set_num_threads(share)
         try:
-            # ... and on its own block of cores: the ranks meet at every MCMC step (peer-memory exchange of the block partials),
-            # so a host likelihood that migrates between cores or shares one with another rank stalls all of them
-            cores = sorted(os.sched_getaffinity(0))
-            if len(cores) >= world:
+            # PMC_BENCH_PIN=1: ... and on its own block of cores (the ranks meet at every MCMC step).  Off by default: on the
+            # 8-GPU box of this pool a contiguous split measured no better than the scheduler's own placement (e2e 69.6 M
+            # pinned vs 74.7 M unpinned at N = 8; the split ignores which socket a rank's GPU hangs off)
+            cores = sorted(os.sched_getaffinity(0)) if os.environ.get("PMC_BENCH_PIN") == "1" else []
+            if cores and len(cores) >= world:
                 per = len(cores) // world
                 mine = set(cores[rank * per:(rank + 1) * per])
                 for tid in os.listdir("/proc/self/task"):          # the BLAS / torch worker threads that already exist, too
