@@ -358,10 +358,9 @@ class TcLayout:
     to 8 for l = 0 else H; N_l = 2D padded to 16 for l = L else H) and every k-chunk of <= 32 columns:
     a TF32 ``hi`` image and a ``lo`` image, each in the no-swizzle K-major UMMA layout
     ``[k/4][N_l][4]`` (16-byte chunk of 4 consecutive k for output row n at (k/4)*N_l*16 + n*16), the
-    MADE mask folded in (masked entries are 0).  The last chunk of a layer ends with the bias k-step
-    ``[2][N_l][4]`` whose k = 0 / k = 1 entries are hi(b) / lo(b) (multiplied on the tensor core by a
-    constant (1, 1, 0, ...) A block).  ``gather`` codes: >= 0 hi(raw[g]); -(g+2) lo(raw[g]);
-    g | 2^30 plain copy; -1 zero."""
+    MADE mask folded in (masked entries are 0).  Behind the chunks of a transform, at ``bias_off``, the plain fp32
+    biases ``[L][H]`` + ``[Nout]`` (added by the epilogue threads out of shared memory).  ``gather`` codes:
+    >= 0 hi(raw[g]); -(g+2) lo(raw[g]); g | 2^30 plain copy; -1 zero."""
     tstride: int
     bias_off: int
     slot_bytes: int
@@ -406,26 +405,23 @@ def build_tc(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: 
                 blk = idx[:, c0:c0 + kc].reshape(N, kc // 4, 4).transpose(1, 0, 2).reshape(-1)   # [k/4][N][4]
                 parts.append(blk)                                    # hi image
                 parts.append(np.where(blk >= 0, -(blk + 2), -1))     # lo image
-                nbytes = 2 * kc * N * 4
-                if c0 + kc >= K:                                     # bias k-step [2][N][4]: k = 0 -> hi(b), k = 1 -> lo(b)
-                    bidx = base_r + raw_off[2 * l + 1] + np.arange(N_true)
-                    bb = np.full((2, N, 4), -1, np.int64)
-                    bb[0, :N_true, 0] = bidx
-                    bb[0, :N_true, 1] = -(bidx + 2)
-                    parts.append(bb.reshape(-1))
-                    nbytes += N * 32
-                max_chunk = max(max_chunk, nbytes)
+                max_chunk = max(max_chunk, 2 * kc * N * 4)
                 if t == 0:
                     n_chunks += 1
         w_floats = int(sum(len(a) for a in parts))
+        for l in range(L + 1):                                       # plain fp32 biases behind the chunks: [L][H] then [Nout]
+            N_true, N = (D * total, Nout) if l == L else (H, H)
+            bb = np.full(N, -1, np.int64)
+            bb[:N_true] = (base_r + raw_off[2 * l + 1] + np.arange(N_true)) | TC_BIAS_FLAG
+            parts.append(bb)
         parts_all.append(np.concatenate(parts))
     tstride = len(parts_all[0])
-    assert tstride % 4 == 0 and w_floats % 4 == 0
+    assert tstride % 4 == 0 and w_floats % 4 == 0 and tstride == w_floats + L * H + Nout
     gather = np.concatenate(parts_all)
     slot_bytes = (max_chunk + 1023) // 1024 * 1024
     meta = np.zeros(TC_LEN, np.int64)
     meta[[TC_D, TC_H, TC_L, TC_T, TC_KIND, TC_KX, TC_NOUT, TC_TSTRIDE, TC_BIAS_OFF, TC_NCHUNKS, TC_SLOT_BYTES, TC_VERSION]] = \
-        [D, H, L, T, kind, Kx, Nout, tstride, w_floats, n_chunks, slot_bytes, 100]
+        [D, H, L, T, kind, Kx, Nout, tstride, w_floats, n_chunks, slot_bytes, 101]
     assert np.abs(gather).max() < 2 ** 31
     return TcLayout(tstride, w_floats, slot_bytes, n_chunks, meta.astype(np.int32), gather.astype(np.int32))
 
