@@ -560,7 +560,7 @@ def aux_measurements(flow, peaks, n_dim):
         l = torch.empty(n, device="cuda")
         lay = mod.layout
         kx, nout, h = (n_dim + 7) // 8 * 8, (2 * n_dim + 15) // 16 * 16, lay.n_hidden
-        per_t = 2 * (kx * h + (lay.n_layers - 1) * h * h + h * nout) + 2 * 8 * (lay.n_layers * h + nout)
+        per_t = 2 * (kx * h + (lay.n_layers - 1) * h * h + h * nout)          # dense masked-MLP pass (biases are added by the epilogue)
         ms3 = timeit(lambda: mod.forward_tc_into(x, z, l, 3), 10)
         issued = 3 * per_t * lay.n_transforms * n / (ms3 * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops", 1590.0))
