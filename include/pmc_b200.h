@@ -194,6 +194,14 @@ int pmc_scaler_inverse(int32_t u_is_f32, const void* u_in, const pmc_scaler* sc,
                        double* x, double* logdetj, uint8_t* finite, int64_t n, int32_t d,
                        pmc_stream_t stream);
 
+/* pmc_scaler_inverse followed by pmc_logprior (below) on the x it produced, in one launch: what an MCMC step needs between
+ * the flow pull-back and the likelihood call (mcmc.py:91-109) when the prior is a product of norm / uniform factors.
+ * logp [N] f64; finite also drops the rows whose log-prior is not finite.  Same numbers as the two separate calls.   */
+int pmc_scaler_inverse_prior(int32_t u_is_f32, const void* u_in, const pmc_scaler* sc, const int32_t* prior_kind,
+                             const double* prior_loc, const double* prior_scale, double* u_out, double* x,
+                             double* logdetj, uint8_t* finite, double* logp, int64_t n, int32_t d,
+                             pmc_stream_t stream);
+
 /* Reparameterize.forward (scaler.py:180-202): x -> u (no bounds check; host validates). */
 int pmc_scaler_forward(const double* x, const pmc_scaler* sc, double* u, int64_t n, int32_t d,
                        pmc_stream_t stream);
@@ -383,6 +391,20 @@ int pmc_loglike(int32_t which, const double* x, const uint8_t* finite, const dou
  * Also ANDs isfinite(logp) into `finite` (mcmc.py:108-109).                                     */
 int pmc_logprior(const double* x, uint8_t* finite, const int32_t* kind, const double* loc,
                  const double* scale, double* logp, int64_t n, int32_t d, pmc_stream_t stream);
+
+/* ---- host staging of an MCMC step (mcmc.py:111-121: the likelihood is a host callable) ---------
+ * x' [N,D] f64 leaves the GPU every step and logl' [N] returns.  pmc_download_rows queues, on `stream`, the copy of the
+ * finite flags (may be NULL) followed by the rows of x' in n_chunks contiguous chunks of ceil(N / n_chunks) rows, and
+ * records events[k] behind chunk k: the host waits for chunk k with pmc_event_synchronize and evaluates the likelihood of
+ * those rows while the later chunks are still crossing the PCIe bus.  Host pointers must be page-locked.
+ * pmc_memcpy_async: cudaMemcpyAsync(cudaMemcpyDefault) for the small per-step arrays (logl', the controller block).     */
+int pmc_event_create(void** event_out);
+int pmc_event_destroy(void* event);
+int pmc_event_synchronize(void* event);
+int pmc_stream_synchronize(pmc_stream_t stream);
+int pmc_memcpy_async(void* dst, const void* src, int64_t bytes, pmc_stream_t stream);
+int pmc_download_rows(const double* x_dev, double* x_host, const uint8_t* flag_dev, uint8_t* flag_host,
+                      int64_t n, int32_t d, int32_t n_chunks, void* const* events, pmc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pmc_tpcn_propose": (C.c_int, [_I32, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_rwm_propose": (C.c_int, [_I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_scaler_inverse": (C.c_int, [_I32, _P, C.POINTER(PmcScaler), _P, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_scaler_inverse_prior": (C.c_int, [_I32, _P, C.POINTER(PmcScaler), _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_scaler_forward": (C.c_int, [_P, C.POINTER(PmcScaler), _P, _I64, _I32, _P]),
     "pmc_apply_bc": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "pmc_mh_partials_size": (_I64, [_I64, _I32]),
@@ -76,6 +77,12 @@ SIGNATURES = {
     "pmc_lse_bootstrap_rng": (C.c_int, [_P, _I64, _I64, _U64, _P, _P]),
     "pmc_loglike": (C.c_int, [_I32, _P, _P, _P, _F64, _F64, _P, _I64, _I32, _P]),
     "pmc_logprior": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "pmc_event_create": (C.c_int, [_P]),
+    "pmc_event_destroy": (C.c_int, [_P]),
+    "pmc_event_synchronize": (C.c_int, [_P]),
+    "pmc_stream_synchronize": (C.c_int, [_P]),
+    "pmc_memcpy_async": (C.c_int, [_P, _P, _I64, _P]),
+    "pmc_download_rows": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
 }
 
 _lib = None
@@ -168,18 +175,48 @@ def call(name: str, *args):
     check(getattr(lib, name)(*args, stream_ptr()), name)
 
 
-def bind(name: str, *args):
+def bind(name: str, *args, kernel: bool = True, stream: bool = True):
     """Pre-bound call for per-step hot loops: the argument tuple (fixed device pointers, sizes) is converted once;
-    every invocation only looks up the current stream.  Same error behaviour as ``call``."""
+    every invocation only looks up the current stream.  Same error behaviour as ``call``.  ``kernel=False``: the entry
+    point launches no kernel (copies, events) and is left out of ``entry_calls``; ``stream=False``: it takes no stream."""
     require_cuda()
     fn = getattr(load(), name)
     get_stream, get_dev = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice
 
     counter = _entry_calls
+    inc = 1 if kernel else 0
+
+    if not stream:
+        def run_plain():
+            code = fn(*args)
+            if code != 0:
+                check(code, name)
+        return run_plain
 
     def run():
-        counter[0] += 1
+        counter[0] += inc
         code = fn(*args, C.c_void_p(get_stream(get_dev())))
         if code != 0:
             check(code, name)
     return run
+
+
+class Events:
+    """A few CUDA events (timing disabled) for the chunked x' download of the MCMC step; process-wide cache by count."""
+    _cache = {}
+
+    def __init__(self, k: int):
+        lib = load()
+        self.handles = (C.c_void_p * k)()
+        for i in range(k):
+            h = C.c_void_p()
+            check(lib.pmc_event_create(C.byref(h)), "pmc_event_create")
+            self.handles[i] = h
+        self.wait = [bind("pmc_event_synchronize", C.c_void_p(self.handles[i]), stream=False) for i in range(k)]
+
+    @classmethod
+    def get(cls, k: int) -> "Events":
+        dev = torch.cuda.current_device()
+        if (dev, k) not in cls._cache:
+            cls._cache[(dev, k)] = cls(k)
+        return cls._cache[(dev, k)]

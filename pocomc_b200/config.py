@@ -41,6 +41,14 @@ p2p_exchange
     run (mean acceptance, mean theta, tracked log-density over ALL particles) is exchanged by the accept kernel itself
     through peer memory over NVLink (csrc/mcmc_ops.cu: mh_accept_kernel<2>, pmc_comm_*); False: NCCL all-gather of the block
     partials followed by pmc_mcmc_finalize (also what gloo test set-ups with two ranks on one GPU use).
+host_chunks
+    0 (default): automatic.  With a host likelihood, x' leaves the GPU in this many contiguous row chunks per MCMC step and
+    the likelihood is called once per chunk as soon as the chunk has landed, so the remaining copies overlap the host's
+    work (4 chunks once x' is 1 MB or more, otherwise 1; always 1 with blobs).  Row-wise independence of the
+    likelihood is the reference's own contract (``vectorize`` / ``pool``, sampler.py:807-861).  1: one call per step.
+fuse_prior
+    True (default): the device form of the prior is evaluated inside the reparameterisation kernel
+    (``pmc_scaler_inverse_prior``, one launch less per step, same numbers); False: ``pmc_scaler_inverse`` + ``pmc_logprior``.
 """
 import os
 
@@ -57,6 +65,8 @@ device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
 # experimental: under torch.distributed every rank stores only its block of the particle history (pocomc_b200.sharded)
 shard_history = os.environ.get("PMC_B200_SHARD_HISTORY", "0") == "1"
 p2p_exchange = os.environ.get("PMC_B200_P2P", "1") == "1"
+host_chunks = int(os.environ.get("PMC_B200_HOST_CHUNKS", "0"))
+fuse_prior = os.environ.get("PMC_B200_FUSE_PRIOR", "1") == "1"
 
 
 def set_rng_mode(mode: str):

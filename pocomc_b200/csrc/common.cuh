@@ -43,6 +43,31 @@ static inline int grid_for(long long work, int per_block, int per_sm) {
   return (int)b;
 }
 
+// ---- programmatic dependent launch (the kernels of one MCMC step form a dependent chain of short launches) ----------
+// Every chain kernel starts with pdl_enter(): it lets the NEXT launch of the stream start being scheduled right away
+// (griddepcontrol.launch_dependents) and then waits until the PREVIOUS launch has completed and its writes are visible
+// (griddepcontrol.wait) -- nothing before the wait may touch memory a previous kernel writes.  launch_chain() marks a launch
+// as allowed to start early; without the attribute both instructions are no-ops.  PMC_B200_PDL=0 turns the attribute off.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -402,6 +402,10 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
   unsigned char* dring = ring + (size_t)p.stages * p.slot_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // programmatic dependent launch: the next kernel of the MCMC step may be scheduled now; this kernel's own set-up
+  // (tables -- written once when the layout is built --, descriptor words, mbarriers, the TMEM allocation) overlaps the
+  // tail of the previous kernel, and pdl_wait() below comes before the first read of anything a kernel produces
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < p.NB * TB_FIELDS; i += blockDim.x) (&sh.blocks[0][0])[i] = p.tables[i];
   for (int i = threadIdx.x; i < p.NW * TW_FIELDS; i += blockDim.x) (&sh.wins[0][0])[i] = p.tables[p.NB * TB_FIELDS + i];
   __syncthreads();
@@ -440,6 +444,7 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tm = sh.tmem_slot;
   const long long n_tiles = (p.n + 127) / 128;
   float* ws = p.ws + (size_t)blockIdx.x * (size_t)p.ws_floats;
@@ -745,11 +750,11 @@ extern "C" int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host,
   if (inverse) {
     auto kern = made_sweep_tri_kernel<true>;
     PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TRI_THREADS, smem, st>>>(q);
+    PMC_TRY(launch_chain(kern, dim3(grid), dim3(TRI_THREADS), smem, st, q));
   } else {
     auto kern = made_sweep_tri_kernel<false>;
     PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TRI_THREADS, smem, st>>>(q);
+    PMC_TRY(launch_chain(kern, dim3(grid), dim3(TRI_THREADS), smem, st, q));
   }
   PMC_LAUNCH_CHECK();
   return 0;

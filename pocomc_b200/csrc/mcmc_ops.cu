@@ -14,13 +14,17 @@ constexpr int ROWS_PER_BLOCK = 256;  // accept kernel: fixed row->block map => d
 // ------------------------------------------------------------------------------------------
 // proposals
 // ------------------------------------------------------------------------------------------
-template <typename PosT>
+// DT > 0: the dimension as a compile-time constant (the loops unroll completely and the index arithmetic folds: the
+// kernel is instruction-issue bound, ncu r2ax); DT = 0: any d.  Same arithmetic either way.
+template <typename PosT, int DT>
 __global__ void __launch_bounds__(128)
 tpcn_propose_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl,
                     const double* __restrict__ inv_t, const double* __restrict__ chol_t, double nu,
                     const double* __restrict__ g, const double* __restrict__ z,
                     double* __restrict__ prop64, float* __restrict__ prop32,
-                    double* __restrict__ m_cur, double* __restrict__ m_prop, long long n, int d) {
+                    double* __restrict__ m_cur, double* __restrict__ m_prop, long long n, int d_rt) {
+  const int d = DT > 0 ? DT : d_rt;
+  pdl_enter();
   extern __shared__ double sh[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* diff = sh + (size_t)warp * 3 * d;
@@ -87,6 +91,7 @@ tpcn_propose_tiled_kernel(const PosT* __restrict__ pos, const double* __restrict
                           double* __restrict__ prop64, float* __restrict__ prop32,
                           double* __restrict__ m_cur, double* __restrict__ m_prop, long long n, int d) {
   extern __shared__ double sh[];
+  pdl_enter();
   const int ld = d + 1;
   double* diff = sh;                          // [32][ld]  theta - mu
   double* zz = diff + PROP_ROWS * ld;         // [32][ld]  z, later the proposal's offset from mu
@@ -189,6 +194,7 @@ rwm_propose_kernel(const PosT* __restrict__ pos, const double* __restrict__ ctl,
                    const double* __restrict__ chol_t, const double* __restrict__ z,
                    double* __restrict__ prop64, float* __restrict__ prop32, long long n, int d) {
   extern __shared__ double sh[];
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* zz = sh + (size_t)warp * d;
   const double sigma = ctl[PMC_CTL_SIGMA];
@@ -251,15 +257,29 @@ __device__ __forceinline__ double wrap_bc(double x, int bc, double lo, double hi
   return x;
 }
 
-template <typename UT>
+// log-density of one factor of a product prior: kind 0 = norm(loc, scale), 1 = uniform(loc, loc + scale)
+// (scipy.stats logpdf formulas; prior.py:36-44 sums the factors)
+__device__ __forceinline__ double prior_term(int kind, double loc, double scale, double v) {
+  if (kind == 0) {
+    const double t = (v - loc) / scale;
+    return -0.5 * t * t - 0.91893853320467267 - log(scale);
+  }
+  return (v >= loc && v <= loc + scale) ? -log(scale) : -INFINITY;
+}
+
+// PRIOR: the product prior of the proposed x' (logprior_kernel below) is evaluated in the same pass, on the x' values
+// this kernel has just produced -- one launch less per MCMC step, identical numbers.
+template <typename UT, bool PRIOR>
 __global__ void __launch_bounds__(256)
 scaler_inverse_kernel(const UT* __restrict__ u_in, pmc_scaler sc, double* __restrict__ u_out,
                       double* __restrict__ x_out, double* __restrict__ logdetj,
-                      uint8_t* __restrict__ finite, long long n, int d) {
+                      uint8_t* __restrict__ finite, const int* __restrict__ pkind, const double* __restrict__ ploc,
+                      const double* __restrict__ pscale, double* __restrict__ logp, long long n, int d) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
-    double jsum = 0.0;
+    double jsum = 0.0, ps = 0.0;
     int ok = 1;
     for (int j = lane; j < d; j += 32) {
       double uu = (double)u_in[row * d + j];
@@ -279,13 +299,20 @@ scaler_inverse_kernel(const UT* __restrict__ u_in, pmc_scaler sc, double* __rest
       x_out[row * d + j] = xx;
       jsum += J;
       ok &= isfinite(xx) ? 1 : 0;
+      if (PRIOR) ps += prior_term(pkind[j], ploc[j], pscale[j], xx);
     }
     jsum = warp_sum(jsum);
     ok = warp_and(ok);
+    if (PRIOR) ps = warp_sum(ps);
     if (lane == 0) {
       const double ld = (sc.scale ? sc.log_sigma_sum : 0.0) + jsum;
       logdetj[row] = ld;
-      finite[row] = (uint8_t)(ok && isfinite(ld));
+      int fin = ok && isfinite(ld);
+      if (PRIOR) {                       // logprior_kernel's rule: -inf on rows already out, rows with a non-finite prior go out
+        logp[row] = fin ? ps : -INFINITY;
+        if (fin && !isfinite(ps)) fin = 0;
+      }
+      finite[row] = (uint8_t)fin;
     }
   }
 }
@@ -365,9 +392,10 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
                  const CommDev* __restrict__ comm, long long n_global) {
   constexpr bool FUSED = MODE != 0;
   extern __shared__ double sh[];  // [8 warps][d] theta sums + [8][4] scalars
-  __shared__ float fin_tile[MODE == 1 ? FIN_TILE_FLOATS + FIN_TILE_COLS : 1];
+  __shared__ __align__(16) float fin_tile[FUSED ? FIN_TILE_FLOATS + FIN_TILE_COLS : 1];   // finalize: staging of the block partials / of theta
   __shared__ unsigned int is_last;
   __shared__ unsigned long long epoch_sh;
+  pdl_enter();
   if (FUSED && ctl[PMC_CTL_STOP] != 0.0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* th = sh + (size_t)warp * d;
@@ -406,17 +434,17 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
   const double s_alpha = warp_sum(alpha), s_track = warp_sum(track);
   const int s_fin = __popc(__ballot_sync(FULL, fin));
   // masked row copy + per-column theta sums.  A lane owns column j and walks the warp's 32 rows in ascending order
-  // (the order fixes the f64 sum bit for bit); rows go in batches of 8 whose loads are all issued before the first
+  // (the order fixes the f64 sum bit for bit); rows go in batches of 16 whose loads are all issued before the first
   // use -- one dependent round trip per batch instead of per row (the loop was 32 serial L2 latencies, 30 us at
   // 10 000 particles).
   for (int j = lane; j < d; j += 32) {
     double tsum = 0.0;
 #pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += 8) {
-      float pv[8];
-      double uu[8], xx[8];
+    for (int r0 = 0; r0 < 32; r0 += 16) {
+      float pv[16];
+      double uu[16], xx[16];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 16; ++q) {
         const long long rw = base + r0 + q;
         const bool a = (ballot >> (r0 + q)) & 1u;         // accepted rows are valid rows
         const long long o = rw * d + j;
@@ -430,7 +458,7 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
         }
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 16; ++q) {
         const long long rw = base + r0 + q;
         const long long o = rw * d + j;
         if ((ballot >> (r0 + q)) & 1u) {
@@ -491,28 +519,57 @@ mh_accept_kernel(int kind, double beta, double nu, float* __restrict__ pos32, do
 }
 
 // sigma / mu adaptation and the plateau rule from the block partials (mcmc.py:152-180); one 256-thread block.
-// tot: [d + 4] doubles of shared memory, tile: [FIN_TILE_FLOATS + FIN_TILE_COLS] floats of shared memory.
+// tot: [d + 6] doubles of shared memory, tile: [FIN_TILE_FLOATS + FIN_TILE_COLS] floats of shared memory (8-byte aligned).
 __device__ __forceinline__ void finalize_body(int kind, double* __restrict__ ctl, const double* __restrict__ partials, int n_blocks,
                                               const float* __restrict__ pos32, int mean_mode, int n_steps, int n_max, long long n, int d,
                                               double* tot, float* tile) {
   constexpr int TILE_FLOATS = FIN_TILE_FLOATS, TILE_COLS = FIN_TILE_COLS;
   const bool tpf = (kind == PMC_KIND_TPCN_FLOW);
   const bool seq_mean = tpf && mean_mode != 0;
-  for (int j = threadIdx.x; j < d + 4; j += blockDim.x) {
-    if (j >= 4 && seq_mean) continue;                          // filled by the tiled pass below
-    double s = 0.0;
-    if (j < 4 || tpf) {
+  const int w = d + 4;
+  // Column sums of the block partials, added in block order (fixed: the result does not depend on the launch).  The
+  // partials of a chunk of blocks are staged through shared memory by ALL threads with coalesced, independent loads
+  // (one round trip to L2 per chunk); the thread that owns a column then adds its entries in block order.  Only the
+  // d + 4 column owners used to be busy, each with one dependent round trip per 8 blocks.
+  double* stage = reinterpret_cast<double*>(tile);
+  constexpr int STAGE_DOUBLES = (FIN_TILE_FLOATS + FIN_TILE_COLS) / 2;
+  const int cb = STAGE_DOUBLES / w;                            // blocks per chunk (0: a row of partials does not fit)
+  for (int j = threadIdx.x; j < w; j += blockDim.x) tot[j] = 0.0;
+  // the two pow() of the adaptation that do not depend on the sums are evaluated meanwhile by otherwise idle lanes
+  double* pre = tot + w;                                       // [0] = 2.38 / sqrt(d), [1] = (step + 1)^-0.75 weight
+  if (threadIdx.x == 64) pre[0] = 2.38 / pow((double)d, 0.5);
+  if (threadIdx.x == 96) pre[1] = 1.0 / pow(ctl[PMC_CTL_STEP] + 1.0 + 1.0, 0.75);
+  if (cb >= 1) {
+    for (int b0 = 0; b0 < n_blocks; b0 += cb) {
+      const int nb = min(cb, n_blocks - b0);
+      __syncthreads();
+      const double* src = partials + (size_t)b0 * w;
+      for (int e = threadIdx.x; e < nb * w; e += blockDim.x) stage[e] = src[e];
+      __syncthreads();
+      for (int j = threadIdx.x; j < w; j += blockDim.x) {
+        if ((j >= 4 && seq_mean) || !(j < 4 || tpf)) continue;
+        double s = tot[j];
+        for (int b = 0; b < nb; ++b) s += stage[b * w + j];
+        tot[j] = s;
+      }
+    }
+  } else {
+    for (int j = threadIdx.x; j < w; j += blockDim.x) {
+      if ((j >= 4 && seq_mean) || !(j < 4 || tpf)) continue;
+      double s = 0.0;
       for (int b0 = 0; b0 < n_blocks; b0 += 8) {              // 8 loads in flight, added in block order
         double v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (b0 + q < n_blocks) ? partials[(size_t)(b0 + q) * (d + 4) + j] : 0.0;
+        for (int q = 0; q < 8; ++q) v[q] = (b0 + q < n_blocks) ? partials[(size_t)(b0 + q) * w + j] : 0.0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) if (b0 + q < n_blocks) s += v[q];
       }
-      if (j >= 4) s /= (double)n;
+      tot[j] = s;
     }
-    tot[j] = s;
   }
+  __syncthreads();                                             // the staging area is reused by the sequential mean below
+  if (tpf && !seq_mean)
+    for (int j = 4 + threadIdx.x; j < w; j += blockDim.x) tot[j] /= (double)n;
   if (seq_mean) {
     // np.mean(theta, axis=0) on the f32 theta array (mcmc.py:156): per column a SEQUENTIAL f32 accumulation over the
     // rows in ascending order and an f32 divide.  The order is kept exactly; what changes is how the rows reach the
@@ -549,9 +606,9 @@ __device__ __forceinline__ void finalize_body(int kind, double* __restrict__ ctl
     const double mean_alpha = tot[0] / (double)n;
     const double track = tot[1] / (double)n;
     double sigma = ctl[PMC_CTL_SIGMA];
-    const double cap = 2.38 / pow((double)d, 0.5);
+    const double cap = pre[0];                                 // 2.38 / pow(d, 0.5)
     if (kind == PMC_KIND_TPCN_FLOW || kind == PMC_KIND_TPCN)
-      sigma = fabs(fmin(sigma + 1.0 / pow(step + 1.0, 0.75) * (mean_alpha - 0.234), fmin(cap, 0.99)));  // mcmc.py:152
+      sigma = fabs(fmin(sigma + pre[1] * (mean_alpha - 0.234), fmin(cap, 0.99)));  // mcmc.py:152, pre[1] = 1 / pow(step + 1, 0.75)
     else if (kind == PMC_KIND_RWM_FLOW)
       sigma = sigma + 1.0 / (step + 1.0) * (mean_alpha - 0.234);                                         // mcmc.py:314
     else
@@ -580,8 +637,9 @@ __device__ __forceinline__ void finalize_body(int kind, double* __restrict__ ctl
 __global__ void __launch_bounds__(256)
 mcmc_finalize_kernel(int kind, double* __restrict__ ctl, const double* __restrict__ partials, int n_blocks,
                      const float* __restrict__ pos32, int mean_mode, int n_steps, int n_max, long long n, int d) {
-  extern __shared__ double tot[];  // [d + 4]
-  __shared__ float tile[FIN_TILE_FLOATS + FIN_TILE_COLS];   // [rows][cols + 1] staging of theta for the sequential mean
+  extern __shared__ double tot[];  // [d + 6]
+  __shared__ __align__(16) float tile[FIN_TILE_FLOATS + FIN_TILE_COLS];   // staging: block partials, then [rows][cols + 1] of theta for the sequential mean
+  pdl_enter();
   finalize_body(kind, ctl, partials, n_blocks, pos32, mean_mode, n_steps, n_max, n, d, tot, tile);
 }
 
@@ -614,24 +672,32 @@ __device__ __forceinline__ void box_muller(uint4 c, double& n0, double& n1) {
   n0 = rad * cs; n1 = rad * sn;
 }
 
+// Thread map: the first n * ceil(d / 2) threads draw one pair of normals each, the next n threads one uniform + one gamma
+// each -- every warp runs ONE of the two code paths (a per-row interleave made every warp pay for both: the gamma path
+// is as long as the normal path and 1 lane in d/2 + 1 used it).  Counters are keyed by (particle id, step, slot), so the
+// numbers do not depend on the map.
+template <typename IndexT>
 __global__ void __launch_bounds__(256)
 rng_fill_kernel(uint64_t seed, uint64_t step, const double* __restrict__ ctl, long long offset, double shape, double* __restrict__ g,
                 double* __restrict__ z, double* __restrict__ r, long long n, int d) {
+  pdl_enter();
   if (ctl) step = (uint64_t)ctl[PMC_CTL_STEP] + 1;      // the step about to run, read where the previous step left it
   const Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
-  const int half = (d + 1) / 2;
-  const long long total = n * (half + 1);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long row = i / (half + 1);
-    const int slot = (int)(i - row * (half + 1));
-    const unsigned long long pid = (unsigned long long)(row + offset);
-    if (slot < half) {  // two normals
+  const IndexT half = (IndexT)((d + 1) / 2);
+  const IndexT n_normal = (IndexT)n * half, total = n_normal + (IndexT)n;
+  const IndexT stride = (IndexT)gridDim.x * blockDim.x;
+  for (IndexT i = (IndexT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    if (i < n_normal) {  // two normals
+      const IndexT row = i / half;
+      const int slot = (int)(i - row * half);
+      const unsigned long long pid = (unsigned long long)((long long)row + offset);
       double a, b;
       box_muller(ph(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)slot << 8))), a, b);
-      z[row * d + 2 * slot] = a;
-      if (2 * slot + 1 < d) z[row * d + 2 * slot + 1] = b;
+      z[(long long)row * d + 2 * slot] = a;
+      if (2 * slot + 1 < d) z[(long long)row * d + 2 * slot + 1] = b;
     } else {            // uniform + gamma (Marsaglia-Tsang, shape >= 1)
+      const long long row = (long long)(i - n_normal);
+      const unsigned long long pid = (unsigned long long)(row + offset);
       const uint32_t tag = 0x80000000u;
       uint4 c = ph(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), (uint32_t)step, ((uint32_t)(step >> 32)) ^ tag));
       if (r) r[row] = u53(c.x, c.y);
@@ -657,6 +723,17 @@ rng_fill_kernel(uint64_t seed, uint64_t step, const double* __restrict__ ctl, lo
   }
 }
 
+static inline int launch_rng_fill(uint64_t seed, uint64_t step, const double* ctl, long long offset, double shape, double* g, double* z,
+                                  double* r, long long n, int d, cudaStream_t stream) {
+  const long long total = n * ((d + 1) / 2 + 1);
+  const int blocks = grid_for(total, 256, 8);
+  if (total < (1ll << 31) - (long long)blocks * 256)
+    PMC_TRY(launch_chain(rng_fill_kernel<uint32_t>, dim3(blocks), dim3(256), 0, stream, seed, step, ctl, offset, shape, g, z, r, n, d));
+  else
+    PMC_TRY(launch_chain(rng_fill_kernel<long long>, dim3(blocks), dim3(256), 0, stream, seed, step, ctl, offset, shape, g, z, r, n, d));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // synthetic likelihoods / product priors on device (bench + opt-in fast path)
 // ------------------------------------------------------------------------------------------
@@ -665,6 +742,7 @@ loglike_kernel(int which, const double* __restrict__ x, const uint8_t* __restric
                const double* __restrict__ mat_t, double p0, double p1, double* __restrict__ logl,
                long long n, int d) {
   extern __shared__ double sh[];
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* xr = sh + (size_t)warp * d;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -708,19 +786,14 @@ __global__ void __launch_bounds__(256)
 logprior_kernel(const double* __restrict__ x, uint8_t* __restrict__ finite, const int* __restrict__ kind,
                 const double* __restrict__ loc, const double* __restrict__ scale, double* __restrict__ logp,
                 long long n, int d) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
     if (finite && !finite[row]) { if (lane == 0) logp[row] = -INFINITY; continue; }
     double s = 0.0;
     for (int j = lane; j < d; j += 32) {
-      const double v = x[row * d + j];
-      if (kind[j] == 0) {
-        const double t = (v - loc[j]) / scale[j];
-        s += -0.5 * t * t - 0.91893853320467267 - log(scale[j]);
-      } else {
-        s += (v >= loc[j] && v <= loc[j] + scale[j]) ? -log(scale[j]) : -INFINITY;
-      }
+      s += prior_term(kind[j], loc[j], scale[j], x[row * d + j]);
     }
     s = warp_sum(s);
     if (lane == 0) {
@@ -743,24 +816,27 @@ extern "C" int pmc_tpcn_propose(int32_t pos_is_f32, const void* pos, const doubl
   if (n == 0) return 0;
   const size_t tiled_smem = (size_t)4 * PROP_ROWS * (d + 1) * sizeof(double);
   const char* force_rows = getenv("PMC_TPCN_ROW_KERNEL");          // tests: compare the two kernels bit for bit
-  if (d >= 64 && tiled_smem <= 220 * 1024 && !(force_rows && force_rows[0] == '1')) {
+  static const int tiled_min_d = [] { const char* e = getenv("PMC_TPCN_TILED_MIN_D"); return e && e[0] ? atoi(e) : 64; }();
+  if (d >= tiled_min_d && tiled_smem <= 220 * 1024 && !(force_rows && force_rows[0] == '1')) {
     const int tblocks = grid_for(n, PROP_ROWS, 1);
     if (pos_is_f32) {
       PMC_TRY(cudaFuncSetAttribute(tpcn_propose_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
-      tpcn_propose_tiled_kernel<float><<<tblocks, 256, tiled_smem, as_stream(stream)>>>((const float*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+      PMC_TRY(launch_chain(tpcn_propose_tiled_kernel<float>, dim3(tblocks), dim3(256), tiled_smem, as_stream(stream), (const float*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d));
     } else {
       PMC_TRY(cudaFuncSetAttribute(tpcn_propose_tiled_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
-      tpcn_propose_tiled_kernel<double><<<tblocks, 256, tiled_smem, as_stream(stream)>>>((const double*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+      PMC_TRY(launch_chain(tpcn_propose_tiled_kernel<double>, dim3(tblocks), dim3(256), tiled_smem, as_stream(stream), (const double*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d));
     }
     PMC_LAUNCH_CHECK();
     return 0;
   }
   const size_t smem = (size_t)4 * 3 * d * sizeof(double);
   const int blocks = grid_for(n, 4, 16);
-  if (pos_is_f32)
-    tpcn_propose_kernel<float><<<blocks, 128, smem, as_stream(stream)>>>((const float*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+  if (pos_is_f32 && d == 32)
+    PMC_TRY(launch_chain(tpcn_propose_kernel<float, 32>, dim3(blocks), dim3(128), smem, as_stream(stream), (const float*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d));
+  else if (pos_is_f32)
+    PMC_TRY(launch_chain(tpcn_propose_kernel<float, 0>, dim3(blocks), dim3(128), smem, as_stream(stream), (const float*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d));
   else
-    tpcn_propose_kernel<double><<<blocks, 128, smem, as_stream(stream)>>>((const double*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d);
+    PMC_TRY(launch_chain(tpcn_propose_kernel<double, 0>, dim3(blocks), dim3(128), smem, as_stream(stream), (const double*)pos, ctl, inv_cov_t, chol_t, nu, g, z, prop64, prop32, m_cur, m_prop, n, d));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -774,9 +850,9 @@ extern "C" int pmc_rwm_propose(int32_t pos_is_f32, const void* pos, const double
   const size_t smem = (size_t)4 * d * sizeof(double);
   const int blocks = grid_for(n, 4, 16);
   if (pos_is_f32)
-    rwm_propose_kernel<float><<<blocks, 128, smem, as_stream(stream)>>>((const float*)pos, ctl, chol_t, z, prop64, prop32, n, d);
+    PMC_TRY(launch_chain(rwm_propose_kernel<float>, dim3(blocks), dim3(128), smem, as_stream(stream), (const float*)pos, ctl, chol_t, z, prop64, prop32, n, d));
   else
-    rwm_propose_kernel<double><<<blocks, 128, smem, as_stream(stream)>>>((const double*)pos, ctl, chol_t, z, prop64, prop32, n, d);
+    PMC_TRY(launch_chain(rwm_propose_kernel<double>, dim3(blocks), dim3(128), smem, as_stream(stream), (const double*)pos, ctl, chol_t, z, prop64, prop32, n, d));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -788,9 +864,26 @@ extern "C" int pmc_scaler_inverse(int32_t u_is_f32, const void* u_in, const pmc_
   PMC_REQUIRE(sc->kind && sc->low && sc->high && (!sc->scale || (sc->mu && sc->sigma)), "pmc_scaler_inverse: incomplete scaler");
   const int blocks = grid_for(n, 8, 8);
   if (u_is_f32)
-    scaler_inverse_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((const float*)u_in, *sc, u_out, x, logdetj, finite, n, d);
+    PMC_TRY(launch_chain(scaler_inverse_kernel<float, false>, dim3(blocks), dim3(256), 0, as_stream(stream), (const float*)u_in, *sc, u_out, x, logdetj, finite, nullptr, nullptr, nullptr, nullptr, n, d));
   else
-    scaler_inverse_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>((const double*)u_in, *sc, u_out, x, logdetj, finite, n, d);
+    PMC_TRY(launch_chain(scaler_inverse_kernel<double, false>, dim3(blocks), dim3(256), 0, as_stream(stream), (const double*)u_in, *sc, u_out, x, logdetj, finite, nullptr, nullptr, nullptr, nullptr, n, d));
+  PMC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pmc_scaler_inverse_prior(int32_t u_is_f32, const void* u_in, const pmc_scaler* sc, const int32_t* prior_kind,
+                                        const double* prior_loc, const double* prior_scale, double* u_out, double* x,
+                                        double* logdetj, uint8_t* finite, double* logp, int64_t n, int32_t d,
+                                        pmc_stream_t stream) {
+  if (n == 0) return 0;
+  PMC_REQUIRE(u_in && sc && u_out && x && logdetj && finite && logp && prior_kind && prior_loc && prior_scale,
+              "pmc_scaler_inverse_prior: null pointer");
+  PMC_REQUIRE(sc->kind && sc->low && sc->high && (!sc->scale || (sc->mu && sc->sigma)), "pmc_scaler_inverse_prior: incomplete scaler");
+  const int blocks = grid_for(n, 8, 8);
+  if (u_is_f32)
+    PMC_TRY(launch_chain(scaler_inverse_kernel<float, true>, dim3(blocks), dim3(256), 0, as_stream(stream), (const float*)u_in, *sc, u_out, x, logdetj, finite, prior_kind, prior_loc, prior_scale, logp, n, d));
+  else
+    PMC_TRY(launch_chain(scaler_inverse_kernel<double, true>, dim3(blocks), dim3(256), 0, as_stream(stream), (const double*)u_in, *sc, u_out, x, logdetj, finite, prior_kind, prior_loc, prior_scale, logp, n, d));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -835,9 +928,8 @@ extern "C" int pmc_mh_accept_update(int32_t kind, double beta, double nu, float*
   PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_update: tpCN kinds need the Mahalanobis distances");
   if (n == 0) return 0;
   const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
-  mh_accept_kernel<0><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
-      kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
-      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, nullptr, nullptr, 0, 0, 0, nullptr, 0);
+  PMC_TRY(launch_chain(mh_accept_kernel<0>, dim3((unsigned)mh_blocks(n)), dim3(256), smem, as_stream(stream), kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
+      logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, nullptr, nullptr, 0, 0, 0, nullptr, 0));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -859,10 +951,9 @@ extern "C" int pmc_mh_accept_finalize(int32_t kind, double beta, double nu, floa
   PMC_REQUIRE(!tp || (m_cur && m_prop), "pmc_mh_accept_finalize: tpCN kinds need the Mahalanobis distances");
   PMC_REQUIRE(n > 0, "pmc_mh_accept_finalize: empty batch");
   const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
-  mh_accept_kernel<1><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
-      kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
+  PMC_TRY(launch_chain(mh_accept_kernel<1>, dim3((unsigned)mh_blocks(n)), dim3(256), smem, as_stream(stream), kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
       logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, ctl, ticket, mean_mode, n_steps, n_max,
-      nullptr, 0);
+      nullptr, 0));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -982,10 +1073,9 @@ extern "C" int pmc_mh_accept_finalize_p2p(int32_t kind, double beta, double nu, 
   PMC_REQUIRE(bo[c->rank + 1] - bo[c->rank] == (int)mh_blocks(n), "pmc_mh_accept_finalize_p2p: block table does not match this rank's batch");
   PMC_REQUIRE((long long)bo[c->world] * (d + 4) <= c->capacity, "pmc_mh_accept_finalize_p2p: exchange buffer too small");
   const size_t smem = ((size_t)8 * d + 32) * sizeof(double);
-  mh_accept_kernel<2><<<(unsigned)mh_blocks(n), 256, smem, as_stream(stream)>>>(
-      kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
+  PMC_TRY(launch_chain(mh_accept_kernel<2>, dim3((unsigned)mh_blocks(n)), dim3(256), smem, as_stream(stream), kind, beta, nu, flow ? pos32 : nullptr, u, x, logdetj, logl, logp, logdetj_flow, prop64, u_p, x_p, logdetj_p,
       logl_p, logp_p, logdetj_flow_p, m_cur, m_prop, r, finite, alpha_out, partials, n, d, ctl, ticket, 0, n_steps, n_max,
-      c->dev, n_global);
+      c->dev, n_global));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -995,8 +1085,7 @@ extern "C" int pmc_mcmc_finalize(int32_t kind, double* ctl, const double* partia
                                  int32_t d, pmc_stream_t stream) {
   PMC_REQUIRE(ctl && partials && n > 0, "pmc_mcmc_finalize: bad arguments");
   PMC_REQUIRE(!(kind == PMC_KIND_TPCN_FLOW && mean_mode == 1) || pos32, "pmc_mcmc_finalize: mean_mode 1 needs theta");
-  mcmc_finalize_kernel<<<1, 256, (size_t)(d + 4) * sizeof(double), as_stream(stream)>>>(
-      kind, ctl, partials, (int)(n_blocks > 0 ? n_blocks : mh_blocks(n)), pos32, mean_mode, n_steps, n_max, n, d);
+  PMC_TRY(launch_chain(mcmc_finalize_kernel, dim3(1), dim3(256), (size_t)(d + 6) * sizeof(double), as_stream(stream), kind, ctl, partials, (int)(n_blocks > 0 ? n_blocks : mh_blocks(n)), pos32, mean_mode, n_steps, n_max, n, d));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -1005,8 +1094,7 @@ extern "C" int pmc_rng_fill(uint64_t seed, uint64_t step, int64_t particle_offse
                             double* z, double* r, int64_t n, int32_t d, pmc_stream_t stream) {
   PMC_REQUIRE(z && n >= 0 && d >= 1, "pmc_rng_fill: bad arguments");
   if (n == 0) return 0;
-  const int blocks = grid_for(n * ((d + 1) / 2 + 1), 256, 8);
-  rng_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, step, nullptr, particle_offset, gamma_shape, g, z, r, n, d);
+  if (launch_rng_fill(seed, step, nullptr, particle_offset, gamma_shape, g, z, r, n, d, as_stream(stream))) return 1;
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -1015,8 +1103,7 @@ extern "C" int pmc_rng_fill_ctl(uint64_t seed, const double* ctl, int64_t partic
                                 double* z, double* r, int64_t n, int32_t d, pmc_stream_t stream) {
   PMC_REQUIRE(z && ctl && n >= 0 && d >= 1, "pmc_rng_fill_ctl: bad arguments");
   if (n == 0) return 0;
-  const int blocks = grid_for(n * ((d + 1) / 2 + 1), 256, 8);
-  rng_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seed, 0, ctl, particle_offset, gamma_shape, g, z, r, n, d);
+  if (launch_rng_fill(seed, 0, ctl, particle_offset, gamma_shape, g, z, r, n, d, as_stream(stream))) return 1;
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -1027,7 +1114,7 @@ extern "C" int pmc_loglike(int32_t which, const double* x, const uint8_t* finite
   PMC_REQUIRE(which != PMC_LIKE_GAUSS || mat_t, "pmc_loglike: gauss needs the precision matrix");
   if (n == 0) return 0;
   const int blocks = grid_for(n, 4, 16);
-  loglike_kernel<<<blocks, 128, (size_t)4 * d * sizeof(double), as_stream(stream)>>>(which, x, finite, mat_t, p0, p1, logl, n, d);
+  PMC_TRY(launch_chain(loglike_kernel, dim3(blocks), dim3(128), (size_t)4 * d * sizeof(double), as_stream(stream), which, x, finite, mat_t, p0, p1, logl, n, d));
   PMC_LAUNCH_CHECK();
   return 0;
 }
@@ -1037,7 +1124,7 @@ extern "C" int pmc_logprior(const double* x, uint8_t* finite, const int32_t* kin
   PMC_REQUIRE(x && kind && loc && scale && logp, "pmc_logprior: null pointer");
   if (n == 0) return 0;
   const int blocks = grid_for(n, 8, 8);
-  logprior_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, finite, kind, loc, scale, logp, n, d);
+  PMC_TRY(launch_chain(logprior_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), x, finite, kind, loc, scale, logp, n, d));
   PMC_LAUNCH_CHECK();
   return 0;
 }

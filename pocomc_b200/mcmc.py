@@ -59,6 +59,8 @@ class McmcEngine:
             if spec is not None:
                 from .synthetic import DevicePrior
                 self.logprior_device = DevicePrior(*spec)
+        # the device prior rides in the reparameterisation kernel (one launch for u' -> x', logdetj', finite, logp')
+        self.prior_fused = bool(config.fuse_prior and hasattr(self.logprior_device, '_params'))
         self.scaler = function_dict.get('scaler')
         if not hasattr(self.scaler, '_params'):          # e.g. the reference's own Reparameterize (drop-in use from its Sampler)
             from .scaler import Reparameterize
@@ -160,6 +162,7 @@ class McmcEngine:
         self.stop = False
         self._propose = self._scaler_inverse = self._finalize = None       # pre-bound libpmc_b200 calls (built on first use)
         self._rng_fill = self._sweep = self._logprior = None
+        self._download = self._read_ctl = None
         self._stream = torch.cuda.current_stream()     # the engine lives for one kernel call on the caller's stream; looking it up costs ~20 us per step
         self._accept = {}
         self._accept_fused = {}
@@ -220,58 +223,91 @@ class McmcEngine:
         else:
             src, is32 = self.prop64, 0
         if self._scaler_inverse is None:
-            self._scaler_inverse = _lib.bind("pmc_scaler_inverse", is32, _lib.ptr(src), C.byref(self.sc), _lib.ptr(self.u_p),
-                                             _lib.ptr(self.x_p), _lib.ptr(self.ldj_p), _lib.ptr(self.finite), n, d)
+            if self.prior_fused:
+                self._prior_keep = kind, loc, scale = self.logprior_device._params(self.dev)
+                self._scaler_inverse = _lib.bind("pmc_scaler_inverse_prior", is32, _lib.ptr(src), C.byref(self.sc), _lib.ptr(kind),
+                                                 _lib.ptr(loc), _lib.ptr(scale), _lib.ptr(self.u_p), _lib.ptr(self.x_p),
+                                                 _lib.ptr(self.ldj_p), _lib.ptr(self.finite), _lib.ptr(self.logp_p), n, d)
+            else:
+                self._scaler_inverse = _lib.bind("pmc_scaler_inverse", is32, _lib.ptr(src), C.byref(self.sc), _lib.ptr(self.u_p),
+                                                 _lib.ptr(self.x_p), _lib.ptr(self.ldj_p), _lib.ptr(self.finite), n, d)
         self._scaler_inverse()
+
+    def _bind_host_io(self):
+        """Pre-bound staging calls of the host-likelihood step: chunked download of x' (+ finite flags) with one event per
+        chunk, upload of logl' / logp', download of the controller block."""
+        n, d = self.n, self.d
+        k = config.host_chunks
+        if k <= 0:
+            k = 4 if n * d * 8 >= (1 << 20) else 1
+        if self.have_blobs:
+            k = 1
+        k = max(1, min(int(k), n))
+        per = (n + k - 1) // k
+        self._chunks = [(a, min(a + per, n)) for a in range(0, n, per)]
+        k = len(self._chunks)
+        self._events = _lib.Events.get(k)
+        self._download = _lib.bind("pmc_download_rows", _lib.ptr(self.x_p), _lib.ptr(self.h_x), _lib.ptr(self.finite),
+                                   _lib.ptr(self.h_fin), n, d, k, self._events.handles, kernel=False)
+        self._up_logl = _lib.bind("pmc_memcpy_async", _lib.ptr(self.logl_p), _lib.ptr(self.h_ll[0]), n * 8, kernel=False)
+        self._up_logp = _lib.bind("pmc_memcpy_async", _lib.ptr(self.logp_p), _lib.ptr(self.h_ll[1]), n * 8, kernel=False)
 
     def evaluate_host(self):
         """Host black boxes on the finite rows only (mcmc.py:100-121).  When the prior is a
         ``pocomc_b200.Prior`` of frozen scipy norm / uniform factors it is evaluated on the GPU
-        (config.device_prior) and only the likelihood crosses the PCIe bus."""
+        (config.device_prior) and only the likelihood crosses the PCIe bus.  x' comes down in row chunks
+        (config.host_chunks); the callables see each chunk as soon as it has landed."""
         n = self.n
-        if self.logprior_device is not None:
+        if self.logprior_device is not None and not self.prior_fused:
             if self._logprior is None:
                 bind = getattr(self.logprior_device, "bind", None)
                 self._logprior = bind(self.x_p, self.finite, self.logp_p) if bind is not None else \
                     (lambda: self.logprior_device(self.x_p, self.finite, self.logp_p))
             self._logprior()                                                # also clears finite where logp' is not finite
-        self.h_x.copy_(self.x_p, non_blocking=True)
-        self.h_fin.copy_(self.finite, non_blocking=True)
-        self._stream.synchronize()
-        x_p = self.h_x.numpy()
-        mask = self.h_fin.numpy().view(np.bool_)
-        all_rows = bool(mask.all())
+        if self._download is None:
+            self._bind_host_io()
+        self._download()
+        x_all = self.h_x.numpy()
+        mask_all = self.h_fin.numpy().view(np.bool_)
         hl = self.h_ll.numpy()
-        if self.logprior_device is None:
-            logp_p = hl[1]
-            if all_rows:
-                logp_p[:] = self.log_prior(x_p)
-            else:
-                logp_p.fill(-np.inf)
-                logp_p[mask] = self.log_prior(x_p[mask])
-            ok = np.isfinite(logp_p)
-            if not ok.all():
-                mask = mask & ok
-                all_rows = False
-            self.logp_p.copy_(self.h_ll[1], non_blocking=True)
-        logl_p = hl[0]
+        host_prior = self.logprior_device is None
+        calls = 0
         blobs_p = None
-        if all_rows and not self.have_blobs:
-            logl_p[:], _ = self.log_like(x_p)
-        else:
-            logl_p.fill(-np.inf)
-            if self.have_blobs:
-                blobs_p = np.empty(n, dtype=np.dtype((self.blobs[0].dtype, self.blobs[0].shape)))
-                logl_p[mask], blobs_p[mask] = self.log_like(x_p[mask])
+        for (a, b), wait in zip(self._chunks, self._events.wait):
+            wait()
+            x_p, mask = x_all[a:b], mask_all[a:b]
+            all_rows = bool(mask.all())
+            if host_prior:
+                logp_p = hl[1, a:b]
+                if all_rows:
+                    logp_p[:] = self.log_prior(x_p)
+                else:
+                    logp_p.fill(-np.inf)
+                    logp_p[mask] = self.log_prior(x_p[mask])
+                ok = np.isfinite(logp_p)
+                if not ok.all():
+                    mask = mask & ok
+                    all_rows = False
+            logl_p = hl[0, a:b]
+            if all_rows and not self.have_blobs:
+                logl_p[:], _ = self.log_like(x_p)
             else:
-                logl_p[mask], _ = self.log_like(x_p[mask])
-        calls = n if all_rows else int(np.sum(mask))
-        self.logl_p.copy_(self.h_ll[0], non_blocking=True)
+                logl_p.fill(-np.inf)
+                if self.have_blobs:                                          # one chunk: a = 0, b = n
+                    blobs_p = np.empty(n, dtype=np.dtype((self.blobs[0].dtype, self.blobs[0].shape)))
+                    logl_p[mask], blobs_p[mask] = self.log_like(x_p[mask])
+                elif mask.any() or len(self._chunks) == 1:               # a single chunk keeps the reference's call on zero rows
+                    logl_p[mask], _ = self.log_like(x_p[mask])
+            calls += (b - a) if all_rows else int(np.sum(mask))
+        if host_prior:
+            self._up_logp()
+        self._up_logl()
         return calls, blobs_p
 
     def evaluate_device(self):
         """Opt-in device prior / likelihood (synthetic benchmarks): no PCIe traffic."""
-        self.logprior_device(self.x_p, self.finite, self.logp_p)
+        if not self.prior_fused:
+            self.logprior_device(self.x_p, self.finite, self.logp_p)
         self.loglike_device(self.x_p, self.finite, self.logl_p)
         return None, None
 
@@ -327,8 +363,11 @@ class McmcEngine:
             return
 
     def read_controller(self):
-        self.ctl_host.copy_(self.ctl, non_blocking=True)
-        self._stream.synchronize()
+        if self._read_ctl is None:
+            self._read_ctl = (_lib.bind("pmc_memcpy_async", _lib.ptr(self.ctl_host), _lib.ptr(self.ctl), self.ctl.numel() * 8, kernel=False),
+                              _lib.bind("pmc_stream_synchronize", kernel=False))
+        self._read_ctl[0]()
+        self._read_ctl[1]()
         c = self.ctl_host.numpy()
         self.sigma, self.accept = float(c[CTL_SIGMA]), float(c[CTL_ACCEPT])
         self.step, self.stop = int(c[CTL_STEP]), bool(c[CTL_STOP] != 0.0)
@@ -391,7 +430,7 @@ class McmcEngine:
                     self.accept_and_adapt(None)
                 done_before = self.step
                 c = self.read_controller()
-                self.launches += (per_step + 2) * k
+                self.launches += (per_step + (1 if self.prior_fused else 2)) * k
                 step_calls = int(c[CTL_CALLS]) - self.n_calls
                 self.n_calls = int(c[CTL_CALLS])
                 if self.step > done_before or self.stop:
@@ -403,7 +442,8 @@ class McmcEngine:
             self.draw_noise()
             self.propose()
             self.pull_back()
-            self.launches += per_step + (2 if device_eval else 0) + (1 if (not device_eval and self.logprior_device is not None) else 0)
+            self.launches += per_step + ((1 if self.prior_fused else 2) if device_eval else 0) + \
+                (1 if (not device_eval and self.logprior_device is not None and not self.prior_fused) else 0)
             if device_eval:
                 calls, blobs_p = self.evaluate_device()
             else:
