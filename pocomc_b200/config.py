@@ -44,7 +44,7 @@ p2p_exchange
 host_chunks
     0 (default): automatic.  With a host likelihood, x' leaves the GPU in this many contiguous row chunks per MCMC step and
     the likelihood is called once per chunk as soon as the chunk has landed, so the remaining copies overlap the host's
-    work (4 chunks once x' is 1 MB or more, otherwise 1; always 1 with blobs).  Row-wise independence of the
+    work (4 chunks once x' is 16 MB or more, otherwise 1; always 1 with blobs).  Row-wise independence of the
     likelihood is the reference's own contract (``vectorize`` / ``pool``, sampler.py:807-861).  1: one call per step.
 fuse_prior
     True (default): the device form of the prior is evaluated inside the reparameterisation kernel
@@ -65,6 +65,7 @@ device_callbacks = os.environ.get("PMC_B200_DEVICE_CALLBACKS", "0") == "1"
 # experimental: under torch.distributed every rank stores only its block of the particle history (pocomc_b200.sharded)
 shard_history = os.environ.get("PMC_B200_SHARD_HISTORY", "0") == "1"
 p2p_exchange = os.environ.get("PMC_B200_P2P", "1") == "1"
+tri_rqs_min_hidden = int(os.environ.get("PMC_B200_TRI_RQS_MIN_H", "0"))
 host_chunks = int(os.environ.get("PMC_B200_HOST_CHUNKS", "0"))
 fuse_prior = os.environ.get("PMC_B200_FUSE_PRIOR", "1") == "1"
 

@@ -10,6 +10,7 @@
 // (conflict free); the weights of one 4-unit chunk are one 16-byte read-only load shared by the
 // PW lanes of a slice.  fp32 FMA throughout -- the reference flow is fp32 (tools.py:292).
 #include "common.cuh"
+#include "flow_heads.cuh"
 #include <algorithm>
 #include <stdlib.h>
 
@@ -20,76 +21,7 @@ enum { M_D = 0, M_H, M_L, M_T, M_KIND, M_TOTAL, M_TP, M_NG, M_TSTRIDE, M_HP, M_M
        M_OFF_GSTART, M_OFF_NCHUNK, M_OFF_SLOT, M_OFF_W0, M_OFF_WH, M_OFF_WO, M_OFF_B0, M_OFF_BH,
        M_OFF_BO, M_RAW_TSTRIDE, M_BINS, M_VERSION, M_NCHUNKS, M_SLOT_FLOATS, M_OFF_CHUNKS };
 
-constexpr float LOG_SLOPE = -6.90775527898213705205f;  // log(1e-3)
-
-__device__ __forceinline__ float softclip(float a, float ls) { return a / (1.0f + fabsf(a / ls)); }
-
-// ---- univariate transforms -----------------------------------------------------------------
-// zuko MonotonicAffineTransform: y = x*exp(ls) + shift, ls soft-clipped.
-struct Affine {
-  static constexpr int TOTAL = 2, TP = 4;
-  __device__ static __forceinline__ float apply(const float* phi, float v, bool inverse, float& ladj) {
-    const float ls = softclip(phi[1], LOG_SLOPE);
-    ladj = ls;
-    const float sc = expf(ls);
-    return inverse ? (v - phi[0]) / sc : fmaf(v, sc, phi[0]);
-  }
-};
-
-// zuko MonotonicRQSTransform, bins = 8, bound = 5.
-struct Rqs {
-  static constexpr int BINS = 8, TOTAL = 23, TP = 24;
-  __device__ static __forceinline__ void knots(const float* a, float* out /*BINS+1*/) {
-    float c[BINS], mx = -INFINITY, sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < BINS; ++i) { c[i] = softclip(a[i], 0.5f * LOG_SLOPE); mx = fmaxf(mx, c[i]); }
-#pragma unroll
-    for (int i = 0; i < BINS; ++i) { c[i] = expf(c[i] - mx); sum += c[i]; }
-    double acc = 0.0;  // torch's CPU cumsum accumulates float inputs in double
-    out[0] = -5.0f;
-#pragma unroll
-    for (int i = 0; i < BINS; ++i) {
-      acc += (double)(c[i] / sum);
-      out[i + 1] = 5.0f * (2.0f * (float)acc - 1.0f);
-    }
-  }
-  __device__ static __forceinline__ float apply(const float* phi, float v, bool inverse, float& ladj) {
-    float hx[BINS + 1], hy[BINS + 1], dv[BINS + 1];
-    knots(phi, hx);
-    knots(phi + BINS, hy);
-    dv[0] = 1.0f; dv[BINS] = 1.0f;
-#pragma unroll
-    for (int i = 0; i < BINS - 1; ++i) dv[i + 1] = expf(softclip(phi[2 * BINS + i], LOG_SLOPE));
-    int cnt = 0;  // searchsorted(left) = #knots < v
-#pragma unroll
-    for (int i = 0; i <= BINS; ++i) cnt += ((inverse ? hy[i] : hx[i]) < v) ? 1 : 0;
-    const int k = cnt - 1;
-    const bool in = (k >= 0) && (k < BINS);
-    const int kk = ((k % BINS) + BINS) % BINS;
-    float x0 = 0, x1 = 0, y0 = 0, y1 = 0, d0 = 0, d1 = 0;
-#pragma unroll
-    for (int i = 0; i < BINS; ++i)
-      if (i == kk) { x0 = hx[i]; x1 = hx[i + 1]; y0 = hy[i]; y1 = hy[i + 1]; d0 = dv[i]; d1 = dv[i + 1]; }
-    const float s = (y1 - y0) / (x1 - x0);
-    const float t2 = d0 + d1 - 2.0f * s;
-    float x = v, res = v;
-    if (inverse) {
-      const float y_ = in ? (v - y0) : 0.0f;
-      const float a = (y1 - y0) * (s - d0) + y_ * t2;
-      const float b = (y1 - y0) * d0 - y_ * t2;
-      const float c = -s * y_;
-      const float z = 2.0f * c / (-b - sqrtf(b * b - 4.0f * a * c));
-      x = in ? (x0 + z * (x1 - x0)) : v;
-      res = x;
-    }
-    const float z = in ? (x - x0) / (x1 - x0) : 0.0f;
-    const float den = s + t2 * z * (1.0f - z);
-    const float jac = s * s * (2.0f * s * z * (1.0f - z) + d0 * (1.0f - z) * (1.0f - z) + d1 * z * z) / (den * den);
-    ladj = in ? logf(jac) : 0.0f;
-    if (!inverse) res = in ? (y0 + (y1 - y0) * (s * z * z + d0 * z * (1.0f - z)) / den) : v;
-    return res;
-  }
-};
+// univariate heads (zuko MonotonicAffineTransform / MonotonicRQSTransform): flow_heads.cuh
 
 // ---- partial dot products --------------------------------------------------------------------
 // acc[0..3] = sum_{s in slice q} slab[s][col..col+3] * act[s][p], then butterfly over the LPP slices.

@@ -20,11 +20,17 @@
 //   * what stays inside a block -- the dependencies between its own 4 degree groups -- is fp32 FMA work with one
 //     thread per particle: the block's accumulators are pulled out of TMEM into registers (they BECOME the activation
 //     registers), the in-block weights arrive as warp-uniform LDS.128 broadcasts from a slab the producer streamed in;
+//   * spline flows (zuko NSF, the reference's default presets; template parameter RQS) differ in the univariate head only: an
+//     order position owns 24 output columns (8 widths, 8 heights, 7 slopes, one zero column) instead of 2, pulled out of
+//     TMEM position by position; their in-block part is 24 packed-FMA dot products per source unit, then the monotonic
+//     rational-quadratic spline of flow_heads.cuh (the code the fp32-FMA sweep runs); a window holds two blocks (256
+//     output columns, the widest tcgen05.mma);
 //   * weights stream from L2 through two shared-memory rings (update slabs / init chunks, in-block slabs) with 1-D bulk
 //     copies and mbarrier transaction counts; producer lanes, the MMA issuer and the 128 particle threads are coupled
 //     by mbarriers only.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "flow_heads.cuh"
 #include <algorithm>
 #include <stdlib.h>
 
@@ -35,17 +41,18 @@ using namespace tc;
 // header / tables of tri_layout.build_tri -- keep in sync
 enum { TRI_VER = 0, TRI_D, TRI_H, TRI_L, TRI_T, TRI_GSIZE, TRI_NB, TRI_NW, TRI_TSTRIDE, TRI_KCHUNK, TRI_SLOT_BYTES, TRI_DSLOT_BYTES,
        TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_OFF_BLOCKS, TRI_OFF_WINDOWS, TRI_SMEM_BYTES,
-       TRI_NCOLS, TRI_CHUNK_OFF, TRI_HEADER };
+       TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND, TRI_HEADER };
 enum { TB_K0 = 0, TB_NST, TB_NR, TB_W, TB_KP, TB_WIN, TB_WC, TB_OC, TB_DOFF, TB_DN, TB_KS, TB_UPD_N, TB_UPD_DCOL, TB_OUT_N, TB_OUT_DCOL,
        TB_FLAGS, TB_FIELDS };
 enum { TW_B0 = 0, TW_NB, TW_WP, TW_OP, TW_COL_OUT, TW_KH, TW_KX, TW_PAD, TW_FIELDS };
 enum { TBF_LAST_IN_WIN = 1, TBF_LAST = 2 };
 
-constexpr int TRI_LAYOUT_VERSION = 300;
+constexpr int TRI_LAYOUT_VERSION = 301;
 constexpr int TRI_MAX_STAGES = 8;          // ring depth: as many slots as fit, decided by tri_layout.build_tri
 constexpr int TRI_MAX_SLOTS = 12;          // + the slots a window initialisation borrows from the (then idle) A-tile area
 constexpr int TRI_MAX_BLOCKS = 64;
-constexpr int TRI_MAX_WINDOWS = 16;
+constexpr int TRI_MAX_WINDOWS = 32;
+constexpr int TRI_P_RQS = 24;             // tensor-memory columns per order position of a spline flow: 23 parameters + a zero column
 constexpr int TRI_THREADS = 224;           // warps 0-3 particles, 4 ring producer, 5 MMA issuer, 6 in-block slab producer
 constexpr int G = 4;                       // order positions per block
 constexpr float TRI_LOG_SLOPE = -6.90775527898213705205f;
@@ -200,13 +207,84 @@ __device__ __forceinline__ void tri_hidden(const float4* __restrict__ q, int& of
   relu_into<NR, J>(dst, acc);
 }
 
-// order position J of a block: output -> affine map -> the degree group's three hidden layers
+// spline head of order position J: the 24 parameter columns of the position (accumulators in tensor memory: everything
+// earlier blocks contribute) + bias + the contribution of the block's own earlier groups, then the spline itself.
+// In-block slab: 6 float4 of bias, then per source unit (4 regular units of a group, then its extras) 6 float4 = the
+// unit's weight into parameters 0..23.
 template <int NR, bool INV, int J>
-__device__ __forceinline__ void tri_stage(const float4* __restrict__ q, int& off, TriActs& a1, TriActs& a2, TriActs& a3,
-                                          const uint32_t (&o)[2 * G], float2 (&xbp)[G / 2], const float (&y)[G], float& ladj,
-                                          float* __restrict__ out_row, const bool valid, const int kstep, const int feat0) {
-  using S = TriShape<NR>;
+__device__ __forceinline__ float rqs_head(const float4* __restrict__ q, int& off, const TriActs& a3, const uint32_t ocol,
+                                          const bool have_acc, const float v, float& lj) {
+  constexpr int E = TriShape<NR>::E;
+  float2 ph[12];
+  if (have_acc) {
+    uint32_t r0[8], r1[8], r2[8];
+    tmem_ld8_async(ocol + TRI_P_RQS * J, r0);
+    tmem_ld8_async(ocol + TRI_P_RQS * J + 8, r1);
+    tmem_ld8_async(ocol + TRI_P_RQS * J + 16, r2);
+    tmem_ld_fence8(r0);
+    tmem_ld_fence8(r1);
+    tmem_ld_fence8(r2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ph[i] = make_float2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+      ph[4 + i] = make_float2(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+      ph[8 + i] = make_float2(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) ph[i] = make_float2(0.f, 0.f);
+  }
   {
+    float4 b[6];
+    load_v(q + off, b);
+    off += 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      ph[2 * i].x += b[i].x; ph[2 * i].y += b[i].y;
+      ph[2 * i + 1].x += b[i].z; ph[2 * i + 1].y += b[i].w;
+    }
+  }
+  auto add_unit = [&](const float a) {
+    float4 w[6];
+    load_v(q + off, w);
+    off += 6;
+    const float2 aa = make_float2(a, a);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      ph[2 * i] = ffma2(make_float2(w[i].x, w[i].y), aa, ph[2 * i]);
+      ph[2 * i + 1] = ffma2(make_float2(w[i].z, w[i].w), aa, ph[2 * i + 1]);
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < J; ++c) {
+    add_unit(a3.r[2 * c].x);
+    add_unit(a3.r[2 * c].y);
+    add_unit(a3.r[2 * c + 1].x);
+    add_unit(a3.r[2 * c + 1].y);
+    if constexpr (E >= 1) add_unit(a3.e[c].x);
+    if constexpr (E == 2) add_unit(a3.e[c].y);
+  }
+  float phi[24];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { phi[2 * i] = ph[i].x; phi[2 * i + 1] = ph[i].y; }
+  return RqsLean::apply<INV>(phi, v, lj);
+}
+
+// order position J of a block: output -> affine map / spline -> the degree group's three hidden layers
+template <int NR, bool INV, bool RQS, int J>
+__device__ __forceinline__ void tri_stage(const float4* __restrict__ q, int& off, TriActs& a1, TriActs& a2, TriActs& a3,
+                                          const uint32_t (&o)[2 * G], const uint32_t ocol, const bool have_acc, float2 (&xbp)[G / 2],
+                                          const float (&y)[G], float& ladj, float* __restrict__ out_row, const bool valid,
+                                          const int kstep, const int feat0) {
+  using S = TriShape<NR>;
+  if constexpr (RQS) {
+    float lj;
+    const float res = rqs_head<NR, INV, J>(q, off, a3, ocol, have_acc, y[J], lj);
+    const float xk = INV ? res : y[J];
+    ladj = INV ? ladj - lj : ladj + lj;
+    if (valid) out_row[feat0 + J * kstep] = res;
+    if (J & 1) xbp[J >> 1].y = xk; else xbp[J >> 1].x = xk;
+  } else {
     const float4 ob = q[off];
     off += 1;
     float2 shf = make_float2(__uint_as_float(o[2 * J]) + ob.x, 0.f), srw = make_float2(__uint_as_float(o[2 * J + 1]) + ob.y, 0.f);
@@ -258,13 +336,14 @@ __device__ __forceinline__ void tri_stage(const float4* __restrict__ q, int& off
 }
 
 // order positions J .. G-1 of a block (compile-time recursion: every register index stays static)
-template <int NR, bool INV, int J>
+template <int NR, bool INV, bool RQS, int J>
 __device__ __forceinline__ void tri_stages(const float4* __restrict__ q, int& off, const int nst, TriActs& a1, TriActs& a2,
-                                           TriActs& a3, const uint32_t (&o)[2 * G], float2 (&xbp)[G / 2], const float (&y)[G], float& ladj,
+                                           TriActs& a3, const uint32_t (&o)[2 * G], const uint32_t ocol, const bool have_acc,
+                                           float2 (&xbp)[G / 2], const float (&y)[G], float& ladj,
                                            float* __restrict__ out_row, const bool valid, const int kstep, const int feat0) {
   if (J >= nst) return;
-  tri_stage<NR, INV, J>(q, off, a1, a2, a3, o, xbp, y, ladj, out_row, valid, kstep, feat0);
-  if constexpr (J + 1 < G) tri_stages<NR, INV, J + 1>(q, off, nst, a1, a2, a3, o, xbp, y, ladj, out_row, valid, kstep, feat0);
+  tri_stage<NR, INV, RQS, J>(q, off, a1, a2, a3, o, ocol, have_acc, xbp, y, ladj, out_row, valid, kstep, feat0);
+  if constexpr (J + 1 < G) tri_stages<NR, INV, RQS, J + 1>(q, off, nst, a1, a2, a3, o, ocol, have_acc, xbp, y, ladj, out_row, valid, kstep, feat0);
 }
 
 struct TriShared {
@@ -302,7 +381,7 @@ __device__ __forceinline__ void store_tile(unsigned char* hi, unsigned char* lo,
 }
 
 // one block of the substitution on the 128 particle threads
-template <int NR, bool INV>
+template <int NR, bool INV, bool RQS>
 __device__ __forceinline__ void run_block(const TriParams& p, const int bi, const int t, const uint32_t lane_base, unsigned char* smem,
                                           const float4* __restrict__ slab, TriShared& sh, uint32_t& n_groups, const int row_in_tile,
                                           float* out_row, const bool valid, float& ladj, const float (&y)[G], float* ws) {
@@ -313,6 +392,7 @@ __device__ __forceinline__ void run_block(const TriParams& p, const int bi, cons
   const int kstep = rev ? -1 : 1;
   TriActs a1, a2, a3;
   uint32_t o[2 * G];
+  const uint32_t ocol = lane_base + (uint32_t)(sh.wins[win][TW_COL_OUT] + B[TB_OC]);     // this block's output columns
   if (bi == 0) {
     acts_zero(a1); acts_zero(a2); acts_zero(a3);
 #pragma unroll
@@ -326,17 +406,21 @@ __device__ __forceinline__ void run_block(const TriParams& p, const int bi, cons
     raw_load<NR>(lane_base + wc, t1);
     raw_load<NR>(lane_base + Wp + wc, t2);
     raw_load<NR>(lane_base + 2 * Wp + wc, t3);
-    tmem_ld8_async(lane_base + sh.wins[win][TW_COL_OUT] + B[TB_OC], o);
+    if constexpr (!RQS) tmem_ld8_async(ocol, o);                   // spline heads pull their 24 columns position by position
     raw_take<NR>(t1, a1);
     raw_take<NR>(t2, a2);
     raw_take<NR>(t3, a3);
-    tmem_ld_fence8(o);
+    if constexpr (!RQS) tmem_ld_fence8(o);
+    else {
+#pragma unroll
+      for (int i = 0; i < 2 * G; ++i) o[i] = 0u;
+    }
   }
   float2 xbp[G / 2];
 #pragma unroll
   for (int i = 0; i < G / 2; ++i) xbp[i] = make_float2(0.f, 0.f);
   int off = 0;
-  tri_stages<NR, INV, 0>(slab, off, nst, a1, a2, a3, o, xbp, y, ladj, out_row, valid, kstep, feat0);
+  tri_stages<NR, INV, RQS, 0>(slab, off, nst, a1, a2, a3, o, ocol, bi != 0, xbp, y, ladj, out_row, valid, kstep, feat0);
   if (!(flags & TBF_LAST)) {
     const float4 xv = make_float4(xbp[0].x, xbp[0].y, xbp[1].x, xbp[1].y), z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.NW > 1 && win + 1 < p.NW) {
@@ -392,7 +476,7 @@ struct Ring {
   }
 };
 
-template <bool INV>
+template <bool INV, bool RQS>
 __global__ void __launch_bounds__(TRI_THREADS, 1)
 made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -621,9 +705,9 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
           mbar_wait(sh.dfull + slot, (dit >> 1) & 1);
           const float4* dslab = reinterpret_cast<const float4*>(dring + (size_t)slot * p.dslot_bytes);
           const int nr = sh.blocks[bi][TB_NR], flags = sh.blocks[bi][TB_FLAGS];
-          if (nr == 4) run_block<4, INV>(p, bi, t, lane_base, smem, dslab, sh, n_groups, row_in_tile, out_row, valid, ladj, y, ws);
-          else if (nr == 5) run_block<5, INV>(p, bi, t, lane_base, smem, dslab, sh, n_groups, row_in_tile, out_row, valid, ladj, y, ws);
-          else run_block<6, INV>(p, bi, t, lane_base, smem, dslab, sh, n_groups, row_in_tile, out_row, valid, ladj, y, ws);
+          if (nr == 4) run_block<4, INV, RQS>(p, bi, t, lane_base, smem, dslab, sh, n_groups, row_in_tile, out_row, valid, ladj, y, ws);
+          else if (nr == 5) run_block<5, INV, RQS>(p, bi, t, lane_base, smem, dslab, sh, n_groups, row_in_tile, out_row, valid, ladj, y, ws);
+          else run_block<6, INV, RQS>(p, bi, t, lane_base, smem, dslab, sh, n_groups, row_in_tile, out_row, valid, ladj, y, ws);
           mbar_arrive(sh.dempty + slot);
           ++dit;
           // the next block's inputs (this thread's own earlier stores; L2 latency hides behind the tensor-core work)
@@ -665,6 +749,7 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
 
 static int tri_check(const int32_t* m, int32_t meta_len) {
   PMC_REQUIRE(m && meta_len >= TRI_HEADER && m[TRI_VER] == TRI_LAYOUT_VERSION, "pmc_flow_sweep_tri: not a block-triangular layout table (tri_layout.build_tri)");
+  PMC_REQUIRE(m[TRI_KIND] == 0 || m[TRI_KIND] == 1, "pmc_flow_sweep_tri: unknown univariate head");
   PMC_REQUIRE(m[TRI_L] == 3 && m[TRI_GSIZE] == G, "pmc_flow_sweep_tri: built for 3 hidden layers and blocks of 4 order positions");
   PMC_REQUIRE(m[TRI_NB] >= 2 && m[TRI_NB] <= TRI_MAX_BLOCKS && m[TRI_NW] >= 1 && m[TRI_NW] <= TRI_MAX_WINDOWS, "pmc_flow_sweep_tri: table sizes out of range");
   PMC_REQUIRE(m[TRI_OFF_BLOCKS] == TRI_HEADER && m[TRI_OFF_WINDOWS] == TRI_HEADER + m[TRI_NB] * TB_FIELDS &&
@@ -747,15 +832,11 @@ extern "C" int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host,
                 "pmc_flow_sweep_tri: workspace too small (pmc_flow_sweep_tri_workspace)");
   }
   cudaStream_t st = as_stream(stream);
-  if (inverse) {
-    auto kern = made_sweep_tri_kernel<true>;
-    PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PMC_TRY(launch_chain(kern, dim3(grid), dim3(TRI_THREADS), smem, st, q));
-  } else {
-    auto kern = made_sweep_tri_kernel<false>;
-    PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PMC_TRY(launch_chain(kern, dim3(grid), dim3(TRI_THREADS), smem, st, q));
-  }
+  const bool rqs = m[TRI_KIND] != 0;
+  auto kern = inverse ? (rqs ? made_sweep_tri_kernel<true, true> : made_sweep_tri_kernel<true, false>)
+                      : (rqs ? made_sweep_tri_kernel<false, true> : made_sweep_tri_kernel<false, false>);
+  PMC_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PMC_TRY(launch_chain(kern, dim3(grid), dim3(TRI_THREADS), smem, st, q));
   PMC_LAUNCH_CHECK();
   return 0;
 }

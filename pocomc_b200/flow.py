@@ -286,6 +286,8 @@ class MaskedAutoregressiveFlow(nn.Module):
         (csrc/flow_tc.cu, H <= 128) does not cover -- the BASELINE widths 256 / 512 / 1024"""
         if not self.tri_available():
             return False
+        if self.layout.kind != ML.KIND_AFFINE and self.layout.n_hidden < config.tri_rqs_min_hidden:
+            return False                     # narrow spline flows: the fp32-FMA stream sweep is as fast (tests/nsf_bench.py)
         if inverse:
             return config.inverse_path == "tri"
         return self._tc is None and config.forward_path == "tc" and config.inverse_path == "tri"

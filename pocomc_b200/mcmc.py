@@ -239,7 +239,7 @@ class McmcEngine:
         n, d = self.n, self.d
         k = config.host_chunks
         if k <= 0:
-            k = 4 if n * d * 8 >= (1 << 20) else 1
+            k = 4 if n * d * 8 >= (16 << 20) else 1       # measured: 10 000 x 32-D loses with any split, 50 000 x 50-D gains 4 % with 4
         if self.have_blobs:
             k = 1
         k = max(1, min(int(k), n))

@@ -1,5 +1,5 @@
 """Host-side layout of the tcgen05 block-triangular sweep (csrc/flow_tri.cu): Flow.inverse / Flow.forward of affine
-(zuko MAF) flows of ANY width.
+(zuko MAF) and rational-quadratic-spline (zuko NSF, the reference's default presets) flows of ANY width.
 
 The degree-ordered sweep (made_layout.py) is a nonlinear forward substitution.  Order positions are cut into BLOCKS of
 TRI_G = 4; the hidden units born in a block (its degree groups) form one K-slab.  Blocks are grouped into WINDOWS: the
@@ -16,7 +16,11 @@ memory (512 fp32 columns per 128-particle tile), so a window holds as many block
     TF32 hi / lo images in place by the particle threads;
   * the dependencies inside a block run as fp32 FMAs, one thread per particle (the in-block slab).
 
-A flow whose accumulators fit one window (D <= 36 at the preset widths) never touches the scratch area.
+A flow whose accumulators fit one window (affine, D <= 36 at the preset widths) never touches the scratch area.
+
+Outputs per order position: P = 2 tensor-memory columns for affine heads (shift, raw log-scale), P = 24 for spline heads (the
+23 = 3 * 8 - 1 spline parameters of zuko's NSF padded by one zero column); a window holds at most 256 output columns
+(the widest tcgen05.mma), i.e. two blocks of a spline flow.
 
 Packed image per transform (floats; gather codes of pmc_flow_tc_pack: >= 0 hi, -(g+2) lo, g | 2^30 plain, -1 zero):
     [in-block slab of block 0] ... [in-block slab of block NB-1]
@@ -33,14 +37,14 @@ from functools import lru_cache
 
 import numpy as np
 
-from .made_layout import KIND_AFFINE, TC_BIAS_FLAG, build_layout
+from .made_layout import KIND_AFFINE, KIND_RQS, TC_BIAS_FLAG, build_layout
 
 TRI_G = 4
-TRI_KC = 16               # K extent of one init chunk (A from the scratch area + B weights)
-TRI_VERSION = 300
+TRI_KC = 16               # K extent of one init chunk (A from the scratch area + B weights); 8 when 16 leaves < 4 ring slots
+TRI_VERSION = 301
 (TRI_VER, TRI_D, TRI_H, TRI_L, TRI_T, TRI_GSIZE, TRI_NB, TRI_NW, TRI_TSTRIDE, TRI_KCHUNK, TRI_SLOT_BYTES, TRI_DSLOT_BYTES,
  TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_OFF_BLOCKS, TRI_OFF_WINDOWS, TRI_SMEM_BYTES,
- TRI_NCOLS, TRI_CHUNK_OFF, TRI_HEADER) = range(23)
+ TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND, TRI_HEADER) = range(24)
 # per block
 (TB_K0, TB_NST, TB_NR, TB_W, TB_KP, TB_WIN, TB_WC, TB_OC, TB_DOFF, TB_DN, TB_KS, TB_UPD_N, TB_UPD_DCOL, TB_OUT_N, TB_OUT_DCOL,
  TB_FLAGS, TB_FIELDS) = range(17)
@@ -50,7 +54,8 @@ TRI_SMEM_BUDGET = 227 * 1024
 TRI_STATIC_SMEM = 14 * 1024       # barriers, tables and per-block issue records of the kernel (sizeof(TriShared))
 TRI_MAX_STAGES = 8
 TRI_MAX_BLOCKS = 64
-TRI_MAX_WINDOWS = 16
+TRI_MAX_WINDOWS = 32
+TRI_P_RQS = 24             # output columns per order position of a spline flow (23 parameters + one zero column)
 
 
 def tri_slot(j, s, G, E):
@@ -63,18 +68,25 @@ def _shape(NR):
     return dict(E=E, nrv=1 if NR == 4 else 2, q1=(2 * NR + 3) // 4, xv=(0, 2, 3)[E], ogx=(0, 1, 1)[E])
 
 
-def tri_diag_floats(G: int, NR: int) -> int:
+def tri_out_cols(kind: int) -> int:
+    """tensor-memory columns per order position for the univariate head's parameters"""
+    return 2 if kind == KIND_AFFINE else TRI_P_RQS
+
+
+def tri_diag_floats(G: int, NR: int, kind: int = KIND_AFFINE) -> int:
     """floats of one block's FFMA weight slab (walked in lock step by csrc/flow_tri.cu: tri_stage; float4 granularity).
     NR = 4 + E destination units per group; sources come in PAIRS (packed fp32 FMAs: one float2 of weights
     (w[src 2p], w[src 2p+1]) per destination unit):
       stage j:  out bias f4 | out weights of source groups 0..j-1: 2 f4 (+1 f4 for the extra unit(s))
+                [spline heads: out bias 6 f4 (24 parameters) | per source group and source unit (4 regular, then the
+                 extras) 6 f4 = that unit's weight into each of the 24 parameters]
                 layer-1 bias | layer-1 weights of x pairs 0..j>>1: NR float2 each
                 layers 2, 3: bias | source groups 0..j: NR f4 regular + the extras (E = 1: NR floats in 2 f4;
                                                                                   E = 2: NR float2 in 3 f4)."""
     sh = _shape(NR)
     n = 0
     for j in range(G):
-        n += 1 + j * (2 + sh["ogx"])
+        n += (1 + j * (2 + sh["ogx"])) if kind == KIND_AFFINE else (6 + j * 6 * (4 + sh["E"]))
         n += sh["nrv"] + (j // 2 + 1) * sh["q1"]
         n += 2 * (sh["nrv"] + (j + 1) * (NR + sh["xv"]))
     return 4 * n
@@ -99,9 +111,10 @@ def _r(n, m):
     return (int(n) + m - 1) // m * m
 
 
-def _tri_blocks(D: int, H: int):
-    """blocks (with their unit maps) and windows of a (D, H) masked MLP"""
+def _tri_blocks(D: int, H: int, P: int = 2):
+    """blocks (with their unit maps) and windows of a (D, H) masked MLP with P output columns per order position"""
     G = TRI_G
+    PG = P * G
     ng = D - 1
     deg = (np.arange(H) % ng) + 1
     hperm = np.argsort(deg, kind="stable")
@@ -129,16 +142,16 @@ def _tri_blocks(D: int, H: int):
         nb, wsum = 0, 0
         while b0 + nb < len(blocks):
             w2 = wsum + blocks[b0 + nb]["W"]
-            if 3 * _r(w2, 16) + _r(2 * G * (nb + 1), 16) > 512:
+            if 3 * _r(w2, 16) + _r(PG * (nb + 1), 16) > 512 or _r(PG * (nb + 1), 16) > 256:
                 break
             wsum, nb = w2, nb + 1
         if nb == 0:
             raise ValueError("a single block exceeds tensor memory")
-        windows.append(dict(b0=b0, nb=nb, Wp=_r(wsum, 16), Op=_r(2 * G * nb, 16), Kh=blocks[b0]["ks"], Kx=8 * b0))
+        windows.append(dict(b0=b0, nb=nb, Wp=_r(wsum, 16), Op=_r(PG * nb, 16), Kh=blocks[b0]["ks"], Kx=8 * b0))
         wc = 0
         for i in range(nb):
             blk = blocks[b0 + i]
-            blk.update(win=len(windows) - 1, wc=wc, oc=2 * G * i, last_in_win=(i == nb - 1))
+            blk.update(win=len(windows) - 1, wc=wc, oc=PG * i, last_in_win=(i == nb - 1))
             wc += blk["W"]
         b0 += nb
     for w in windows:
@@ -150,14 +163,14 @@ def _tri_blocks(D: int, H: int):
         else:
             nxt = blk["wc"] + blk["W"]                   # first later hidden column of the window
             start = nxt // 16 * 16                       # MMA widths are multiples of 16 (Wp is one): start early, on consumed columns
-            onxt = blk["oc"] + 2 * G
+            onxt = blk["oc"] + PG
             ostart = onxt // 16 * 16
             blk.update(upd_N=w["Wp"] - start, upd_dcol=start, out_N=w["Op"] - ostart, out_dcol=ostart)
     return blocks, windows, ks
 
 
 def tri_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int) -> bool:
-    if kind != KIND_AFFINE or n_layers != 3 or n_dim < 2:
+    if kind not in (KIND_AFFINE, KIND_RQS) or n_layers != 3 or n_dim < 2:
         return False
     try:
         build_tri(n_dim, n_hidden, n_layers, 1, kind)
@@ -168,11 +181,13 @@ def tri_supported(n_dim: int, n_hidden: int, n_layers: int, kind: int) -> bool:
 
 @lru_cache(maxsize=None)
 def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind: int, bins: int = 8) -> TriLayout:
-    if kind != KIND_AFFINE or n_layers != 3:
-        raise ValueError("the tcgen05 block-triangular sweep is built for affine flows with 3 hidden layers")
+    if kind not in (KIND_AFFINE, KIND_RQS) or n_layers != 3 or (kind == KIND_RQS and bins != 8):
+        raise ValueError("the tcgen05 block-triangular sweep is built for affine / 8-bin spline flows with 3 hidden layers")
     lay = build_layout(n_dim, n_hidden, n_layers, n_transforms, kind, bins)
     D, H, L, T, G = n_dim, n_hidden, n_layers, n_transforms, TRI_G
-    blocks, windows, kh_total = _tri_blocks(D, H)
+    P, total = tri_out_cols(kind), lay.total
+    PG = P * G
+    blocks, windows, kh_total = _tri_blocks(D, H, P)
     NB, NW = len(blocks), len(windows)
     if any(b["U"] > 6 for b in blocks) or NB < 2:
         raise ValueError("degree groups too wide (or too few order positions) for the block-triangular sweep")
@@ -180,7 +195,19 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
         raise ValueError("too many blocks / windows for the kernel's tables")
     raw_off = np.concatenate([[0], np.cumsum([int(np.prod(s)) for s in lay.raw_sizes])]).astype(np.int64)
     PLAIN = TC_BIAS_FLAG
-    KC = TRI_KC
+    # ---- sizes of the shared-memory ring (decide the K extent of an init chunk before the chunk stream is laid out) ----
+    max_upd = max([max(8, b["Kp"]) * max(b["upd_N"], b["out_N"]) * 8 for b in blocks if not b["last_in_win"]], default=0)
+    dslot_bytes = _r(max(tri_diag_floats(G, b["NR"], kind) for b in blocks) * 4, 1024)
+    tile_bytes = max(b["Kp"] for b in blocks) * 512
+    fixed = L * 2 * tile_bytes + 2 * 4096 + 2 * dslot_bytes + TRI_STATIC_SMEM
+    for KC in ((TRI_KC,) if kind == KIND_AFFINE else (TRI_KC, 8)):       # affine flows keep K = 16 chunks (fewer hand-offs per window)
+        max_init = max([KC * (1024 + max(w["Wp"], w["Op"]) * 8) for w in windows[1:]], default=0)
+        slot_bytes = _r(max(max_upd, max_init, 1024), 1024)
+        stages = min(TRI_MAX_STAGES, (TRI_SMEM_BUDGET - fixed) // slot_bytes)
+        if stages >= 4:
+            break
+    if stages < 2:
+        raise ValueError("shared memory budget exceeded")
     # global slot axes: hidden slot -> unit (all blocks), x slot -> order position
     hslot_unit = np.full(kh_total, -1, np.int64)
     for b in blocks:
@@ -216,11 +243,20 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
                 valid = j < nst
                 row_s = 2 * iperm[k0 + j] if valid else -1
                 row_r = row_s + 1 if valid else -1
-                bo = np.full(4, -1, np.int64)
-                if valid:
-                    bo[0], bo[1] = bia[L] + row_s, bia[L] + row_r
-                d.append(bo)
-                for c in range(j):
+                if kind == KIND_RQS:
+                    rows = np.full(P, -1, np.int64)
+                    if valid:
+                        rows[:total] = total * iperm[k0 + j] + np.arange(total)
+                    d.append(np.where(rows >= 0, bia[L] + rows, -1))
+                    for c in range(j):
+                        for src in [unit[4 * c + u_] for u_ in range(4)] + [unit[4 * G + E * c + e_] for e_ in range(E)]:
+                            d.append(np.array([wsrc(L, H, r_, src) for r_ in rows], np.int64))
+                else:
+                    bo = np.full(4, -1, np.int64)
+                    if valid:
+                        bo[0], bo[1] = bia[L] + row_s, bia[L] + row_r
+                    d.append(bo)
+                for c in range(j if kind == KIND_AFFINE else 0):
                     for p in range(2):
                         u0, u1 = unit[4 * c + 2 * p], unit[4 * c + 2 * p + 1]
                         d.append(np.array([wsrc(L, H, row_s, u0), wsrc(L, H, row_s, u1), wsrc(L, H, row_r, u0), wsrc(L, H, row_r, u1)], np.int64))
@@ -266,7 +302,7 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
                                     blk[2 * s_ + h] = wsrc(l, H, own[s_], unit[4 * G + 2 * c + h])
                             d.append(blk)
             d = np.concatenate(d)
-            assert len(d) == tri_diag_floats(G, NR), (len(d), tri_diag_floats(G, NR))
+            assert len(d) == tri_diag_floats(G, NR, kind), (len(d), tri_diag_floats(G, NR, kind))
             diag_tab.append((off, len(d)))
             parts.append(np.where(d >= 0, d | PLAIN, -1))
             off += len(d)
@@ -282,8 +318,7 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
                 col_unit[bb["wc"]:bb["wc"] + bb["W"]] = bb["unit"]
                 col_k0[bb["wc"]:bb["wc"] + bb["W"]] = bb["k0"]
                 for j in range(bb["nst"]):
-                    out_row[bb["oc"] + 2 * j] = 2 * iperm[bb["k0"] + j]
-                    out_row[bb["oc"] + 2 * j + 1] = 2 * iperm[bb["k0"] + j] + 1
+                    out_row[bb["oc"] + P * j:bb["oc"] + P * j + total] = total * iperm[bb["k0"] + j] + np.arange(total)
             return col_unit, col_k0, out_row
 
         def b_matrix(op, dst_cols, src_units=None, src_orders=None, col_unit=None, out_row=None):
@@ -318,7 +353,7 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
             if not b["last_in_win"]:
                 # update slabs: destination = later columns of the window (columns before them, reached only because
                 # widths are multiples of 16, get zero weights: they belong to consumed blocks)
-                nxt, onxt = b["wc"] + b["W"], b["oc"] + 2 * G
+                nxt, onxt = b["wc"] + b["W"], b["oc"] + PG
                 hcols = np.array([c if c >= nxt else -1 for c in range(b["upd_dcol"], wd["Wp"])], np.int64)
                 ocols = np.array([c if c >= onxt else -1 for c in range(b["out_dcol"], wd["Op"])], np.int64)
                 xo = np.full(8, -1, np.int64)
@@ -354,15 +389,7 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
     assert all(len(g) == tstride for g in gathers) and tstride % 4 == 0 and chunk_off % 4 == 0
 
     # ---- sizes ----
-    max_upd = max([max(8, b["Kp"]) * max(b["upd_N"], b["out_N"]) * 8 for b in blocks if not b["last_in_win"]], default=0)
-    max_init = max([KC * (1024 + max(w["Wp"], w["Op"]) * 8) for w in windows[1:]], default=0)
-    slot_bytes = _r(max(max_upd, max_init, 1024), 1024)
-    dslot_bytes = _r(max(dn for _, dn in diag_tab) * 4, 1024)
-    tile_bytes = max(b["Kp"] for b in blocks) * 512
-    fixed = L * 2 * tile_bytes + 2 * 4096 + 2 * dslot_bytes + TRI_STATIC_SMEM
-    stages = min(TRI_MAX_STAGES, (TRI_SMEM_BUDGET - fixed) // slot_bytes)
-    if stages < 2:
-        raise ValueError("shared memory budget exceeded")
+    assert dslot_bytes >= max(dn for _, dn in diag_tab) * 4
     smem = fixed + stages * slot_bytes
     ncols = max(3 * w["Wp"] + w["Op"] for w in windows)
     assert ncols <= 512
@@ -377,9 +404,9 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
         win_rows[wi] = [w["b0"], w["nb"], w["Wp"], w["Op"], w["col_out"], w["Kh"], w["Kx"], 0]
     meta = np.zeros(TRI_HEADER, np.int64)
     meta[[TRI_VER, TRI_D, TRI_H, TRI_L, TRI_T, TRI_GSIZE, TRI_NB, TRI_NW, TRI_TSTRIDE, TRI_KCHUNK, TRI_SLOT_BYTES, TRI_DSLOT_BYTES,
-          TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_SMEM_BYTES, TRI_NCOLS, TRI_CHUNK_OFF]] = \
+          TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_SMEM_BYTES, TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND]] = \
         [TRI_VERSION, D, H, L, T, G, NB, NW, tstride, KC, slot_bytes, dslot_bytes, tile_bytes, stages, kh_total, kx_total, ws_floats,
-         smem, ncols, chunk_off]
+         smem, ncols, chunk_off, kind]
     meta[TRI_OFF_BLOCKS] = TRI_HEADER
     meta[TRI_OFF_WINDOWS] = TRI_HEADER + block_rows.size
     meta = np.concatenate([meta, block_rows.reshape(-1), win_rows.reshape(-1)])

@@ -211,6 +211,8 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
     n = len(v)
     ladj = np.zeros(n, f32)
     log_slope = f32(np.log(1e-3))
+    kind = int(m[TL.TRI_KIND])
+    PO = TL.tri_out_cols(kind)                    # output columns per order position
 
     def mma(A, Bh, Bl):
         Ah = rnd(A)
@@ -241,12 +243,12 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
             nrv, q1 = (1 if NR == 4 else 2), (2 * NR + 3) // 4
             first_block = (win == 0 and bi == 0)
             a = [None] + [np.zeros((n, W), f32) for _ in range(L)]
-            o = np.zeros((n, 2 * G), f32)
+            o = np.zeros((n, PO * G), f32)
             if not first_block:
                 for l in range(1, L + 1):
                     a[l] = acc[:, (l - 1) * Wp + wc:(l - 1) * Wp + wc + W].copy()
-                o = acc[:, col_out + oc:col_out + oc + 2 * G].copy()
-                assert np.isfinite(o[:, :2 * nst]).all() and all(np.isfinite(a[l]).all() for l in range(1, L + 1)), (t, bi)
+                o = acc[:, col_out + oc:col_out + oc + PO * G].copy()
+                assert np.isfinite(o[:, :PO * nst]).all() and all(np.isfinite(a[l]).all() for l in range(1, L + 1)), (t, bi)
                 o = np.nan_to_num(o)
             xb = np.zeros((n, G), f32)
             p = doff
@@ -258,10 +260,23 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
                 return out_
 
             for j in range(G):
-                bo = take(1)
+                if kind != 0:
+                    # spline head: 24 parameter columns; bias 6 f4, then per source group 4 regular units + the extras, 6 f4 each
+                    phi = o[:, PO * j:PO * j + PO] + take(6)[None, :]
+                    for c in range(j):
+                        for src in [4 * c + u_ for u_ in range(4)] + [4 * G + E * c + e_ for e_ in range(E)]:
+                            phi = phi + a[L][:, src][:, None] * take(6)[None, :]
+                    if j < nst:
+                        feat = iperm[k0 + j]
+                        res, lj = rqs(phi[:, :23].astype(f32), v[:, feat].copy(), inverse)
+                        xk = res if inverse else v[:, feat].copy()
+                        ladj = (ladj - lj if inverse else ladj + lj).astype(f32)
+                        v[:, feat] = res
+                        xb[:, j] = xk
+                bo = take(1) if kind == 0 else np.zeros(4, f32)
                 shift = o[:, 2 * j] + bo[0]
                 sraw = o[:, 2 * j + 1] + bo[1]
-                for c in range(j):
+                for c in range(j if kind == 0 else 0):
                     for pp in range(2):
                         w4 = take(1)
                         s0, s1 = 4 * c + 2 * pp, 4 * c + 2 * pp + 1
@@ -276,7 +291,7 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
                         e0, e1 = 4 * G + 2 * c, 4 * G + 2 * c + 1
                         shift = shift + w4[0] * a[L][:, e0] + w4[1] * a[L][:, e1]
                         sraw = sraw + w4[2] * a[L][:, e0] + w4[3] * a[L][:, e1]
-                if j < nst:
+                if j < nst and kind == 0:
                     feat = iperm[k0 + j]
                     ls = sraw / (f32(1) + np.abs(sraw / log_slope))
                     if inverse:

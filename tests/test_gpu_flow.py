@@ -279,14 +279,17 @@ def test_config_shapes_vs_oracle(preset, d, n_fwd, n_inv):
 
 @pytest.mark.parametrize("preset,d,n", [("maf6", 32, 1000), ("maf3", 10, 77), ("maf3", 21, 300), ("maf3", 16, 129),
                                         ("maf6", 33, 515), ("maf6", 32, 20011), ("maf12", 14, 64), ("maf3", 9, 200), ("maf3", 17, 130), ("maf3", 36, 257), ("maf3", 8, 100),
-                                        ("maf3", 40, 300), ("maf6", 50, 1500), ("maf3", 100, 19000), ("maf3", 200, 300)])
+                                        ("maf3", 40, 300), ("maf6", 50, 1500), ("maf3", 100, 19000), ("maf3", 200, 300),
+                                        ("nsf6", 10, 300), ("nsf6", 8, 77), ("nsf3", 32, 1000), ("nsf3", 21, 300), ("nsf3", 14, 130),
+                                        ("nsf6", 32, 5011), ("nsf3", 50, 700), ("nsf3", 100, 400), ("nsf3", 200, 200)])
 def test_tensor_core_block_triangular_sweep_matches_oracle(preset, d, n):
     """csrc/flow_tri.cu (tcgen05 right-looking block updates + in-block fp32 substitution), BOTH directions, against the
     oracle's 1-pass forward / D+1-pass inverse: ragged last tile, several tiles per CTA, every block shape (4, 5, 6 units
     per degree group), one tensor-memory window (D <= 36) and several (the BASELINE widths 50 / 100 / 200 with their scratch
     area); fp32 bar 5e-5.  It is the default path of Flow.inverse for these shapes."""
     from pocomc_b200 import config, made_layout as ML, tri_layout as TL
-    assert TL.tri_supported(d, F.hidden_width(d), 3, ML.KIND_AFFINE)
+    spline = preset.startswith("nsf")          # zuko NSF (the reference's default presets): 24 output columns per order position + the RQS head
+    assert TL.tri_supported(d, F.hidden_width(d), 3, ML.KIND_RQS if spline else ML.KIND_AFFINE)
     torch.manual_seed(d * 5 + n)
     ref = F.make_flow(d, preset)
     with torch.no_grad():
@@ -303,7 +306,8 @@ def test_tensor_core_block_triangular_sweep_matches_oracle(preset, d, n):
     out = torch.empty(n, d, device=dev); ladj = torch.empty(n, device=dev)
     f.flow.sweep_tri_into(x.to(dev), out, ladj, inverse=False)
     # 12 scaled transforms amplify fp32 rounding with the magnitude of the values: the absolute bar scales with it
-    tol = dict(rtol=5e-5, atol=5e-5 * max(1.0, float(z_ref.abs().max()), float(xi_ref.abs().max())))
+    bar = 5e-4 if spline else 5e-5                               # the spline flows' bar
+    tol = dict(rtol=bar, atol=bar * max(1.0, float(z_ref.abs().max()), float(xi_ref.abs().max())))
     np.testing.assert_allclose(out.cpu().numpy(), z_ref.numpy(), **tol)
     np.testing.assert_allclose(ladj.cpu().numpy(), l_ref.numpy(), **tol)
     xi, li = f.inverse(z_ref)                                    # the public call takes the tensor-core path
