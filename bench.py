@@ -271,9 +271,10 @@ def committed_traffic(kernel_name, n, n_dim):
     except OSError:
         return None, "profiles/roofline_traffic.json missing"
     for entry in table:
-        if re.search(entry["kernel"], kernel_name) and int(entry.get("n_dim", n_dim)) == n_dim and int(entry.get("n", n)) == n:
+        if re.search(entry["kernel"], kernel_name) and int(entry.get("n_dim", n_dim)) == n_dim and int(entry.get("n", n)) == n \
+                and entry.get("flow", "maf6") == FLOW:
             return float(entry["dram_bytes_per_launch"]), entry["source"]
-    return None, f"no committed ncu capture of {kernel_name!r} at n={n}, n_dim={n_dim}"
+    return None, f"no committed ncu capture of {kernel_name!r} at n={n}, n_dim={n_dim}, flow={FLOW}"
 
 
 def tri_issued_flop(tri_meta, n):
@@ -459,7 +460,8 @@ def run_b200(args):
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     mod = flow.flow
     if mod.tri_available() and config.inverse_path == "tri":
-        kernel = "made_sweep_tri_kernel<true> (flow inverse: windowed tcgen05 block-triangular sweep)"
+        kernel = "made_sweep_tri_kernel<true> (flow inverse: windowed tcgen05 block-triangular sweep)" if lay.kind == ML.KIND_AFFINE else \
+            "made_sweep_tri_kernel<true, rqs> (flow inverse of a spline flow: windowed tcgen05 block-triangular sweep, rational-quadratic head)"
         issued = tri_issued_flop(mod._tri_meta_host, n_local)
         note = ("tcgen05.mma kind::tf32 (3xTF32 split): right-looking updates inside a tensor-memory window, left-looking window "
                 "initialisation from the fp32 scratch area, in-block fp32 substitution; achieved = issued MMA FLOP per launch (2*128*N*K per "
@@ -499,7 +501,7 @@ def run_b200(args):
                          ms_per_step=1e3 * t_e2e / e2e_steps, steps=e2e_steps, rng="device Philox",
                          callbacks="host numpy likelihood (black box); pc.Prior of scipy norm / uniform factors evaluated on the GPU"),
                 gpu_launches=launches, roofline=roofline, roofline_other=[roofline_chain], accept_rate=accept_dev)
-    if rank == 0 and world == 1 and not args.no_aux and args.config == 1:
+    if rank == 0 and world == 1 and not args.no_aux and args.config == 1 and FLOW == "maf6":
         line["aux"] = aux_measurements(flow, peaks, D)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -682,6 +684,7 @@ def flow_param_arrays(flow):
 
 
 def main():
+    global FLOW
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -689,9 +692,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE configs index (5 = the literal 10k x 32-D Rosenbrock line)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--flow", default=FLOW, choices=["maf3", "maf6", "maf12", "nsf3", "nsf6", "nsf12"],
+                    help="flow preset of both arms (BASELINE's configs use maf6; nsf6 is the reference's own default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the untimed auxiliary measurements (tcgen05 forward, fit step, full run)")
     args = ap.parse_args()
+    FLOW = args.flow
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -41,13 +41,13 @@ using namespace tc;
 // header / tables of tri_layout.build_tri -- keep in sync
 enum { TRI_VER = 0, TRI_D, TRI_H, TRI_L, TRI_T, TRI_GSIZE, TRI_NB, TRI_NW, TRI_TSTRIDE, TRI_KCHUNK, TRI_SLOT_BYTES, TRI_DSLOT_BYTES,
        TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_OFF_BLOCKS, TRI_OFF_WINDOWS, TRI_SMEM_BYTES,
-       TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND, TRI_HEADER };
+       TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND, TRI_KCHUNK_OUT, TRI_HEADER };
 enum { TB_K0 = 0, TB_NST, TB_NR, TB_W, TB_KP, TB_WIN, TB_WC, TB_OC, TB_DOFF, TB_DN, TB_KS, TB_UPD_N, TB_UPD_DCOL, TB_OUT_N, TB_OUT_DCOL,
        TB_FLAGS, TB_FIELDS };
 enum { TW_B0 = 0, TW_NB, TW_WP, TW_OP, TW_COL_OUT, TW_KH, TW_KX, TW_PAD, TW_FIELDS };
 enum { TBF_LAST_IN_WIN = 1, TBF_LAST = 2 };
 
-constexpr int TRI_LAYOUT_VERSION = 301;
+constexpr int TRI_LAYOUT_VERSION = 302;
 constexpr int TRI_MAX_STAGES = 8;          // ring depth: as many slots as fit, decided by tri_layout.build_tri
 constexpr int TRI_MAX_SLOTS = 12;          // + the slots a window initialisation borrows from the (then idle) A-tile area
 constexpr int TRI_MAX_BLOCKS = 64;
@@ -66,7 +66,7 @@ struct TriParams {
   float* ws;               // scratch: gridDim.x * ws_floats
   long long n;
   long long ws_floats;
-  int D, T, NB, NW, tstride, chunk_off, passes, stages, extra, kc, kh_total, kx_total;
+  int D, T, NB, NW, tstride, chunk_off, passes, stages, extra, kc, kc_out, kh_total, kx_total;   // kc / kc_out: K extent of an init chunk (hidden layers / outputs)
   uint32_t slot_bytes, dslot_bytes, tile_bytes;
 };
 
@@ -566,8 +566,9 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
                 const int ktot = op == 0 ? Wn[TW_KX] : Wn[TW_KH];
                 const uint32_t N = (uint32_t)(op < 3 ? Wn[TW_WP] : Wn[TW_OP]);
                 const float* a_src = ws + (op == 0 ? (size_t)0 : ((size_t)p.kx_total + (size_t)(op - 1) * p.kh_total) * 128);
-                for (int k = 0; k < ktot; k += p.kc) {
-                  const uint32_t ke = (uint32_t)min(p.kc, ktot - k);
+                const int kc = op < 3 ? p.kc : p.kc_out;
+                for (int k = 0; k < ktot; k += kc) {
+                  const uint32_t ke = (uint32_t)min(kc, ktot - k);
                   const uint32_t a_bytes = ke * 512u, b_bytes = N * ke * 8u;
                   const uint32_t sl = rg.next_init(init_slots);
                   rg.acquire(sh.bempty, sl);
@@ -648,8 +649,9 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
                 const uint32_t N = (uint32_t)(op < 3 ? Wn[TW_WP] : Wn[TW_OP]);
                 const uint32_t d = tm + (uint32_t)(op < 3 ? op * Wn[TW_WP] : Wn[TW_COL_OUT]);
                 const uint32_t idesc = idesc_tf32(128, (int)N);
-                for (int k = 0; k < ktot; k += p.kc) {
-                  const uint32_t ke = (uint32_t)min(p.kc, ktot - k);
+                const int kc = op < 3 ? p.kc : p.kc_out;
+                for (int k = 0; k < ktot; k += kc) {
+                  const uint32_t ke = (uint32_t)min(kc, ktot - k);
                   const uint32_t sl = rg.next_init(init_slots);
                   rg.pass(sl);                                   // the chunk's arrival is observed by the splitting threads
                   const uint32_t base16 = sl < stages ? ring16 + sl * slot16 : tiles16 + (sl - stages) * slot16;
@@ -717,11 +719,13 @@ made_sweep_tri_kernel(const __grid_constant__ TriParams p) {
             for (int op = 0; op < 4; ++op) rg.pass(rg.next_update(stages));      // the four update slabs of this block go by untouched
           } else if (!(flags & TBF_LAST)) {
             // window initialisation: split this row of every A chunk into its TF32 hi / lo images
+            // (publishing 2 - 4 chunks behind one proxy fence was measured and is no faster: profiles/r2bf_split_batch.log)
             const int* Wn = sh.wins[sh.blocks[bi][TB_WIN] + 1];
             for (int op = 0; op < 4; ++op) {
               const int ktot = op == 0 ? Wn[TW_KX] : Wn[TW_KH];
-              for (int k = 0; k < ktot; k += p.kc) {
-                const int ke = min(p.kc, ktot - k);
+              const int kc = op < 3 ? p.kc : p.kc_out;
+              for (int k = 0; k < ktot; k += kc) {
+                const int ke = min(kc, ktot - k);
                 const uint32_t sl = rg.next_init(init_slots);
                 rg.wait(sh.bfull, sl);
                 float4* a = reinterpret_cast<float4*>(slot_ptr(sl)) + row_in_tile;
@@ -779,7 +783,7 @@ extern "C" int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host,
   q.packed = packed; q.in = in; q.out = out; q.ladj = ladj; q.n = n; q.ws = workspace;
   q.D = m[TRI_D]; q.T = m[TRI_T]; q.NB = m[TRI_NB]; q.NW = m[TRI_NW];
   q.tstride = m[TRI_TSTRIDE]; q.chunk_off = m[TRI_CHUNK_OFF]; q.passes = passes;
-  q.stages = m[TRI_NSTAGES]; q.kc = m[TRI_KCHUNK]; q.kh_total = m[TRI_KH_TOTAL]; q.kx_total = m[TRI_KX_TOTAL];
+  q.stages = m[TRI_NSTAGES]; q.kc = m[TRI_KCHUNK]; q.kc_out = m[TRI_KCHUNK_OUT]; q.kh_total = m[TRI_KH_TOTAL]; q.kx_total = m[TRI_KX_TOTAL];
   q.ws_floats = m[TRI_WS_FLOATS];
   {
     const char* e = getenv("PMC_TRI_STAGES");
@@ -789,6 +793,7 @@ extern "C" int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host,
   }
   q.slot_bytes = (uint32_t)m[TRI_SLOT_BYTES]; q.dslot_bytes = (uint32_t)m[TRI_DSLOT_BYTES]; q.tile_bytes = (uint32_t)m[TRI_TILE_BYTES];
   PMC_REQUIRE(m[TRI_NCOLS] <= 512, "pmc_flow_sweep_tri: accumulators exceed tensor memory");
+  PMC_REQUIRE(q.kc_out >= 8 && q.kc_out % 8 == 0, "pmc_flow_sweep_tri: bad K chunking of the outputs");
   PMC_REQUIRE(q.kc >= 8 && q.kc % 8 == 0 && q.kh_total % 8 == 0 && q.kx_total == 8 * q.NB, "pmc_flow_sweep_tri: bad K chunking");
   q.tables = meta_dev + TRI_HEADER;
   const int* mb = m + m[TRI_OFF_BLOCKS];
@@ -811,7 +816,8 @@ extern "C" int pmc_flow_sweep_tri(const float* packed, const int32_t* meta_host,
     PMC_REQUIRE(Wn[TW_WP] % 16 == 0 && Wn[TW_WP] >= 16 && Wn[TW_WP] <= 256 && Wn[TW_OP] % 16 == 0 && Wn[TW_OP] >= 16 &&
                 3 * Wn[TW_WP] + Wn[TW_OP] <= 512 && Wn[TW_COL_OUT] == 3 * Wn[TW_WP], "pmc_flow_sweep_tri: bad window shape");
     PMC_REQUIRE(Wn[TW_KH] % 8 == 0 && Wn[TW_KX] % 8 == 0 && Wn[TW_KH] <= q.kh_total && Wn[TW_KX] <= q.kx_total, "pmc_flow_sweep_tri: bad window K extents");
-    if (w > 0) PMC_REQUIRE((uint32_t)q.kc * (1024u + (uint32_t)std::max(Wn[TW_WP], Wn[TW_OP]) * 8u) <= q.slot_bytes, "pmc_flow_sweep_tri: init chunk exceeds a ring slot");
+    if (w > 0) PMC_REQUIRE((uint32_t)q.kc * (1024u + (uint32_t)Wn[TW_WP] * 8u) <= q.slot_bytes && (uint32_t)q.kc_out * (1024u + (uint32_t)Wn[TW_OP] * 8u) <= q.slot_bytes,
+                           "pmc_flow_sweep_tri: init chunk exceeds a ring slot");
   }
   PMC_REQUIRE(q.stages >= 2 && q.stages <= TRI_MAX_STAGES, "pmc_flow_sweep_tri: bad ring depth");
   // a window initialisation borrows the A-tile area (3 layers x hi / lo + the x tile: idle between the last update of a

@@ -41,10 +41,10 @@ from .made_layout import KIND_AFFINE, KIND_RQS, TC_BIAS_FLAG, build_layout
 
 TRI_G = 4
 TRI_KC = 16               # K extent of one init chunk (A from the scratch area + B weights); 8 when 16 leaves < 4 ring slots
-TRI_VERSION = 301
+TRI_VERSION = 302
 (TRI_VER, TRI_D, TRI_H, TRI_L, TRI_T, TRI_GSIZE, TRI_NB, TRI_NW, TRI_TSTRIDE, TRI_KCHUNK, TRI_SLOT_BYTES, TRI_DSLOT_BYTES,
  TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_OFF_BLOCKS, TRI_OFF_WINDOWS, TRI_SMEM_BYTES,
- TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND, TRI_HEADER) = range(24)
+ TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND, TRI_KCHUNK_OUT, TRI_HEADER) = range(25)
 # per block
 (TB_K0, TB_NST, TB_NR, TB_W, TB_KP, TB_WIN, TB_WC, TB_OC, TB_DOFF, TB_DN, TB_KS, TB_UPD_N, TB_UPD_DCOL, TB_OUT_N, TB_OUT_DCOL,
  TB_FLAGS, TB_FIELDS) = range(17)
@@ -200,8 +200,11 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
     dslot_bytes = _r(max(tri_diag_floats(G, b["NR"], kind) for b in blocks) * 4, 1024)
     tile_bytes = max(b["Kp"] for b in blocks) * 512
     fixed = L * 2 * tile_bytes + 2 * 4096 + 2 * dslot_bytes + TRI_STATIC_SMEM
-    for KC in ((TRI_KC,) if kind == KIND_AFFINE else (TRI_KC, 8)):       # affine flows keep K = 16 chunks (fewer hand-offs per window)
-        max_init = max([KC * (1024 + max(w["Wp"], w["Op"]) * 8) for w in windows[1:]], default=0)
+    # K extent of an init chunk for the hidden layers (KC) and for the outputs (KCO): a chunk is [A: 128 rows x K fp32 | B: N x K
+    # hi + lo]; spline flows have wide output slabs (N = 192), so their output chunks are shorter than their hidden ones.
+    # Every chunk costs one hand-off between producer, splitting threads and issuer: take the longest that leaves >= 4 slots.
+    for KC, KCO in (((TRI_KC, TRI_KC),) if kind == KIND_AFFINE else ((32, 16), (16, 16), (16, 8), (8, 8))):
+        max_init = max([max(KC * (1024 + w["Wp"] * 8), KCO * (1024 + w["Op"] * 8)) for w in windows[1:]], default=0)
         slot_bytes = _r(max(max_upd, max_init, 1024), 1024)
         stages = min(TRI_MAX_STAGES, (TRI_SMEM_BUDGET - fixed) // slot_bytes)
         if stages >= 4:
@@ -375,8 +378,9 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
                     ktot = nw["Kx"] if op == 1 else nw["Kh"]
                     idx = b_matrix(op, hcols if op < 4 else ocols, src_units=hslot_unit[:ktot], src_orders=xslot_order[:ktot],
                                    col_unit=ncol_unit, out_row=nout_row)
-                    for k_ in range(0, ktot, KC):
-                        for img in k_major(idx[:, k_:min(k_ + KC, ktot)]):
+                    kc_ = KC if op < 4 else KCO
+                    for k_ in range(0, ktot, kc_):
+                        for img in k_major(idx[:, k_:min(k_ + kc_, ktot)]):
                             parts.append(img)
                             off += len(img)
         return np.concatenate(parts), diag_tab, chunk_off
@@ -404,9 +408,9 @@ def build_tri(n_dim: int, n_hidden: int, n_layers: int, n_transforms: int, kind:
         win_rows[wi] = [w["b0"], w["nb"], w["Wp"], w["Op"], w["col_out"], w["Kh"], w["Kx"], 0]
     meta = np.zeros(TRI_HEADER, np.int64)
     meta[[TRI_VER, TRI_D, TRI_H, TRI_L, TRI_T, TRI_GSIZE, TRI_NB, TRI_NW, TRI_TSTRIDE, TRI_KCHUNK, TRI_SLOT_BYTES, TRI_DSLOT_BYTES,
-          TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_SMEM_BYTES, TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND]] = \
+          TRI_TILE_BYTES, TRI_NSTAGES, TRI_KH_TOTAL, TRI_KX_TOTAL, TRI_WS_FLOATS, TRI_SMEM_BYTES, TRI_NCOLS, TRI_CHUNK_OFF, TRI_KIND, TRI_KCHUNK_OUT]] = \
         [TRI_VERSION, D, H, L, T, G, NB, NW, tstride, KC, slot_bytes, dslot_bytes, tile_bytes, stages, kh_total, kx_total, ws_floats,
-         smem, ncols, chunk_off, kind]
+         smem, ncols, chunk_off, kind, KCO]
     meta[TRI_OFF_BLOCKS] = TRI_HEADER
     meta[TRI_OFF_WINDOWS] = TRI_HEADER + block_rows.size
     meta = np.concatenate([meta, block_rows.reshape(-1), win_rows.reshape(-1)])

@@ -350,8 +350,9 @@ def sweep_tri(tri, packed, x, inverse, passes=3):
                 for op in (1, 2, 3, 4):
                     ktot = nKx if op == 1 else nKh
                     N, dcol = (nWp, (op - 1) * nWp) if op < 4 else (nOp, ncol_out)
-                    for k_ in range(0, ktot, KC):
-                        ke = min(KC, ktot - k_)
+                    kc_ = KC if op < 4 else int(m[TL.TRI_KCHUNK_OUT])
+                    for k_ in range(0, ktot, kc_):
+                        ke = min(kc_, ktot - k_)
                         A = scratch[op - 1][:, k_:k_ + ke]
                         Bh, Bl = take_b(N, ke)
                         Dm = mma(A, Bh, Bl)
