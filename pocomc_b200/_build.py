@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIBPATH = os.path.join(LIBDIR, "libpmc_b200.so")
+LIBPATH = os.environ.get("PMC_B200_LIBPATH") or os.path.join(LIBDIR, "libpmc_b200.so")     # override: diagnostic builds (tests/nsf_truth.py)
 SOURCES = ["lib.cu", "flow_sweep.cu", "mcmc_ops.cu", "smc_ops.cu", "train_ops.cu", "flow_tc.cu", "flow_train.cu", "flow_tri.cu", "geom_ops.cu", "flow_train_lw.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
@@ -30,11 +30,13 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=""):
+    """Build the library (in-tree path, or LIBPATH's override).  `defines` / `tag`: a diagnostic variant with extra -D flags,
+    objects under build/obj<tag>/ (e.g. -DPMC_TRI_RQS_REFERENCE_HEAD: the spline head in the reference's operation order)."""
     if not force and not needs_build():
         return LIBPATH
-    os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "..", "build", "obj")
+    os.makedirs(os.path.dirname(LIBPATH), exist_ok=True)
+    objdir = os.path.join(HERE, "..", "build", "obj" + tag)
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     procs = []
@@ -45,7 +47,7 @@ def build(force=False, verbose=False):
             continue
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

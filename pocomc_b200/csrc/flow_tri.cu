@@ -267,7 +267,11 @@ __device__ __forceinline__ float rqs_head(const float4* __restrict__ q, int& off
   float phi[24];
 #pragma unroll
   for (int i = 0; i < 12; ++i) { phi[2 * i] = ph[i].x; phi[2 * i + 1] = ph[i].y; }
+#ifdef PMC_TRI_RQS_REFERENCE_HEAD
+  return Rqs::apply(phi, v, INV, lj);            // diagnostic build: the reference's operation order (tests/nsf_truth.py)
+#else
   return RqsLean::apply<INV>(phi, v, lj);
+#endif
 }
 
 // order position J of a block: output -> affine map / spline -> the degree group's three hidden layers
