@@ -65,8 +65,9 @@ int pmc_flow_forward_tc(const float* packed, const int32_t* meta_host, int32_t m
                         pmc_stream_t stream);
 
 /* ---- tensor-core (tcgen05) block-triangular sweep: Flow.inverse (flow.py:116-132 -> zuko
- * transform.inv.call_and_ladj, the hot call of pocomc/mcmc.py:88,256) and Flow.forward of affine flows
- * of any preset width (D = 8 .. 200, H = 32 .. 1024).
+ * transform.inv.call_and_ladj, the hot call of pocomc/mcmc.py:88,256) and Flow.forward of affine (zuko MAF,
+ * flow.py:54-63) and 8-bin spline (zuko NSF, flow.py:65-86: the reference's default presets) flows of any preset
+ * width (D = 8 .. 200, H = 32 .. 1024); the table's TRI_KIND field selects the univariate head.
  * Order positions are processed in blocks of 4, blocks in windows whose per-unit accumulators fit tensor
  * memory: the dense dependence on earlier blocks runs as tcgen05.mma (right-looking updates inside a
  * window, a left-looking initialisation from a scratch area when a window starts; 3xTF32 split,
