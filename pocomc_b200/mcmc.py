@@ -2,9 +2,10 @@
 ``preconditioned_pcn`` (8-183), ``preconditioned_rwm`` (186-341), ``pcn`` (344-506), ``rwm``
 (508-654).  One implementation drives all four: the particle state stays on the GPU for the whole
 call, every step is a short chain of libpmc_b200 kernels
-(noise -> proposal -> flow pull-back -> reparameterisation -> [host prior / likelihood] ->
-Metropolis update -> scalar adaptation), and only x' / logp' / logl' cross the PCIe bus because the
-user's log_likelihood is a host-side black box.
+(noise -> proposal -> flow pull-back -> reparameterisation [+ device prior, same launch] -> [host prior / likelihood] ->
+Metropolis update + scalar adaptation, one launch), each a programmatic dependent launch of its predecessor, and only
+x' / logp' / logl' cross the PCIe bus because the user's log_likelihood is a host-side black box (x' through pinned memory, in
+row chunks for large clouds: config.host_chunks).
 """
 from __future__ import annotations
 
